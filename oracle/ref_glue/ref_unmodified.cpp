@@ -1,0 +1,128 @@
+// TEST INFRASTRUCTURE — not part of the product.
+//
+// Builds the UNMODIFIED reference (SmallVCM, /root/reference/src, compiled in place
+// with -I, nothing copied) into oracle/_ref/libsvcm_ref.so behind a small C interface,
+// because the BASELINE configurations (resolution, path length, radius, thread count)
+// have no command-line switch in the reference (src/config.hxx:233-240).
+//
+// Uses: (1) pins oracle/vcm_oracle.cpp against the reference's own output
+// (tests/test_oracle_pin.py), (2) regenerates tests/golden/*, (3) is the
+// `--impl reference` / cpu_baseline arm of bench.py (the reference's own OpenMP path,
+// src/smallvcm.cxx:52-151, timed with a wall clock because render() returns CPU time).
+//
+// The reference headers define non-inline functions, so they can only be included into
+// ONE translation unit: this file is that TU for this library.
+#include <vector>
+#include <cmath>
+#include <cstring>
+#include <cstdio>
+#include <algorithm>
+#include <chrono>
+
+#define main smallvcm_reference_main
+#include "smallvcm.cxx"
+#undef main
+
+#include "svcm.h"
+#include "../../smallvcm_b200/host/flatten_scene.hxx"
+
+#define REF_API extern "C" __attribute__((visibility("default")))
+
+// Number of built-in scene configurations (src/config.hxx:146-151).
+REF_API int ref_scene_count() { return SizeOfArray(g_SceneConfigs); }
+
+REF_API unsigned ref_scene_mask(int sceneId)
+{
+    if(sceneId < 0 || sceneId >= SizeOfArray(g_SceneConfigs)) return 0;
+    return g_SceneConfigs[sceneId];
+}
+
+REF_API int ref_num_procs() { return omp_get_num_procs(); }
+
+// Runs the reference's own render() (src/smallvcm.cxx:52) on a programmatically filled
+// Config. `algorithm` is Config::Algorithm (0 el, 1 pt, 2 lt, 3 ppm, 4 bpm, 5 bpt, 6 vcm).
+// Writes W*H*3 floats (the averaged framebuffer render() produces) and returns the
+// WALL seconds spent inside render(), or a negative value on error.
+REF_API double ref_render(int sceneId, int algorithm, int width, int height,
+                          int iterations, int threads, int baseSeed,
+                          unsigned maxPathLength, unsigned minPathLength,
+                          float radiusFactor, float radiusAlpha, float *outRgb)
+{
+    if(sceneId < 0 || sceneId >= SizeOfArray(g_SceneConfigs)) return -1.0;
+    if(algorithm < 0 || algorithm >= (int)Config::kAlgorithmMax) return -1.0;
+
+    Scene *scene = new Scene;
+    scene->LoadCornellBox(Vec2i(width, height), g_SceneConfigs[sceneId]);
+    scene->BuildSceneSphere();
+
+    Framebuffer fb;
+    Config config;
+    config.mScene         = scene;
+    config.mAlgorithm     = Config::Algorithm(algorithm);
+    config.mIterations    = iterations;
+    config.mMaxTime       = -1.f;
+    config.mRadiusFactor  = radiusFactor;
+    config.mRadiusAlpha   = radiusAlpha;
+    config.mFramebuffer   = &fb;
+    config.mNumThreads    = threads > 0 ? threads : std::max(1, omp_get_num_procs());
+    config.mBaseSeed      = baseSeed;
+    config.mMaxPathLength = maxPathLength;
+    config.mMinPathLength = minPathLength;
+    config.mOutputName    = "";
+    config.mResolution    = Vec2i(width, height);
+    config.mFullReport    = false;
+
+    const auto t0 = std::chrono::steady_clock::now();
+    render(config);
+    const auto t1 = std::chrono::steady_clock::now();
+
+    if(outRgb)
+    {
+        // Framebuffer::mColor is private; this TU is compiled with -fno-access-control
+        memcpy(outRgb, &fb.mColor[0], sizeof(float) * 3 * size_t(width) * size_t(height));
+    }
+
+    delete scene;
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// Framebuffer::TotalLuminance (src/framebuffer.hxx:89) of an image, float accumulation
+// in the reference's pixel order — the KAT scalar of BASELINE.md §3.
+REF_API float ref_total_luminance(const float *rgb, int width, int height)
+{
+    Framebuffer fb;
+    fb.Setup(Vec2f(float(width), float(height)));
+    memcpy(&fb.mColor[0], rgb, sizeof(float) * 3 * size_t(width) * size_t(height));
+    return fb.TotalLuminance();
+}
+
+// Flattens the reference's own Scene for `sceneId` with the product's host glue
+// (smallvcm_b200/host/flatten_scene.hxx) into caller-provided arrays; used to check the
+// library's built-in scene builder (svcm_scene_cornell_box) field by field.
+REF_API int ref_flatten_scene(int sceneId, int width, int height,
+                              SvcmPrimitive *prims, int *numPrims,
+                              SvcmMaterial *mats, int *numMats,
+                              SvcmLight *lights, int *numLights,
+                              int *materialToLight, int *backgroundLight,
+                              SvcmCamera *camera, SvcmSceneSphere *sphere)
+{
+    if(sceneId < 0 || sceneId >= SizeOfArray(g_SceneConfigs)) return -1;
+    Scene scene;
+    scene.LoadCornellBox(Vec2i(width, height), g_SceneConfigs[sceneId]);
+    scene.BuildSceneSphere();
+
+    svcm_host::FlatScene flat;
+    if(!svcm_host::FlattenScene(scene, flat)) return -2;
+
+    *numPrims  = (int)flat.primitives.size();
+    *numMats   = (int)flat.materials.size();
+    *numLights = (int)flat.lights.size();
+    memcpy(prims,  flat.primitives.data(), sizeof(SvcmPrimitive) * flat.primitives.size());
+    memcpy(mats,   flat.materials.data(),  sizeof(SvcmMaterial)  * flat.materials.size());
+    memcpy(lights, flat.lights.data(),     sizeof(SvcmLight)     * flat.lights.size());
+    memcpy(materialToLight, flat.materialToLight.data(), sizeof(int) * flat.materialToLight.size());
+    *backgroundLight = flat.desc.backgroundLight;
+    *camera = flat.desc.camera;
+    *sphere = flat.desc.sceneSphere;
+    return 0;
+}
