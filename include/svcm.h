@@ -53,12 +53,14 @@ enum {
 };
 
 /* ----------------------------------------------------------------------------------
- * compiled-in scene limits (the whole scene lives in __constant__ memory; a spatial
- * acceleration structure is SURVEY §8(f) rank 2, not part of this path)
+ * compiled-in scene limits: the whole scene travels to every kernel as a __grid_constant__
+ * parameter (constant bank, ~5 KB), so concurrent handles with different scenes never
+ * share state. The reference's scenes hold <= 22 primitives, 9 materials, 2 lights. A
+ * spatial acceleration structure for bigger scenes is SURVEY §8(f) rank 2, not this path.
  * -------------------------------------------------------------------------------- */
-#define SVCM_MAX_PRIMITIVES 256
-#define SVCM_MAX_MATERIALS  64
-#define SVCM_MAX_LIGHTS     16
+#define SVCM_MAX_PRIMITIVES 64
+#define SVCM_MAX_MATERIALS  16
+#define SVCM_MAX_LIGHTS     8
 
 /* ----------------------------------------------------------------------------------
  * flattened scene (replaces the pointer graph of reference src/scene.hxx:474-485)
@@ -160,11 +162,11 @@ typedef struct SvcmParams {
     int32_t device;         /* CUDA device ordinal this handle runs on                 */
     /* Path sharding for one-process-per-GPU runs.  Path index p (= pixel
      * index = light sub-path index, src/vertexcm.hxx:321,415,504-506) is owned by the
-     * rank  (p / shardRows-of-pixels-rows) — see DESIGN.md "sharding"; with
+     * rank (p / width) % worldSize (svcm_shard_owner below; DESIGN.md "sharding"); with
      * worldSize == 1 the handle owns every path. */
     int32_t rank;
     int32_t worldSize;
-    int32_t reserved[5];
+    int32_t reserved[5];    /* must be zero */
 } SvcmParams;
 
 /* Per-iteration workload counters and device timings of the LAST completed iteration;
@@ -250,6 +252,21 @@ SVCM_API int svcm_clear_accum(svcm_renderer *r);
 
 SVCM_API int svcm_get_stats(svcm_renderer *r, SvcmStats *out);
 
+/* Page-locks / releases caller memory (cudaHostRegister) so that svcm_download_accum into it
+ * runs at DMA speed; optional. svcm_device_count returns the number of CUDA devices (0 if
+ * none or no driver). */
+SVCM_API int svcm_host_register(void *ptr, size_t bytes);
+SVCM_API int svcm_host_unregister(void *ptr);
+SVCM_API int svcm_device_count(void);
+
+/* CUDA-event timing on the handle's own stream (the library launches on a private
+ * non-blocking stream, so events recorded elsewhere do not see its kernels):
+ * svcm_event_record enqueues event `slot` (0..7) behind everything submitted so far;
+ * svcm_event_elapsed_ms waits for both events and returns the device time between them. */
+#define SVCM_NUM_USER_EVENTS 8
+SVCM_API int svcm_event_record(svcm_renderer *r, int32_t slot);
+SVCM_API int svcm_event_elapsed_ms(svcm_renderer *r, int32_t startSlot, int32_t stopSlot, float *ms);
+
 /* ----------------------------------------------------------------------------------
  * multi-GPU (one process per GPU; no counterpart in the reference)
  * -------------------------------------------------------------------------------- */
@@ -264,6 +281,18 @@ SVCM_API int svcm_comm_init(svcm_renderer *r, const uint8_t id[SVCM_COMM_ID_BYTE
 /* Sums the accumulated images of all ranks into rank `root`'s image (ncclReduce). After
  * it, svcm_download_accum on `root` returns the whole image. */
 SVCM_API int svcm_reduce_accum(svcm_renderer *r, int32_t root);
+
+/* The path -> rank map of a sharded run (host code, no GPU needed): image rows are dealt
+ * round-robin, rank = (path / width) % worldSize; both sub-paths of an index live on the
+ * same rank (vertex connection pairs them, src/vertexcm.hxx:504-506).
+ *   svcm_shard_local_paths : number of paths rank owns
+ *   svcm_shard_owner       : owning rank of global path index `path`
+ *   svcm_shard_local_index : index of `path` inside its owner's local numbering
+ *   svcm_shard_global_index: inverse of the above for (rank, local) */
+SVCM_API int64_t svcm_shard_local_paths(int32_t width, int32_t height, int32_t rank, int32_t worldSize);
+SVCM_API int32_t svcm_shard_owner(int32_t width, int32_t worldSize, int64_t path);
+SVCM_API int64_t svcm_shard_local_index(int32_t width, int32_t worldSize, int64_t path);
+SVCM_API int64_t svcm_shard_global_index(int32_t width, int32_t rank, int32_t worldSize, int64_t local);
 
 /* ----------------------------------------------------------------------------------
  * kernel-level entry points (the stages of the path, callable on their own; used by

@@ -8,7 +8,7 @@ the sizes the library itself reports.
 import ctypes as C
 
 # --- limits / enums (include/svcm.h) -------------------------------------------------------
-MAX_PRIMITIVES, MAX_MATERIALS, MAX_LIGHTS = 256, 64, 16
+MAX_PRIMITIVES, MAX_MATERIALS, MAX_LIGHTS = 64, 16, 8
 PRIM_TRIANGLE, PRIM_SPHERE = 0, 1
 LIGHT_AREA, LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_BACKGROUND = 0, 1, 2, 3
 # VertexCM::AlgorithmType numbering (reference src/vertexcm.hxx:182-204)
@@ -108,6 +108,15 @@ PROTOTYPES = {
     "svcm_download_accum": (i32, [VP, VP, C.POINTER(i32)]),
     "svcm_clear_accum": (i32, [VP]),
     "svcm_get_stats": (i32, [VP, C.POINTER(Stats)]),
+    "svcm_host_register": (i32, [VP, C.c_size_t]),
+    "svcm_host_unregister": (i32, [VP]),
+    "svcm_device_count": (i32, []),
+    "svcm_event_record": (i32, [VP, i32]),
+    "svcm_event_elapsed_ms": (i32, [VP, i32, i32, C.POINTER(f32)]),
+    "svcm_shard_local_paths": (i64, [i32, i32, i32, i32]),
+    "svcm_shard_owner": (i32, [i32, i32, i64]),
+    "svcm_shard_local_index": (i64, [i32, i32, i64]),
+    "svcm_shard_global_index": (i64, [i32, i32, i32, i64]),
     "svcm_comm_unique_id": (i32, [VP]),
     "svcm_comm_init": (i32, [VP, VP]),
     "svcm_reduce_accum": (i32, [VP, i32]),

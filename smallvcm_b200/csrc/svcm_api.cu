@@ -1,0 +1,1163 @@
+// svcm_api.cu — host side of the C-ABI (include/svcm.h): handle life cycle, the per-iteration
+// kernel schedule that replaces VertexCM::RunIteration (reference src/vertexcm.hxx:284-548),
+// the NCCL all-gather of light vertices for pixel-sharded multi-GPU runs, and the kernel-level
+// entry points. No reference types, no torch types, no CPU fallback: every entry point that
+// computes needs a CUDA device and says so loudly if there is none.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdint.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <algorithm>
+#include <string>
+#include <vector>
+#include <mutex>
+#include "svcm.h"
+#include "svcm_internal.h"
+
+using namespace svcm;
+
+// ------------------------------------------------------------------------------------------
+// NCCL, resolved at run time (the process may already carry torch's libnccl.so.2; linking a
+// second copy at build time would be wrong). Minimal declarations of the stable C API.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { NCCL_SUCCESS = 0 };
+enum { NCCL_UINT8 = 1, NCCL_INT32 = 2, NCCL_UINT32 = 3, NCCL_FLOAT32 = 7 };
+enum { NCCL_SUM = 0 };
+
+struct NcclApi
+{
+    void *lib;
+    int (*GetUniqueId)(ncclUniqueId *);
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    int (*CommDestroy)(ncclComm_t);
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t);
+    int (*Reduce)(const void *, void *, size_t, int, int, int, ncclComm_t, cudaStream_t);
+    int (*GroupStart)();
+    int (*GroupEnd)();
+    const char *(*GetErrorString)(int);
+    std::string error;
+};
+
+NcclApi *ncclApi()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        const char *names[] = { getenv("SVCM_NCCL_LIB"), "libnccl.so.2", "libnccl.so", NULL };
+        api.lib = NULL;
+        for(int i = 0; i < 3 && !api.lib; i++)
+            if(names[i] && names[i][0]) api.lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+        if(!api.lib) { api.error = std::string("cannot load NCCL: ") + (dlerror() ? dlerror() : "?"); return; }
+#define SVCM_NCCL_SYM(field, name) \
+        *(void**)(&api.field) = dlsym(api.lib, name); \
+        if(!api.field) { api.error = std::string("NCCL symbol missing: ") + name; api.lib = NULL; return; }
+        SVCM_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+        SVCM_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+        SVCM_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+        SVCM_NCCL_SYM(AllGather, "ncclAllGather")
+        SVCM_NCCL_SYM(Reduce, "ncclReduce")
+        SVCM_NCCL_SYM(GroupStart, "ncclGroupStart")
+        SVCM_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+        SVCM_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef SVCM_NCCL_SYM
+    });
+    return &api;
+}
+
+thread_local std::string t_createError;
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------
+// the renderer handle
+// ------------------------------------------------------------------------------------------
+struct svcm_renderer
+{
+    SvcmParams params;
+    DevScene   scene;
+    int        device;
+    cudaStream_t stream;
+    bool useVC, useVM, ppm, lightTraceOnly;
+    int  resX, resY;
+    uint32_t paths, localPaths, localRows;
+    float baseRadius;
+
+    // device buffers
+    PathQueue queue[2];
+    uint32_t *queueCountsLight, *queueCountsCamera;   // [countsAlloc]
+    uint32_t  countsAlloc;
+    VertexStore verts;
+    uint32_t  vertSlots;            // rows of verts.pathVerts
+    uint8_t  *pathVertCount;
+    QueryStore queries;
+    unsigned long long *counters;   // CNT_WORDS
+    unsigned long long *hostCounters; // pinned mirror of the last iteration
+    float    *accum;
+    GridBuffers grid;
+    uint32_t  gridCells, gridCapacity;
+    int32_t  *bboxInit;
+    // multi-rank
+    ncclComm_t comm;
+    float4 *gPosLen, *gThrVcm, *gDirVm; float *gContProb;   // gathered records
+    uint32_t gatherCapacity;        // records per gathered stream
+    uint32_t *devCounts;            // [worldSize] per-rank vertex counts (device)
+    uint32_t *hostCounts;           // pinned
+
+    int  iterationsDone;
+    int  mergeGroup;
+    bool profile;
+    cudaEvent_t ev[6];
+    cudaEvent_t userEv[SVCM_NUM_USER_EVENTS];
+    bool evValid;
+    SvcmStats stats;
+    bool statsPending;
+    int  lastLaunches;
+    std::string error;
+
+    svcm_renderer() { memset(&params, 0, sizeof(params)); memset(&scene, 0, sizeof(scene)); }
+};
+
+namespace {
+
+int fail(svcm_renderer *r, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    if(r) r->error = buf; else t_createError = buf;
+    return code;
+}
+
+#define SVCM_CUDA(r, call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) \
+    return fail(r, e_ == cudaErrorMemoryAllocation ? SVCM_E_NOMEM : SVCM_E_CUDA, "%s failed: %s (%s:%d)", #call, \
+                cudaGetErrorString(e_), __FILE__, __LINE__); } while(0)
+
+int checkDevice(svcm_renderer *r, int device)
+{
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if(e != cudaSuccess || n <= 0)
+        return fail(r, SVCM_E_NO_DEVICE, "no CUDA device available (%s); this library has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if(device < 0 || device >= n) return fail(r, SVCM_E_INVALID, "device %d out of range (have %d)", device, n);
+    return SVCM_OK;
+}
+
+// flat scene -> the kernels' constant block; validates every limit and index
+int buildDevScene(svcm_renderer *r, const SvcmSceneDesc *d, DevScene &s)
+{
+    if(!d) return fail(r, SVCM_E_INVALID, "scene is NULL");
+    if(d->numPrimitives < 0 || d->numPrimitives > SVCM_MAX_PRIMITIVES ||
+       d->numMaterials < 1 || d->numMaterials > SVCM_MAX_MATERIALS ||
+       d->numLights < 1 || d->numLights > SVCM_MAX_LIGHTS)
+        return fail(r, SVCM_E_INVALID, "scene exceeds limits: %d primitives (max %d), %d materials (1..%d), %d lights (1..%d)",
+                    d->numPrimitives, SVCM_MAX_PRIMITIVES, d->numMaterials, SVCM_MAX_MATERIALS,
+                    d->numLights, SVCM_MAX_LIGHTS);
+    if((d->numPrimitives && !d->primitives) || !d->materials || !d->lights || !d->materialToLight)
+        return fail(r, SVCM_E_INVALID, "scene arrays must not be NULL");
+    memset(&s, 0, sizeof(s));
+    s.numPrims = d->numPrimitives; s.numMats = d->numMaterials; s.numLights = d->numLights;
+    s.background = d->backgroundLight;
+    if(s.background >= s.numLights) return fail(r, SVCM_E_INVALID, "backgroundLight out of range");
+    if(s.background >= 0 && d->lights[s.background].type != SVCM_LIGHT_BACKGROUND)
+        return fail(r, SVCM_E_INVALID, "backgroundLight does not index a background light");
+    for(int i = 0; i < 3; i++) { s.camPos[i] = d->camera.position[i]; s.camFwd[i] = d->camera.forward[i]; }
+    s.resX = d->camera.resolution[0]; s.resY = d->camera.resolution[1];
+    memcpy(s.rasterToWorld, d->camera.rasterToWorld, sizeof(float) * 16);
+    memcpy(s.worldToRaster, d->camera.worldToRaster, sizeof(float) * 16);
+    s.imagePlaneDist = d->camera.imagePlaneDist;
+    for(int i = 0; i < 3; i++) s.sphereCenter[i] = d->sceneSphere.center[i];
+    s.sphereRadius = d->sceneSphere.radius;
+    s.sphereInvRadiusSqr = d->sceneSphere.invRadiusSqr;
+    for(int i = 0; i < d->numMaterials; i++)
+    {
+        s.mats[i] = d->materials[i];
+        s.matToLight[i] = d->materialToLight[i];
+        if(s.matToLight[i] >= d->numLights) return fail(r, SVCM_E_INVALID, "materialToLight[%d] out of range", i);
+    }
+    for(int i = 0; i < d->numPrimitives; i++)
+    {
+        const SvcmPrimitive &p = d->primitives[i];
+        if(p.type != SVCM_PRIM_TRIANGLE && p.type != SVCM_PRIM_SPHERE)
+            return fail(r, SVCM_E_INVALID, "primitive %d has unknown type %d", i, p.type);
+        if(p.matID < 0 || p.matID >= d->numMaterials)
+            return fail(r, SVCM_E_INVALID, "primitive %d has material %d out of range", i, p.matID);
+        memcpy(s.prims[i].v, p.v, sizeof(float) * 12);
+        s.prims[i].type = p.type; s.prims[i].matID = p.matID;
+    }
+    for(int i = 0; i < d->numLights; i++)
+    {
+        const SvcmLight &l = d->lights[i];
+        if(l.type < SVCM_LIGHT_AREA || l.type > SVCM_LIGHT_BACKGROUND)
+            return fail(r, SVCM_E_INVALID, "light %d has unknown type %d", i, l.type);
+        DevLight &o = s.lights[i];
+        o.type = l.type;
+        memcpy(o.p0, l.p0, 12); memcpy(o.e1, l.e1, 12); memcpy(o.e2, l.e2, 12);
+        memcpy(o.fx, l.frameX, 12); memcpy(o.fy, l.frameY, 12); memcpy(o.fz, l.frameZ, 12);
+        memcpy(o.intensity, l.intensity, 12);
+        if(l.type == SVCM_LIGHT_BACKGROUND)   // radiance = mBackgroundColor * mScale (src/lights.hxx:424)
+            for(int k = 0; k < 3; k++) o.intensity[k] = l.intensity[k] * l.scale;
+        o.invArea = l.invArea;
+    }
+    return SVCM_OK;
+}
+
+template<typename T> int devAlloc(svcm_renderer *r, T **p, size_t count)
+{
+    *p = NULL;
+    if(count == 0) count = 1;
+    SVCM_CUDA(r, cudaMalloc((void**)p, sizeof(T) * count));
+    return SVCM_OK;
+}
+template<typename T> void devFree(T *&p) { if(p) cudaFree(p); p = NULL; }
+
+int allocQueue(svcm_renderer *r, PathQueue &q, size_t n)
+{
+    int rc;
+    if((rc = devAlloc(r, &q.s0, n))) return rc;
+    if((rc = devAlloc(r, &q.s1, n))) return rc;
+    if((rc = devAlloc(r, &q.s2, n))) return rc;
+    if((rc = devAlloc(r, &q.s3, n))) return rc;
+    return SVCM_OK;
+}
+void freeQueue(PathQueue &q) { devFree(q.s0); devFree(q.s1); devFree(q.s2); devFree(q.s3); }
+
+void freeVerts(svcm_renderer *r)
+{
+    devFree(r->verts.posLen); devFree(r->verts.thrVcm); devFree(r->verts.dirVm); devFree(r->verts.contProb);
+    devFree(r->verts.nrmVc); devFree(r->verts.ldfMat); devFree(r->verts.pathVerts);
+    r->verts.capacity = 0; r->vertSlots = 0;
+}
+void freeQueries(svcm_renderer *r)
+{
+    devFree(r->queries.q0); devFree(r->queries.q1); devFree(r->queries.q2); devFree(r->queries.q3);
+    r->queries.capacity = 0;
+}
+void freeGridSorted(svcm_renderer *r)
+{
+    devFree(r->grid.cellKey); devFree(r->grid.sPosLen); devFree(r->grid.sThrVcm); devFree(r->grid.sDirVm);
+    devFree(r->grid.sContProb); devFree(r->grid.sIndex);
+    r->gridCapacity = 0;
+}
+void freeGather(svcm_renderer *r)
+{
+    devFree(r->gPosLen); devFree(r->gThrVcm); devFree(r->gDirVm); devFree(r->gContProb);
+    r->gatherCapacity = 0;
+}
+
+int ensureGridSorted(svcm_renderer *r, uint32_t capacity)
+{
+    if(capacity <= r->gridCapacity) return SVCM_OK;
+    freeGridSorted(r);
+    int rc;
+    if((rc = devAlloc(r, &r->grid.cellKey, capacity))) return rc;
+    if((rc = devAlloc(r, &r->grid.sPosLen, capacity))) return rc;
+    if((rc = devAlloc(r, &r->grid.sThrVcm, capacity))) return rc;
+    if((rc = devAlloc(r, &r->grid.sDirVm, capacity))) return rc;
+    if((rc = devAlloc(r, &r->grid.sContProb, capacity))) return rc;
+    if((rc = devAlloc(r, &r->grid.sIndex, capacity))) return rc;
+    r->gridCapacity = capacity;
+    return SVCM_OK;
+}
+
+int ensureGridCells(svcm_renderer *r, uint32_t numCells)
+{
+    if(numCells == r->gridCells) return SVCM_OK;
+    devFree(r->grid.cellCount); devFree(r->grid.blockSums);
+    int rc;
+    if((rc = devAlloc(r, &r->grid.cellCount, size_t(numCells) + 1))) return rc;
+    if((rc = devAlloc(r, &r->grid.blockSums, (size_t(numCells) + 1) / 2048 + 2))) return rc;
+    r->gridCells = numCells;
+    return SVCM_OK;
+}
+
+// Sizes everything that depends on the path-length limit. Worst case is one stored vertex
+// per light bounce and one query per camera bounce; if that does not fit comfortably the
+// stores are bounded and an overflow is reported as an error at the next synchronisation.
+int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
+{
+    const uint32_t lightBounces = std::max(1u, maxLen > 0 ? maxLen - 1u : 0u);
+    const uint32_t camBounces = std::max(1u, maxLen);
+    if(lightBounces > 255u) return fail(r, SVCM_E_INVALID, "maxPathLength %u too large (max 256)", maxLen);
+    int rc;
+
+    const uint32_t needCounts = camBounces + 3u;
+    if(needCounts > r->countsAlloc)
+    {
+        devFree(r->queueCountsLight); devFree(r->queueCountsCamera);
+        if((rc = devAlloc(r, &r->queueCountsLight, needCounts))) return rc;
+        if((rc = devAlloc(r, &r->queueCountsCamera, needCounts))) return rc;
+        r->countsAlloc = needCounts;
+    }
+
+    size_t freeB = 0, totalB = 0;
+    cudaMemGetInfo(&freeB, &totalB);
+
+    const bool needVerts = r->useVC || r->useVM;
+    if(needVerts && (r->vertSlots < lightBounces || r->verts.capacity == 0))
+    {
+        freeVerts(r);
+        freeGridSorted(r);
+        cudaMemGetInfo(&freeB, &totalB);
+        const uint64_t worst = uint64_t(r->localPaths) * lightBounces;
+        // bytes per vertex: local record 84 + sorted copy/key (60, single rank only grows with it)
+        const uint64_t budget = uint64_t(double(freeB) * 0.45);
+        uint64_t cap = std::min<uint64_t>(worst, budget / 150u);
+        cap = std::min<uint64_t>(cap, 0xFFFFFF00u);
+        cap = std::max<uint64_t>(cap, std::min<uint64_t>(worst, uint64_t(r->localPaths)));
+        cap = (cap + 255u) & ~uint64_t(255u);
+        if((rc = devAlloc(r, &r->verts.posLen, cap))) return rc;
+        if((rc = devAlloc(r, &r->verts.thrVcm, cap))) return rc;
+        if((rc = devAlloc(r, &r->verts.dirVm, cap))) return rc;
+        if((rc = devAlloc(r, &r->verts.contProb, cap))) return rc;
+        if((rc = devAlloc(r, &r->verts.nrmVc, cap))) return rc;
+        if((rc = devAlloc(r, &r->verts.ldfMat, cap))) return rc;
+        if((rc = devAlloc(r, &r->verts.pathVerts, size_t(lightBounces) * r->localPaths))) return rc;
+        r->verts.capacity = uint32_t(cap);
+        r->vertSlots = lightBounces;
+        if(r->useVM && r->params.worldSize == 1)
+            if((rc = ensureGridSorted(r, r->verts.capacity))) return rc;
+    }
+
+    if(r->useVM)
+    {
+        const uint64_t worst = uint64_t(r->localPaths) * (r->ppm ? 1u : camBounces);
+        if(r->queries.capacity < worst)
+        {
+            const uint32_t old = r->queries.capacity;
+            freeQueries(r);
+            cudaMemGetInfo(&freeB, &totalB);
+            const uint64_t budget = uint64_t(double(freeB) * 0.5);
+            uint64_t cap = std::min<uint64_t>(worst, budget / 64u);
+            cap = std::min<uint64_t>(cap, 0xFFFFFF00u);
+            cap = std::max<uint64_t>(cap, old);
+            if((rc = devAlloc(r, &r->queries.q0, cap))) return rc;
+            if((rc = devAlloc(r, &r->queries.q1, cap))) return rc;
+            if((rc = devAlloc(r, &r->queries.q2, cap))) return rc;
+            if((rc = devAlloc(r, &r->queries.q3, cap))) return rc;
+            r->queries.capacity = uint32_t(cap);
+        }
+        if((rc = ensureGridCells(r, r->paths))) return rc;
+    }
+    return SVCM_OK;
+}
+
+// the scalars of reference src/vertexcm.hxx:288-308, computed on the host in the same order
+void iterationConstants(const svcm_renderer *r, int iteration, uint32_t minLen, uint32_t maxLen, IterConst &ic)
+{
+    memset(&ic, 0, sizeof(ic));
+    const float lightSubPathCount = float(r->resX * r->resY);
+    float radius = r->baseRadius;
+    radius /= std::pow(float(iteration + 1), 0.5f * (1 - r->params.radiusAlpha));
+    radius = std::max(radius, 1e-7f);
+    const float radiusSqr = radius * radius;
+    const float kPi = 3.14159265358979f;
+    ic.radius = radius;
+    ic.radiusSqr = radiusSqr;
+    ic.invCellSize = 1.f / (radius * 2.f);                       // src/hashgrid.hxx:47-48
+    ic.vmNormalization = 1.f / (radiusSqr * kPi * lightSubPathCount);
+    const float etaVCM = (kPi * radiusSqr) * lightSubPathCount;
+    ic.misVmWeightFactor = r->useVM ? etaVCM : 0.f;
+    ic.misVcWeightFactor = r->useVC ? 1.f / etaVCM : 0.f;
+    ic.lightSubPathCount = lightSubPathCount;
+    ic.minLen = minLen; ic.maxLen = maxLen;
+    ic.keyLight  = rngKey(r->params.seed, iteration, 0);
+    ic.keyCamera = rngKey(r->params.seed, iteration, 1);
+    ic.useVC = r->useVC; ic.useVM = r->useVM; ic.ppm = r->ppm; ic.lightTraceOnly = r->lightTraceOnly;
+    ic.resX = r->resX; ic.resY = r->resY;
+    ic.rank = r->params.rank; ic.worldSize = r->params.worldSize;
+    ic.localPaths = r->localPaths;
+    ic.numCells = r->paths;
+}
+
+int ncclCheck(svcm_renderer *r, int rc, const char *what)
+{
+    if(rc == NCCL_SUCCESS) return SVCM_OK;
+    return fail(r, SVCM_E_NCCL, "%s failed: %s", what, ncclApi()->GetErrorString ? ncclApi()->GetErrorString(rc) : "?");
+}
+
+// all-gather of the merge records of every rank's light vertices: exchange the
+// per-rank counts, then ONE NCCL group of four all-gathers padded to the largest count.
+int gatherLightVertices(svcm_renderer *r, MergeSet &set)
+{
+    NcclApi *n = ncclApi();
+    const int ws = r->params.worldSize;
+    if(!r->comm) return fail(r, SVCM_E_STATE, "worldSize %d but svcm_comm_init was not called", ws);
+
+    // own count -> device slot -> all ranks
+    SVCM_CUDA(r, cudaMemcpyAsync(r->hostCounts + 8, r->counters + CNT_LIGHT_VERTS, sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, r->stream));
+    SVCM_CUDA(r, cudaStreamSynchronize(r->stream));
+    unsigned long long mine64; memcpy(&mine64, r->hostCounts + 8, 8);
+    const uint32_t mine = uint32_t(std::min<unsigned long long>(mine64, r->verts.capacity));
+    r->hostCounts[r->params.rank] = mine;
+    SVCM_CUDA(r, cudaMemcpyAsync(r->devCounts + r->params.rank, r->hostCounts + r->params.rank, 4,
+                                 cudaMemcpyHostToDevice, r->stream));
+    int rc;
+    if((rc = ncclCheck(r, n->AllGather(r->devCounts + r->params.rank, r->devCounts, 1, NCCL_UINT32, r->comm, r->stream),
+                       "ncclAllGather(counts)"))) return rc;
+    SVCM_CUDA(r, cudaMemcpyAsync(r->hostCounts, r->devCounts, sizeof(uint32_t) * ws, cudaMemcpyDeviceToHost, r->stream));
+    SVCM_CUDA(r, cudaStreamSynchronize(r->stream));
+
+    uint32_t maxCount = 0;
+    for(int i = 0; i < ws; i++) maxCount = std::max(maxCount, r->hostCounts[i]);
+    const uint32_t stride = (maxCount + 255u) & ~255u;
+    if(stride > r->verts.capacity)
+        return fail(r, SVCM_E_STATE, "rank vertex count %u exceeds the local store (%u)", maxCount, r->verts.capacity);
+
+    const uint64_t need = uint64_t(stride) * ws;
+    if(need > r->gatherCapacity)
+    {
+        freeGather(r);
+        const uint64_t cap = need + need / 8;
+        if((rc = devAlloc(r, &r->gPosLen, cap))) return rc;
+        if((rc = devAlloc(r, &r->gThrVcm, cap))) return rc;
+        if((rc = devAlloc(r, &r->gDirVm, cap))) return rc;
+        if((rc = devAlloc(r, &r->gContProb, cap))) return rc;
+        r->gatherCapacity = uint32_t(std::min<uint64_t>(cap, 0xFFFFFFFFu));
+    }
+    if((rc = ensureGridSorted(r, uint32_t(need)))) return rc;
+
+    if(stride > 0)
+    {
+        if((rc = ncclCheck(r, n->GroupStart(), "ncclGroupStart"))) return rc;
+        n->AllGather(r->verts.posLen, r->gPosLen, size_t(stride) * 4, NCCL_FLOAT32, r->comm, r->stream);
+        n->AllGather(r->verts.thrVcm, r->gThrVcm, size_t(stride) * 4, NCCL_FLOAT32, r->comm, r->stream);
+        n->AllGather(r->verts.dirVm, r->gDirVm, size_t(stride) * 4, NCCL_FLOAT32, r->comm, r->stream);
+        n->AllGather(r->verts.contProb, r->gContProb, size_t(stride), NCCL_FLOAT32, r->comm, r->stream);
+        if((rc = ncclCheck(r, n->GroupEnd(), "ncclGroupEnd(all-gather light vertices)"))) return rc;
+    }
+
+    memset(&set, 0, sizeof(set));
+    set.posLen = r->gPosLen; set.thrVcm = r->gThrVcm; set.dirVm = r->gDirVm; set.contProb = r->gContProb;
+    set.singleCount = NULL;
+    set.capacity = uint32_t(need);
+    set.segStride = stride;
+    set.numSegs = uint32_t(ws);
+    for(int i = 0; i < ws; i++) set.segCount[i] = r->hostCounts[i];
+    return SVCM_OK;
+}
+
+// One iteration: the kernel schedule that replaces the two serial per-pixel loops
+int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t maxLen)
+{
+    IterConst ic;
+    iterationConstants(r, iteration, minLen, maxLen, ic);
+    cudaStream_t st = r->stream;
+    int launches = 0;
+
+    SVCM_CUDA(r, cudaMemsetAsync(r->counters, 0, sizeof(unsigned long long) * CNT_WORDS, st));
+    SVCM_CUDA(r, cudaMemsetAsync(r->queueCountsLight, 0, sizeof(uint32_t) * r->countsAlloc, st));
+    SVCM_CUDA(r, cudaMemsetAsync(r->queueCountsCamera, 0, sizeof(uint32_t) * r->countsAlloc, st));
+    if(r->useVC) SVCM_CUDA(r, cudaMemsetAsync(r->pathVertCount, 0, r->localPaths, st));
+    if(r->profile) cudaEventRecord(r->ev[0], st);
+
+    TraceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.verts = r->verts;
+    a.pathVertCount = r->pathVertCount;
+    a.queries = r->queries;
+    a.counters = r->counters;
+    a.accum = r->accum;
+    a.bboxBits = r->grid.bboxBits;
+
+    // ---- light sub-paths (reference src/vertexcm.hxx:321-396) -----------------------------
+    const uint32_t lightBounces = std::max(1u, maxLen > 0 ? maxLen - 1u : 0u);
+    a.queueCounts = r->queueCountsLight;
+    for(uint32_t b = 1; b <= lightBounces; b++)
+    {
+        a.in = r->queue[(b + 1) & 1]; a.out = r->queue[b & 1];
+        launchLightBounce(r->scene, ic, a, b, r->localPaths, st);
+        launches++;
+    }
+    if(r->profile) cudaEventRecord(r->ev[1], st);
+
+    // ---- hash grid over ALL light vertices (src/vertexcm.hxx:403-408) ----------------------
+    if(r->profile) cudaEventRecord(r->ev[2], st);
+    if(r->useVM)
+    {
+        MergeSet set;
+        if(r->params.worldSize > 1)
+        {
+            const int rc = gatherLightVertices(r, set);
+            if(rc) return rc;
+            launches++;
+            if(r->profile) cudaEventRecord(r->ev[2], st);
+        }
+        else
+        {
+            memset(&set, 0, sizeof(set));
+            set.posLen = r->verts.posLen; set.thrVcm = r->verts.thrVcm; set.dirVm = r->verts.dirVm;
+            set.contProb = r->verts.contProb;
+            set.singleCount = r->counters + CNT_LIGHT_VERTS;
+            set.capacity = r->verts.capacity;
+            set.segStride = r->verts.capacity; set.numSegs = 1;
+        }
+        launches += launchGridBuild(ic, set, r->grid, st);
+    }
+    if(r->profile) cudaEventRecord(r->ev[3], st);
+
+    // ---- camera sub-paths (src/vertexcm.hxx:415-545) ---------------------------------------
+    if(!r->lightTraceOnly)
+    {
+        const uint32_t camBounces = std::max(1u, maxLen);
+        a.queueCounts = r->queueCountsCamera;
+        for(uint32_t b = 1; b <= camBounces; b++)
+        {
+            a.in = r->queue[(b + 1) & 1]; a.out = r->queue[b & 1];
+            launchCameraBounce(r->scene, ic, a, b, r->localPaths, st);
+            launches++;
+        }
+    }
+    if(r->profile) cudaEventRecord(r->ev[4], st);
+
+    // ---- deferred merging of all queued camera vertices ------------------------------------
+    if(r->useVM && !r->lightTraceOnly)
+    {
+        launchMerge(r->scene, ic, r->queries, r->counters + CNT_QUERIES, 0, r->grid, r->accum, NULL, NULL,
+                    r->counters, r->mergeGroup, st);
+        launches++;
+    }
+    if(r->profile) cudaEventRecord(r->ev[5], st);
+
+    SVCM_CUDA(r, cudaMemcpyAsync(r->hostCounters, r->counters, sizeof(unsigned long long) * CNT_WORDS,
+                                 cudaMemcpyDeviceToHost, st));
+    SVCM_CUDA(r, cudaGetLastError());
+    r->evValid = r->profile;
+    r->stats.radius = ic.radius;
+    r->statsPending = true;
+    r->lastLaunches = launches;
+    r->iterationsDone++;
+    return SVCM_OK;
+}
+
+int finishStats(svcm_renderer *r)
+{
+    if(!r->statsPending) return SVCM_OK;
+    const unsigned long long *c = r->hostCounters;
+    SvcmStats &s = r->stats;
+    s.paths = r->paths; s.localPaths = r->localPaths;
+    s.localLightVertices = (int64_t)c[CNT_LIGHT_VERTS];
+    s.lightVertices = s.localLightVertices;
+    if(r->params.worldSize > 1 && r->useVM)
+    {
+        s.lightVertices = 0;
+        for(int i = 0; i < r->params.worldSize; i++) s.lightVertices += r->hostCounts[i];
+    }
+    s.mergeQueries = (int64_t)c[CNT_QUERIES];
+    s.mergeCandidates = (int64_t)c[CNT_CANDIDATES];
+    s.mergeAccepted = (int64_t)c[CNT_ACCEPTED];
+    s.lightRays = (int64_t)c[CNT_LIGHT_RAYS];
+    s.cameraRays = (int64_t)c[CNT_CAMERA_RAYS];
+    s.shadowRays = (int64_t)c[CNT_SHADOW_RAYS];
+    s.kernelLaunches = r->lastLaunches;
+    if(r->evValid)
+    {
+        cudaEventElapsedTime(&s.msLightTrace, r->ev[0], r->ev[1]);
+        cudaEventElapsedTime(&s.msGather, r->ev[1], r->ev[2]);
+        cudaEventElapsedTime(&s.msGridBuild, r->ev[2], r->ev[3]);
+        cudaEventElapsedTime(&s.msCameraTrace, r->ev[3], r->ev[4]);
+        cudaEventElapsedTime(&s.msMerge, r->ev[4], r->ev[5]);
+        cudaEventElapsedTime(&s.msTotal, r->ev[0], r->ev[5]);
+    }
+    r->statsPending = false;
+    if(c[CNT_OVERFLOW])
+        return fail(r, SVCM_E_NOMEM, "light-vertex or query store overflowed (%llu records dropped): "
+                    "not enough device memory for this resolution / path length", c[CNT_OVERFLOW]);
+    return SVCM_OK;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------
+// C-ABI: life cycle
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *svcm_version(void) { return "svcm 0.1 (sm_100a; CUDA wavefront VCM; C-ABI 1)"; }
+
+const char *svcm_last_error(const svcm_renderer *r) { return r ? r->error.c_str() : t_createError.c_str(); }
+
+int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_renderer **out)
+{
+    if(!out) return fail(NULL, SVCM_E_INVALID, "out is NULL");
+    *out = NULL;
+    if(!params) return fail(NULL, SVCM_E_INVALID, "params is NULL");
+    if(params->algorithm < SVCM_ALG_LIGHT_TRACE || params->algorithm > SVCM_ALG_VCM)
+        return fail(NULL, SVCM_E_INVALID, "unknown algorithm %d", params->algorithm);
+    if(params->worldSize < 1 || params->worldSize > 8 || params->rank < 0 || params->rank >= params->worldSize)
+        return fail(NULL, SVCM_E_INVALID, "bad rank/worldSize %d/%d (1..8 ranks)", params->rank, params->worldSize);
+    int rc = checkDevice(NULL, params->device);
+    if(rc) return rc;
+
+    svcm_renderer *r = new svcm_renderer;
+    // zero the POD part by hand (the struct holds std::string members)
+    r->device = params->device; r->stream = NULL;
+    memset(r->queue, 0, sizeof(r->queue));
+    r->queueCountsLight = r->queueCountsCamera = NULL; r->countsAlloc = 0;
+    memset(&r->verts, 0, sizeof(r->verts)); r->vertSlots = 0; r->pathVertCount = NULL;
+    memset(&r->queries, 0, sizeof(r->queries));
+    r->counters = NULL; r->hostCounters = NULL; r->accum = NULL;
+    memset(&r->grid, 0, sizeof(r->grid)); r->gridCells = 0; r->gridCapacity = 0; r->bboxInit = NULL;
+    r->comm = NULL; r->gPosLen = r->gThrVcm = r->gDirVm = NULL; r->gContProb = NULL; r->gatherCapacity = 0;
+    r->devCounts = NULL; r->hostCounts = NULL;
+    r->iterationsDone = 0; r->mergeGroup = 8; r->profile = false; r->evValid = false;
+    memset(r->ev, 0, sizeof(r->ev)); memset(r->userEv, 0, sizeof(r->userEv)); memset(&r->stats, 0, sizeof(r->stats));
+    r->statsPending = false; r->lastLaunches = 0;
+    r->params = *params;
+
+#define SVCM_CREATE_FAIL(code) do { t_createError = r->error; svcm_destroy(r); return (code); } while(0)
+    if((rc = buildDevScene(r, scene, r->scene))) SVCM_CREATE_FAIL(rc);
+
+    // algorithm flags, reference src/vertexcm.hxx:222-244
+    r->useVC = r->useVM = r->ppm = r->lightTraceOnly = false;
+    switch(params->algorithm)
+    {
+    case SVCM_ALG_LIGHT_TRACE: r->lightTraceOnly = true; break;
+    case SVCM_ALG_PPM: r->ppm = true; r->useVM = true; break;
+    case SVCM_ALG_BPM: r->useVM = true; break;
+    case SVCM_ALG_BPT: r->useVC = true; break;
+    case SVCM_ALG_VCM: r->useVC = true; r->useVM = true; break;
+    }
+    if(r->ppm)
+    {
+        // PPM cannot handle materials mixing specular and non-specular lobes: switch to BPM
+        // like the reference does (src/vertexcm.hxx:246-278)
+        for(int i = 0; i < r->scene.numMats; i++)
+        {
+            const SvcmMaterial &m = r->scene.mats[i];
+            const bool nonSpec = std::max(std::max(m.diffuse[0], m.diffuse[1]), m.diffuse[2]) > 0 ||
+                                 std::max(std::max(m.phong[0], m.phong[1]), m.phong[2]) > 0;
+            const bool spec = std::max(std::max(m.mirror[0], m.mirror[1]), m.mirror[2]) > 0 || m.ior > 0;
+            if(nonSpec && spec) { r->ppm = false; break; }
+        }
+    }
+
+    r->resX = int(r->scene.resX); r->resY = int(r->scene.resY);
+    if(r->resX <= 0 || r->resY <= 0 || uint64_t(r->resX) * uint64_t(r->resY) > 0x7FFFFFFFull)
+    { fail(r, SVCM_E_INVALID, "bad resolution %d x %d", r->resX, r->resY); SVCM_CREATE_FAIL(SVCM_E_INVALID); }
+    r->paths = uint32_t(r->resX) * uint32_t(r->resY);
+    const uint32_t ws = uint32_t(params->worldSize), rk = uint32_t(params->rank);
+    r->localRows = (uint32_t(r->resY) + ws - 1u - rk) / ws;     // rows y with y % ws == rank
+    r->localPaths = r->localRows * uint32_t(r->resX);
+    r->baseRadius = params->radiusFactor * r->scene.sphereRadius;  // src/vertexcm.hxx:280
+
+#define SVCM_TRY(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { \
+        fail(r, e_ == cudaErrorMemoryAllocation ? SVCM_E_NOMEM : SVCM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+        SVCM_CREATE_FAIL(e_ == cudaErrorMemoryAllocation ? SVCM_E_NOMEM : SVCM_E_CUDA); } } while(0)
+    SVCM_TRY(cudaSetDevice(r->device));
+    SVCM_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+    for(int i = 0; i < 6; i++) SVCM_TRY(cudaEventCreate(&r->ev[i]));
+    for(int i = 0; i < SVCM_NUM_USER_EVENTS; i++) SVCM_TRY(cudaEventCreate(&r->userEv[i]));
+    for(int i = 0; i < 2; i++) if((rc = allocQueue(r, r->queue[i], r->localPaths))) SVCM_CREATE_FAIL(rc);
+    if((rc = devAlloc(r, &r->pathVertCount, r->localPaths))) SVCM_CREATE_FAIL(rc);
+    if((rc = devAlloc(r, &r->counters, CNT_WORDS))) SVCM_CREATE_FAIL(rc);
+    if((rc = devAlloc(r, &r->accum, size_t(r->paths) * 3))) SVCM_CREATE_FAIL(rc);
+    if((rc = devAlloc(r, &r->grid.bboxBits, 6))) SVCM_CREATE_FAIL(rc);
+    if((rc = devAlloc(r, &r->bboxInit, 6))) SVCM_CREATE_FAIL(rc);
+    if((rc = devAlloc(r, &r->devCounts, 8))) SVCM_CREATE_FAIL(rc);
+    SVCM_TRY(cudaMallocHost((void**)&r->hostCounters, sizeof(unsigned long long) * CNT_WORDS));
+    SVCM_TRY(cudaMallocHost((void**)&r->hostCounts, sizeof(uint32_t) * 16));
+    memset(r->hostCounters, 0, sizeof(unsigned long long) * CNT_WORDS);
+    memset(r->hostCounts, 0, sizeof(uint32_t) * 16);
+    const int32_t init[6] = { floatToOrdered(1e36f), floatToOrdered(1e36f), floatToOrdered(1e36f),
+                              floatToOrdered(-1e36f), floatToOrdered(-1e36f), floatToOrdered(-1e36f) };
+    SVCM_TRY(cudaMemcpy(r->bboxInit, init, sizeof(init), cudaMemcpyHostToDevice));
+    SVCM_TRY(cudaMemcpy(r->grid.bboxBits, init, sizeof(init), cudaMemcpyHostToDevice));
+    r->grid.bboxInit = r->bboxInit;
+    SVCM_TRY(cudaMemset(r->accum, 0, sizeof(float) * 3 * size_t(r->paths)));
+    SVCM_TRY(cudaMemset(r->devCounts, 0, sizeof(uint32_t) * 8));
+#undef SVCM_TRY
+#undef SVCM_CREATE_FAIL
+    *out = r;
+    return SVCM_OK;
+}
+
+void svcm_destroy(svcm_renderer *r)
+{
+    if(!r) return;
+    cudaSetDevice(r->device);
+    if(r->stream) cudaStreamSynchronize(r->stream);
+    if(r->comm && ncclApi()->lib) ncclApi()->CommDestroy(r->comm);
+    freeQueue(r->queue[0]); freeQueue(r->queue[1]);
+    devFree(r->queueCountsLight); devFree(r->queueCountsCamera);
+    freeVerts(r); freeQueries(r); freeGridSorted(r); freeGather(r);
+    devFree(r->pathVertCount); devFree(r->counters); devFree(r->accum);
+    devFree(r->grid.cellCount); devFree(r->grid.blockSums); devFree(r->grid.bboxBits);
+    devFree(r->bboxInit); devFree(r->devCounts);
+    if(r->hostCounters) cudaFreeHost(r->hostCounters);
+    if(r->hostCounts) cudaFreeHost(r->hostCounts);
+    for(int i = 0; i < 6; i++) if(r->ev[i]) cudaEventDestroy(r->ev[i]);
+    for(int i = 0; i < SVCM_NUM_USER_EVENTS; i++) if(r->userEv[i]) cudaEventDestroy(r->userEv[i]);
+    if(r->stream) cudaStreamDestroy(r->stream);
+    delete r;
+}
+
+int svcm_set_option(svcm_renderer *r, int32_t option, int64_t value)
+{
+    if(!r) return SVCM_E_INVALID;
+    switch(option)
+    {
+    case SVCM_OPT_PROFILE: r->profile = value != 0; return SVCM_OK;
+    case SVCM_OPT_MERGE_GROUP:
+        if(value != 8 && value != 16 && value != 32) return fail(r, SVCM_E_INVALID, "merge group must be 8, 16 or 32");
+        r->mergeGroup = int(value); return SVCM_OK;
+    case SVCM_OPT_COUNTERS: return SVCM_OK;   // counters are always maintained
+    default: return fail(r, SVCM_E_INVALID, "unknown option %d", option);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// C-ABI: the hot path
+// ------------------------------------------------------------------------------------------
+int svcm_run_iterations(svcm_renderer *r, int32_t firstIteration, int32_t count, uint32_t minPathLength,
+                        uint32_t maxPathLength)
+{
+    if(!r) return SVCM_E_INVALID;
+    if(count < 0 || firstIteration < 0) return fail(r, SVCM_E_INVALID, "bad iteration range %d+%d", firstIteration, count);
+    SVCM_CUDA(r, cudaSetDevice(r->device));
+    int rc = ensureCapacity(r, maxPathLength);
+    if(rc) return rc;
+    for(int i = 0; i < count; i++)
+    {
+        // per-iteration counters of the previous iteration are overwritten: check overflow first
+        if(r->statsPending && i > 0) { /* stats of intermediate iterations are not retained */ }
+        if((rc = runOneIteration(r, firstIteration + i, minPathLength, maxPathLength))) return rc;
+    }
+    return SVCM_OK;
+}
+
+int svcm_synchronize(svcm_renderer *r)
+{
+    if(!r) return SVCM_E_INVALID;
+    SVCM_CUDA(r, cudaSetDevice(r->device));
+    SVCM_CUDA(r, cudaStreamSynchronize(r->stream));
+    return finishStats(r);
+}
+
+int svcm_download_accum(svcm_renderer *r, float *rgb, int32_t *iterationsDone)
+{
+    if(!r || !rgb) return SVCM_E_INVALID;
+    SVCM_CUDA(r, cudaSetDevice(r->device));
+    SVCM_CUDA(r, cudaMemcpyAsync(rgb, r->accum, sizeof(float) * 3 * size_t(r->paths), cudaMemcpyDeviceToHost, r->stream));
+    SVCM_CUDA(r, cudaStreamSynchronize(r->stream));
+    if(iterationsDone) *iterationsDone = r->iterationsDone;
+    return finishStats(r);
+}
+
+int svcm_clear_accum(svcm_renderer *r)
+{
+    if(!r) return SVCM_E_INVALID;
+    SVCM_CUDA(r, cudaSetDevice(r->device));
+    SVCM_CUDA(r, cudaMemsetAsync(r->accum, 0, sizeof(float) * 3 * size_t(r->paths), r->stream));
+    r->iterationsDone = 0;
+    return SVCM_OK;
+}
+
+int svcm_get_stats(svcm_renderer *r, SvcmStats *out)
+{
+    if(!r || !out) return SVCM_E_INVALID;
+    const int rc = svcm_synchronize(r);
+    *out = r->stats;
+    return rc;
+}
+
+int svcm_host_register(void *ptr, size_t bytes)
+{
+    if(!ptr || !bytes) return SVCM_E_INVALID;
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    if(e != cudaSuccess) { cudaGetLastError(); return fail(NULL, SVCM_E_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e)); }
+    return SVCM_OK;
+}
+
+int svcm_host_unregister(void *ptr)
+{
+    if(!ptr) return SVCM_E_INVALID;
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if(e != cudaSuccess) { cudaGetLastError(); return fail(NULL, SVCM_E_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e)); }
+    return SVCM_OK;
+}
+
+int svcm_device_count(void)
+{
+    int n = 0;
+    if(cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int svcm_event_record(svcm_renderer *r, int32_t slot)
+{
+    if(!r || slot < 0 || slot >= SVCM_NUM_USER_EVENTS) return r ? fail(r, SVCM_E_INVALID, "bad event slot") : SVCM_E_INVALID;
+    SVCM_CUDA(r, cudaSetDevice(r->device));
+    SVCM_CUDA(r, cudaEventRecord(r->userEv[slot], r->stream));
+    return SVCM_OK;
+}
+
+int svcm_event_elapsed_ms(svcm_renderer *r, int32_t startSlot, int32_t stopSlot, float *ms)
+{
+    if(!r || !ms || startSlot < 0 || startSlot >= SVCM_NUM_USER_EVENTS || stopSlot < 0 || stopSlot >= SVCM_NUM_USER_EVENTS)
+        return r ? fail(r, SVCM_E_INVALID, "bad event arguments") : SVCM_E_INVALID;
+    SVCM_CUDA(r, cudaSetDevice(r->device));
+    SVCM_CUDA(r, cudaEventSynchronize(r->userEv[stopSlot]));
+    SVCM_CUDA(r, cudaEventElapsedTime(ms, r->userEv[startSlot], r->userEv[stopSlot]));
+    return SVCM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// C-ABI: multi-GPU
+// ------------------------------------------------------------------------------------------
+int64_t svcm_shard_local_paths(int32_t width, int32_t height, int32_t rank, int32_t worldSize)
+{
+    if(width <= 0 || height <= 0 || worldSize <= 0 || rank < 0 || rank >= worldSize) return -1;
+    const int64_t rows = (int64_t(height) + worldSize - 1 - rank) / worldSize;
+    return rows * width;
+}
+int32_t svcm_shard_owner(int32_t width, int32_t worldSize, int64_t path)
+{
+    if(width <= 0 || worldSize <= 0 || path < 0) return -1;
+    return int32_t((path / width) % worldSize);
+}
+int64_t svcm_shard_local_index(int32_t width, int32_t worldSize, int64_t path)
+{
+    if(width <= 0 || worldSize <= 0 || path < 0) return -1;
+    const int64_t y = path / width, x = path - y * width;
+    return (y / worldSize) * width + x;
+}
+int64_t svcm_shard_global_index(int32_t width, int32_t rank, int32_t worldSize, int64_t local)
+{
+    if(width <= 0 || worldSize <= 0 || rank < 0 || rank >= worldSize || local < 0) return -1;
+    const int64_t ly = local / width, x = local - ly * width;
+    return (ly * worldSize + rank) * width + x;
+}
+
+int svcm_comm_unique_id(uint8_t id[SVCM_COMM_ID_BYTES])
+{
+    NcclApi *n = ncclApi();
+    if(!n->lib) return fail(NULL, SVCM_E_NCCL, "%s", n->error.c_str());
+    ncclUniqueId uid;
+    const int rc = n->GetUniqueId(&uid);
+    if(rc != NCCL_SUCCESS) return fail(NULL, SVCM_E_NCCL, "ncclGetUniqueId failed: %s", n->GetErrorString(rc));
+    memcpy(id, uid.internal, SVCM_COMM_ID_BYTES);
+    return SVCM_OK;
+}
+
+int svcm_comm_init(svcm_renderer *r, const uint8_t id[SVCM_COMM_ID_BYTES])
+{
+    if(!r || !id) return SVCM_E_INVALID;
+    NcclApi *n = ncclApi();
+    if(!n->lib) return fail(r, SVCM_E_NCCL, "%s", n->error.c_str());
+    if(r->comm) return fail(r, SVCM_E_STATE, "communicator already initialised");
+    SVCM_CUDA(r, cudaSetDevice(r->device));
+    ncclUniqueId uid; memcpy(uid.internal, id, SVCM_COMM_ID_BYTES);
+    return ncclCheck(r, n->CommInitRank(&r->comm, r->params.worldSize, uid, r->params.rank), "ncclCommInitRank");
+}
+
+int svcm_reduce_accum(svcm_renderer *r, int32_t root)
+{
+    if(!r) return SVCM_E_INVALID;
+    if(r->params.worldSize == 1) return SVCM_OK;
+    if(!r->comm) return fail(r, SVCM_E_STATE, "svcm_comm_init was not called");
+    SVCM_CUDA(r, cudaSetDevice(r->device));
+    return ncclCheck(r, ncclApi()->Reduce(r->accum, r->accum, size_t(r->paths) * 3, NCCL_FLOAT32, NCCL_SUM, root,
+                                          r->comm, r->stream), "ncclReduce(accum)");
+}
+
+// ------------------------------------------------------------------------------------------
+// C-ABI: kernel-level entry points
+// ------------------------------------------------------------------------------------------
+} // extern "C"
+
+struct svcm_hashgrid
+{
+    int device;
+    cudaStream_t stream;
+    int64_t count;
+    uint32_t numCells;
+    float radius;
+    float4 *posLen, *thrVcm, *dirVm; float *contProb;
+    unsigned long long *countDev;
+    GridBuffers grid;
+    int32_t *bboxInit;
+    std::string error;
+};
+
+namespace {
+
+// RAII device scratch for the batch entry points
+struct Scratch
+{
+    std::vector<void*> ptrs;
+    ~Scratch() { for(size_t i = 0; i < ptrs.size(); i++) cudaFree(ptrs[i]); }
+    template<typename T> T *alloc(size_t n, cudaError_t &err)
+    {
+        void *p = NULL;
+        if(err == cudaSuccess) { err = cudaMalloc(&p, std::max<size_t>(1, n) * sizeof(T)); if(err == cudaSuccess) ptrs.push_back(p); }
+        return (T*)p;
+    }
+};
+
+int batchPrologue(const SvcmSceneDesc *scene, int device, DevScene &sc)
+{
+    int rc = checkDevice(NULL, device);
+    if(rc) return rc;
+    if((rc = buildDevScene(NULL, scene, sc))) return rc;
+    if(cudaSetDevice(device) != cudaSuccess) return fail(NULL, SVCM_E_CUDA, "cudaSetDevice(%d) failed", device);
+    return SVCM_OK;
+}
+
+int cudaDone(cudaError_t e, const char *what)
+{
+    if(e == cudaSuccess) e = cudaDeviceSynchronize();
+    if(e == cudaSuccess) e = cudaGetLastError();
+    if(e != cudaSuccess) return fail(NULL, e == cudaErrorMemoryAllocation ? SVCM_E_NOMEM : SVCM_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return SVCM_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int svcm_hashgrid_build(const SvcmMergeVertex *vertices, int64_t count, float radius, int32_t numCells,
+                        int32_t device, svcm_hashgrid **out)
+{
+    if(!out) return fail(NULL, SVCM_E_INVALID, "out is NULL");
+    *out = NULL;
+    if(count < 0 || count > 0x7FFFFF00ll || numCells <= 0 || !(radius > 0.f) || (count && !vertices))
+        return fail(NULL, SVCM_E_INVALID, "bad hash grid arguments");
+    int rc = checkDevice(NULL, device);
+    if(rc) return rc;
+    cudaSetDevice(device);
+
+    svcm_hashgrid *g = new svcm_hashgrid;
+    g->device = device; g->stream = NULL; g->count = count; g->numCells = uint32_t(numCells); g->radius = radius;
+    g->posLen = g->thrVcm = g->dirVm = NULL; g->contProb = NULL; g->countDev = NULL; g->bboxInit = NULL;
+    memset(&g->grid, 0, sizeof(g->grid));
+
+    cudaError_t e = cudaSuccess;
+    SvcmMergeVertex *staging = NULL;
+    const size_t n = size_t(std::max<int64_t>(count, 1));
+#define G_ALLOC(p, cnt) if(e == cudaSuccess) e = cudaMalloc((void**)&(p), sizeof(*(p)) * (cnt))
+    G_ALLOC(staging, n);
+    G_ALLOC(g->posLen, n); G_ALLOC(g->thrVcm, n); G_ALLOC(g->dirVm, n); G_ALLOC(g->contProb, n);
+    G_ALLOC(g->countDev, 1); G_ALLOC(g->bboxInit, 6);
+    G_ALLOC(g->grid.cellKey, n); G_ALLOC(g->grid.cellCount, size_t(numCells) + 1);
+    G_ALLOC(g->grid.blockSums, (size_t(numCells) + 1) / 2048 + 2); G_ALLOC(g->grid.bboxBits, 6);
+    G_ALLOC(g->grid.sPosLen, n); G_ALLOC(g->grid.sThrVcm, n); G_ALLOC(g->grid.sDirVm, n);
+    G_ALLOC(g->grid.sContProb, n); G_ALLOC(g->grid.sIndex, n);
+#undef G_ALLOC
+    if(e == cudaSuccess)
+    {
+        const int32_t init[6] = { floatToOrdered(1e36f), floatToOrdered(1e36f), floatToOrdered(1e36f),
+                                  floatToOrdered(-1e36f), floatToOrdered(-1e36f), floatToOrdered(-1e36f) };
+        e = cudaMemcpy(g->bboxInit, init, sizeof(init), cudaMemcpyHostToDevice);
+        g->grid.bboxInit = g->bboxInit;
+    }
+    const unsigned long long c64 = (unsigned long long)count;
+    if(e == cudaSuccess) e = cudaMemcpy(g->countDev, &c64, 8, cudaMemcpyHostToDevice);
+    if(e == cudaSuccess && count) e = cudaMemcpy(staging, vertices, sizeof(SvcmMergeVertex) * size_t(count), cudaMemcpyHostToDevice);
+    if(e == cudaSuccess)
+    {
+        launchPackMergeVertices(staging, count, g->posLen, g->thrVcm, g->dirVm, g->contProb, 0);
+        IterConst ic; memset(&ic, 0, sizeof(ic));
+        ic.radius = radius; ic.radiusSqr = radius * radius; ic.invCellSize = 1.f / (radius * 2.f);
+        ic.numCells = uint32_t(numCells);
+        MergeSet set; memset(&set, 0, sizeof(set));
+        set.posLen = g->posLen; set.thrVcm = g->thrVcm; set.dirVm = g->dirVm; set.contProb = g->contProb;
+        set.singleCount = g->countDev; set.capacity = uint32_t(count); set.segStride = uint32_t(count); set.numSegs = 1;
+        launchGridBuild(ic, set, g->grid, 0);
+    }
+    rc = cudaDone(e, "svcm_hashgrid_build");
+    if(staging) cudaFree(staging);
+    if(rc) { svcm_hashgrid_destroy(g); return rc; }
+    *out = g;
+    return SVCM_OK;
+}
+
+void svcm_hashgrid_destroy(svcm_hashgrid *g)
+{
+    if(!g) return;
+    cudaSetDevice(g->device);
+    cudaFree(g->posLen); cudaFree(g->thrVcm); cudaFree(g->dirVm); cudaFree(g->contProb); cudaFree(g->countDev);
+    cudaFree(g->bboxInit); cudaFree(g->grid.cellKey); cudaFree(g->grid.cellCount); cudaFree(g->grid.blockSums);
+    cudaFree(g->grid.bboxBits); cudaFree(g->grid.sPosLen); cudaFree(g->grid.sThrVcm); cudaFree(g->grid.sDirVm);
+    cudaFree(g->grid.sContProb); cudaFree(g->grid.sIndex);
+    delete g;
+}
+
+int svcm_hashgrid_download(svcm_hashgrid *g, float bbox[6], int32_t *cellEnds, int32_t *indices)
+{
+    if(!g) return SVCM_E_INVALID;
+    cudaSetDevice(g->device);
+    cudaError_t e = cudaSuccess;
+    if(bbox)
+    {
+        int32_t bits[6];
+        e = cudaMemcpy(bits, g->grid.bboxBits, sizeof(bits), cudaMemcpyDeviceToHost);
+        for(int i = 0; i < 6; i++) bbox[i] = orderedToFloat(bits[i]);
+    }
+    if(e == cudaSuccess && cellEnds)
+        e = cudaMemcpy(cellEnds, g->grid.cellCount, sizeof(int32_t) * g->numCells, cudaMemcpyDeviceToHost);
+    if(e == cudaSuccess && indices && g->count)
+        e = cudaMemcpy(indices, g->grid.sIndex, sizeof(int32_t) * size_t(g->count), cudaMemcpyDeviceToHost);
+    return cudaDone(e, "svcm_hashgrid_download");
+}
+
+int svcm_hashgrid_query(svcm_hashgrid *g, const SvcmSceneDesc *scene, const SvcmMergeQuery *queries, int64_t count,
+                        uint32_t minPathLength, uint32_t maxPathLength, float misVcWeightFactor, int32_t ppm,
+                        float *contrib, int32_t *counts)
+{
+    if(!g || !scene || count < 0 || count > 0x7FFFFF00ll || (count && (!queries || !contrib)))
+        return fail(NULL, SVCM_E_INVALID, "bad hash grid query arguments");
+    for(int64_t i = 0; i < count; i++)
+        if(queries[i].matID < 0 || queries[i].matID >= scene->numMaterials || queries[i].pathLength > 0xFFFFu)
+            return fail(NULL, SVCM_E_INVALID, "query %lld: material or path length out of range", (long long)i);
+    DevScene sc;
+    int rc = batchPrologue(scene, g->device, sc);
+    if(rc) return rc;
+    if(count == 0) return SVCM_OK;
+
+    Scratch s; cudaError_t e = cudaSuccess;
+    SvcmMergeQuery *dq = s.alloc<SvcmMergeQuery>(size_t(count), e);
+    QueryStore qs;
+    qs.q0 = s.alloc<float4>(size_t(count), e); qs.q1 = s.alloc<float4>(size_t(count), e);
+    qs.q2 = s.alloc<float4>(size_t(count), e); qs.q3 = s.alloc<float4>(size_t(count), e);
+    qs.capacity = uint32_t(count);
+    float *dContrib = s.alloc<float>(size_t(count) * 3, e);
+    int32_t *dCounts = s.alloc<int32_t>(size_t(count) * 2, e);
+    if(e == cudaSuccess) e = cudaMemcpy(dq, queries, sizeof(SvcmMergeQuery) * size_t(count), cudaMemcpyHostToDevice);
+    if(e == cudaSuccess)
+    {
+        IterConst ic; memset(&ic, 0, sizeof(ic));
+        ic.radius = g->radius; ic.radiusSqr = g->radius * g->radius; ic.invCellSize = 1.f / (g->radius * 2.f);
+        ic.numCells = g->numCells; ic.minLen = minPathLength; ic.maxLen = maxPathLength;
+        ic.misVcWeightFactor = misVcWeightFactor; ic.ppm = ppm != 0; ic.useVM = 1;
+        launchPackMergeQueries(sc, dq, count, qs, 0);
+        launchMerge(sc, ic, qs, NULL, uint32_t(count), g->grid, NULL, dContrib, dCounts, NULL, 8, 0);
+        e = cudaMemcpy(contrib, dContrib, sizeof(float) * 3 * size_t(count), cudaMemcpyDeviceToHost);
+        if(e == cudaSuccess && counts) e = cudaMemcpy(counts, dCounts, sizeof(int32_t) * 2 * size_t(count), cudaMemcpyDeviceToHost);
+    }
+    return cudaDone(e, "svcm_hashgrid_query");
+}
+
+int svcm_intersect_batch(const SvcmSceneDesc *scene, const float *rays, int64_t count, int32_t device, int32_t *hit,
+                         float *dist, float *normal, int32_t *matID, int32_t *lightID)
+{
+    if(count < 0 || (count && (!rays || !hit || !dist || !normal || !matID || !lightID)))
+        return fail(NULL, SVCM_E_INVALID, "bad arguments");
+    DevScene sc; int rc = batchPrologue(scene, device, sc); if(rc) return rc;
+    if(count == 0) return SVCM_OK;
+    Scratch s; cudaError_t e = cudaSuccess; const size_t n = size_t(count);
+    float *dRays = s.alloc<float>(n * 6, e); int32_t *dHit = s.alloc<int32_t>(n, e); float *dDist = s.alloc<float>(n, e);
+    float *dN = s.alloc<float>(n * 3, e); int32_t *dMat = s.alloc<int32_t>(n, e); int32_t *dLight = s.alloc<int32_t>(n, e);
+    if(e == cudaSuccess) e = cudaMemcpy(dRays, rays, sizeof(float) * 6 * n, cudaMemcpyHostToDevice);
+    if(e == cudaSuccess)
+    {
+        launchIntersectBatch(sc, dRays, count, dHit, dDist, dN, dMat, dLight, 0);
+        e = cudaMemcpy(hit, dHit, 4 * n, cudaMemcpyDeviceToHost);
+        if(e == cudaSuccess) e = cudaMemcpy(dist, dDist, 4 * n, cudaMemcpyDeviceToHost);
+        if(e == cudaSuccess) e = cudaMemcpy(normal, dN, 12 * n, cudaMemcpyDeviceToHost);
+        if(e == cudaSuccess) e = cudaMemcpy(matID, dMat, 4 * n, cudaMemcpyDeviceToHost);
+        if(e == cudaSuccess) e = cudaMemcpy(lightID, dLight, 4 * n, cudaMemcpyDeviceToHost);
+    }
+    return cudaDone(e, "svcm_intersect_batch");
+}
+
+int svcm_occluded_batch(const SvcmSceneDesc *scene, const float *segments, int64_t count, int32_t device, int32_t *occluded)
+{
+    if(count < 0 || (count && (!segments || !occluded))) return fail(NULL, SVCM_E_INVALID, "bad arguments");
+    DevScene sc; int rc = batchPrologue(scene, device, sc); if(rc) return rc;
+    if(count == 0) return SVCM_OK;
+    Scratch s; cudaError_t e = cudaSuccess; const size_t n = size_t(count);
+    float *dSeg = s.alloc<float>(n * 7, e); int32_t *dOcc = s.alloc<int32_t>(n, e);
+    if(e == cudaSuccess) e = cudaMemcpy(dSeg, segments, sizeof(float) * 7 * n, cudaMemcpyHostToDevice);
+    if(e == cudaSuccess)
+    {
+        launchOccludedBatch(sc, dSeg, count, dOcc, 0);
+        e = cudaMemcpy(occluded, dOcc, 4 * n, cudaMemcpyDeviceToHost);
+    }
+    return cudaDone(e, "svcm_occluded_batch");
+}
+
+static int bsdfBatchCheck(const SvcmSceneDesc *scene, const float *in, int64_t count)
+{
+    for(int64_t i = 0; i < count; i++)
+    {
+        int32_t m; memcpy(&m, in + 10 * i + 9, 4);
+        if(m < 0 || m >= scene->numMaterials) return fail(NULL, SVCM_E_INVALID, "item %lld: material %d out of range", (long long)i, m);
+    }
+    return SVCM_OK;
+}
+
+int svcm_bsdf_evaluate_batch(const SvcmSceneDesc *scene, const float *in, int64_t count, int32_t fixIsLight,
+                             int32_t device, float *out)
+{
+    if(count < 0 || !scene || (count && (!in || !out))) return fail(NULL, SVCM_E_INVALID, "bad arguments");
+    DevScene sc; int rc = batchPrologue(scene, device, sc); if(rc) return rc;
+    if((rc = bsdfBatchCheck(scene, in, count))) return rc;
+    if(count == 0) return SVCM_OK;
+    Scratch s; cudaError_t e = cudaSuccess; const size_t n = size_t(count);
+    float *dIn = s.alloc<float>(n * 10, e); float *dOut = s.alloc<float>(n * 8, e);
+    if(e == cudaSuccess) e = cudaMemcpy(dIn, in, sizeof(float) * 10 * n, cudaMemcpyHostToDevice);
+    if(e == cudaSuccess)
+    {
+        launchBsdfEvaluateBatch(sc, dIn, count, fixIsLight, dOut, 0);
+        e = cudaMemcpy(out, dOut, sizeof(float) * 8 * n, cudaMemcpyDeviceToHost);
+    }
+    return cudaDone(e, "svcm_bsdf_evaluate_batch");
+}
+
+int svcm_bsdf_sample_batch(const SvcmSceneDesc *scene, const float *in, int64_t count, int32_t fixIsLight,
+                           int32_t device, float *out, uint32_t *events)
+{
+    if(count < 0 || !scene || (count && (!in || !out || !events))) return fail(NULL, SVCM_E_INVALID, "bad arguments");
+    DevScene sc; int rc = batchPrologue(scene, device, sc); if(rc) return rc;
+    if((rc = bsdfBatchCheck(scene, in, count))) return rc;
+    if(count == 0) return SVCM_OK;
+    Scratch s; cudaError_t e = cudaSuccess; const size_t n = size_t(count);
+    float *dIn = s.alloc<float>(n * 10, e); float *dOut = s.alloc<float>(n * 8, e); uint32_t *dEv = s.alloc<uint32_t>(n, e);
+    if(e == cudaSuccess) e = cudaMemcpy(dIn, in, sizeof(float) * 10 * n, cudaMemcpyHostToDevice);
+    if(e == cudaSuccess)
+    {
+        launchBsdfSampleBatch(sc, dIn, count, fixIsLight, dOut, dEv, 0);
+        e = cudaMemcpy(out, dOut, sizeof(float) * 8 * n, cudaMemcpyDeviceToHost);
+        if(e == cudaSuccess) e = cudaMemcpy(events, dEv, 4 * n, cudaMemcpyDeviceToHost);
+    }
+    return cudaDone(e, "svcm_bsdf_sample_batch");
+}
+
+int svcm_rng_stream(int32_t seed, int32_t iteration, int32_t phase, uint32_t firstPath, int32_t paths, int32_t draws,
+                    float *out)
+{
+    if(paths < 0 || draws < 0 || !out) return fail(NULL, SVCM_E_INVALID, "bad arguments");
+    for(int p = 0; p < paths; p++)
+    {
+        PathRng rng; rng.key = rngKey(seed, iteration, phase); rng.path = firstPath + uint32_t(p); rng.draw = 0u;
+        for(int k = 0; k < draws; k++) out[size_t(p) * draws + k] = rng.next();
+    }
+    return SVCM_OK;
+}
+
+int svcm_rng_stream_device(int32_t seed, int32_t iteration, int32_t phase, uint32_t firstPath, int32_t paths,
+                           int32_t draws, int32_t device, float *out)
+{
+    if(paths < 0 || draws < 0 || !out) return fail(NULL, SVCM_E_INVALID, "bad arguments");
+    int rc = checkDevice(NULL, device); if(rc) return rc;
+    cudaSetDevice(device);
+    if(paths == 0 || draws == 0) return SVCM_OK;
+    Scratch s; cudaError_t e = cudaSuccess; const size_t n = size_t(paths) * size_t(draws);
+    float *d = s.alloc<float>(n, e);
+    if(e == cudaSuccess)
+    {
+        launchRngStream(rngKey(seed, iteration, phase), firstPath, paths, draws, d, 0);
+        e = cudaMemcpy(out, d, sizeof(float) * n, cudaMemcpyDeviceToHost);
+    }
+    return cudaDone(e, "svcm_rng_stream_device");
+}
+
+} // extern "C"

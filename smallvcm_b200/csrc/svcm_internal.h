@@ -1,0 +1,171 @@
+// svcm_internal.h — structures shared by the kernels (svcm_kernels.cu) and the host side
+// of the C-ABI (svcm_api.cu). Not installed; include/svcm.h is the public face.
+#ifndef SVCM_INTERNAL_H_
+#define SVCM_INTERNAL_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "svcm.h"
+#include "svcm_device.cuh"
+
+namespace svcm {
+
+// Per-iteration constants: the scalars VertexCM::RunIteration derives at its top
+// (reference src/vertexcm.hxx:288-308) plus launch geometry. Travels as a kernel parameter.
+struct IterConst
+{
+    float    radius, radiusSqr, invCellSize;
+    float    vmNormalization;      // 1 / (pi r^2 N)
+    float    misVmWeightFactor;    // eta_VCM  (0 unless merging)
+    float    misVcWeightFactor;    // 1 / eta_VCM (0 unless connecting)
+    float    lightSubPathCount;    // N = W*H (global, also with sharding)
+    uint32_t minLen, maxLen;
+    uint32_t keyLight, keyCamera;  // Philox keys for phase 0 / phase 1 of this iteration
+    int32_t  useVC, useVM, ppm, lightTraceOnly;
+    int32_t  resX, resY;
+    int32_t  rank, worldSize;      // path p is owned by rank (p / resX) % worldSize
+    uint32_t localPaths;
+    uint32_t numCells;             // hash-grid cell count (= W*H, src/vertexcm.hxx:406)
+};
+
+// SoA path state, one slot per queued sub-path; four 16-byte streams so that every
+// access is one coalesced 128-bit load/store per lane.
+//   s0 = origin.xyz      | dVCM
+//   s1 = direction.xyz   | dVC
+//   s2 = throughput.xyz  | dVM
+//   s3 = path index | pathLength + flags | rng draw counter | light: stored-vertex count,
+//                                                             camera: target pixel
+struct PathQueue
+{
+    float4 *s0, *s1, *s2;
+    uint4  *s3;
+};
+enum { PATH_FLAG_FINITE = 1u << 30, PATH_FLAG_SPECULAR = 1u << 31, PATH_LEN_MASK = (1u << 30) - 1u };
+
+// Light vertices of the LOCAL light sub-paths (PathVertex<true>, src/vertexcm.hxx:79-98),
+// split by consumer:
+//   merge record (52 B, all-gathered and cell-sorted): posLen, thrVcm, dirVm, contProb
+//   connection extras (local only)                   : nrmVc, ldfMat
+struct VertexStore
+{
+    float4  *posLen;    // hitpoint.xyz | pathLength (bits)
+    float4  *thrVcm;    // throughput.xyz | dVCM
+    float4  *dirVm;     // WorldDirFix().xyz | dVM
+    float   *contProb;  // light BSDF continuation probability
+    float4  *nrmVc;     // shading normal.xyz | dVC
+    float4  *ldfMat;    // local fixed direction.xyz | matID (bits)
+    int32_t *pathVerts; // [slot k][local path] -> vertex index   (replaces mPathEnds)
+    uint32_t capacity;
+};
+
+// The gathered (all ranks) merge records and their cell-sorted copy + grid
+struct MergeSet
+{
+    // unsorted merge records. Single rank: `*singleCount` records (device counter, clamped
+    // to capacity). Gathered from all ranks: numSegs segments of `segStride` records of which
+    // the first segCount[r] are valid (the rest is all-gather padding).
+    const float4 *posLen; const float4 *thrVcm; const float4 *dirVm; const float *contProb;
+    const unsigned long long *singleCount;
+    uint32_t capacity;
+    uint32_t segStride;
+    uint32_t segCount[8];
+    uint32_t numSegs;
+};
+
+struct GridBuffers
+{
+    uint32_t *cellKey;    // [virtual index] hash bucket of each vertex (or ~0 for padding)
+    uint32_t *cellCount;  // [numCells + 1] histogram -> exclusive scan (cell starts) -> cell ENDS
+                          // after the scatter (the reference's mCellEnds, src/hashgrid.hxx:90-91)
+    uint32_t *blockSums;  // scan scratch
+    int32_t  *bboxBits;   // 6 ordered-int encoded floats: min xyz, max xyz
+    const int32_t *bboxInit; // device copy of the empty box (+1e36 x3, -1e36 x3)
+    // cell-sorted merge records
+    float4   *sPosLen; float4 *sThrVcm; float4 *sDirVm; float *sContProb;
+    int32_t  *sIndex;     // original (virtual) index at each sorted position  (mIndices)
+};
+
+// Merge queries emitted by the camera pass (RangeQuery, src/vertexcm.hxx:109-178):
+//   q0 = position.xyz | pixel (bits)      q1 = normal.xyz | pathLength | matID << 16 (bits)
+//   q2 = local fixed dir.xyz | dVCM       q3 = throughput * vmNormalization .xyz | dVM
+struct QueryStore
+{
+    float4 *q0, *q1, *q2, *q3;
+    uint32_t capacity;
+};
+
+// device-side counters (one block of 64-bit words, zeroed per iteration)
+enum {
+    CNT_LIGHT_VERTS = 0, CNT_QUERIES, CNT_CANDIDATES, CNT_ACCEPTED, CNT_LIGHT_RAYS,
+    CNT_CAMERA_RAYS, CNT_SHADOW_RAYS, CNT_OVERFLOW, CNT_WORDS
+};
+
+struct TraceArgs
+{
+    PathQueue   in, out;
+    uint32_t   *queueCounts;     // [bounce index] number of live sub-paths entering that bounce
+    VertexStore verts;
+    uint8_t    *pathVertCount;   // [local path] number of stored vertices
+    QueryStore  queries;
+    unsigned long long *counters; // CNT_*
+    float      *accum;           // W*H*3 accumulated image
+    const int32_t *bboxBits;     // light-vertex bbox (camera pass: early reject of queries)
+};
+
+// ordered-int encoding of floats for atomicMin/atomicMax
+SVCM_HD int32_t floatToOrdered(float f)
+{
+    int32_t i;
+#ifdef __CUDA_ARCH__
+    i = __float_as_int(f);
+#else
+    memcpy(&i, &f, 4);
+#endif
+    return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+SVCM_HD float orderedToFloat(int32_t i)
+{
+    i = i >= 0 ? i : i ^ 0x7FFFFFFF;
+#ifdef __CUDA_ARCH__
+    return __int_as_float(i);
+#else
+    float f; memcpy(&f, &i, 4); return f;
+#endif
+}
+
+// ---- launchers implemented in svcm_kernels.cu (all asynchronous on `stream`) -------------
+void launchLightBounce(const DevScene &sc, const IterConst &ic, const TraceArgs &args,
+                       uint32_t bounce, uint32_t maxItems, cudaStream_t stream);
+void launchCameraBounce(const DevScene &sc, const IterConst &ic, const TraceArgs &args,
+                        uint32_t bounce, uint32_t maxItems, cudaStream_t stream);
+// HashGrid::Build: bbox -> keys + histogram -> exclusive scan -> scatter. Returns the
+// number of kernels launched.
+int  launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers &grid,
+                     cudaStream_t stream);
+// HashGrid::Process + RangeQuery::Process over `numQueries` (read from *queryCount on the
+// device when queryCount != NULL, else the host value) queued queries.
+void launchMerge(const DevScene &sc, const IterConst &ic, const QueryStore &queries,
+                 const unsigned long long *queryCount, uint32_t hostQueryCount,
+                 const GridBuffers &grid, float *accum, float *contribOut, int32_t *countsOut,
+                 unsigned long long *counters, int groupSize, cudaStream_t stream);
+
+// kernel-level batch entry points (device pointers)
+void launchIntersectBatch(const DevScene &sc, const float *rays, int64_t count, int32_t *hit,
+                          float *dist, float *normal, int32_t *matID, int32_t *lightID,
+                          cudaStream_t stream);
+void launchOccludedBatch(const DevScene &sc, const float *segments, int64_t count,
+                         int32_t *occluded, cudaStream_t stream);
+void launchBsdfEvaluateBatch(const DevScene &sc, const float *in, int64_t count, int fixIsLight,
+                             float *out, cudaStream_t stream);
+void launchBsdfSampleBatch(const DevScene &sc, const float *in, int64_t count, int fixIsLight,
+                           float *out, uint32_t *events, cudaStream_t stream);
+void launchRngStream(uint32_t key, uint32_t firstPath, int paths, int draws, float *out,
+                     cudaStream_t stream);
+// packs host-layout records into the device streams
+void launchPackMergeVertices(const SvcmMergeVertex *verts, int64_t count, float4 *posLen,
+                             float4 *thrVcm, float4 *dirVm, float *contProb, cudaStream_t stream);
+void launchPackMergeQueries(const DevScene &sc, const SvcmMergeQuery *queries, int64_t count,
+                            QueryStore store, cudaStream_t stream);
+
+} // namespace svcm
+#endif

@@ -1,0 +1,1178 @@
+// svcm_kernels.cu — the wavefront kernels of one VCM iteration (sm_100a).
+//
+// One iteration of VertexCM::RunIteration (reference src/vertexcm.hxx:284-548) becomes
+//   light pass : k_lightBounce  x (maxLen-1)   one warp lane per live light sub-path
+//   grid build : k_gridBBox, k_gridKeys, 3-kernel exclusive scan, k_gridScatter
+//   camera pass: k_cameraBounce x maxLen       one warp lane per live camera sub-path
+//   merge      : k_merge                        G lanes cooperate on one range query
+// Sub-path state lives in HBM as four 16-byte SoA streams (svcm_internal.h) and is
+// compacted between bounces with warp-aggregated appends, so every bounce kernel reads and
+// writes full coalesced 128-bit lanes. The scene (<= 64 primitives) rides in the constant
+// bank as a __grid_constant__ parameter: the trace kernels are instruction-bound, only the
+// vertex store, the grid build and the merge move real HBM traffic.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "svcm_internal.h"
+
+namespace svcm {
+
+#define SVCM_BLOCK 256
+#define FULL_MASK 0xffffffffu
+
+// ------------------------------------------------------------------------------------------
+// small device utilities
+// ------------------------------------------------------------------------------------------
+SVCM_D uint32_t laneId() { return threadIdx.x & 31u; }
+
+// Warp-aggregated append: every lane of the warp must call it; lanes with pred get a
+// distinct slot from one atomicAdd issued by the first such lane.
+SVCM_D uint32_t warpAppend(uint32_t *counter, bool pred)
+{
+    const uint32_t m = __ballot_sync(FULL_MASK, pred);
+    if(m == 0u) return 0u;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0u;
+    if(int(laneId()) == leader) base = atomicAdd(counter, uint32_t(__popc(m)));
+    base = __shfl_sync(FULL_MASK, base, leader);
+    return base + uint32_t(__popc(m & ((1u << laneId()) - 1u)));
+}
+SVCM_D uint32_t warpAppend64(unsigned long long *counter, bool pred)
+{
+    const uint32_t m = __ballot_sync(FULL_MASK, pred);
+    if(m == 0u) return 0u;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0ull;
+    if(int(laneId()) == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(FULL_MASK, base, leader);
+    return uint32_t(base) + uint32_t(__popc(m & ((1u << laneId()) - 1u)));
+}
+
+// adds a per-thread count into a 64-bit device counter with one atomic per warp
+SVCM_D void warpCount(unsigned long long *counter, uint32_t mine)
+{
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(FULL_MASK, mine, o);
+    if(laneId() == 0u && mine) atomicAdd(counter, (unsigned long long)mine);
+}
+
+SVCM_D void addPixel(float *accum, uint32_t pixel, f3 c)
+{
+    float *p = accum + 3ull * pixel;
+    if(c.x != 0.f) atomicAdd(p + 0, c.x);
+    if(c.y != 0.f) atomicAdd(p + 1, c.y);
+    if(c.z != 0.f) atomicAdd(p + 2, c.z);
+}
+
+SVCM_D float4 mk4(f3 a, float w) { return make_float4(a.x, a.y, a.z, w); }
+SVCM_D f3 xyz(float4 a) { return mk3(a.x, a.y, a.z); }
+
+// local (per-rank) path index <-> global path index: rows are dealt round-robin to ranks
+SVCM_D uint32_t localToGlobalPath(const IterConst &ic, uint32_t l)
+{
+    if(ic.worldSize == 1) return l;
+    const uint32_t ly = l / uint32_t(ic.resX), x = l - ly * uint32_t(ic.resX);
+    return (ly * uint32_t(ic.worldSize) + uint32_t(ic.rank)) * uint32_t(ic.resX) + x;
+}
+SVCM_D uint32_t globalToLocalPath(const IterConst &ic, uint32_t p)
+{
+    if(ic.worldSize == 1) return p;
+    const uint32_t y = p / uint32_t(ic.resX), x = p - y * uint32_t(ic.resX);
+    return (y / uint32_t(ic.worldSize)) * uint32_t(ic.resX) + x;
+}
+
+// ------------------------------------------------------------------------------------------
+// sub-path state in registers
+// ------------------------------------------------------------------------------------------
+struct SubPath
+{
+    f3 origin, direction, throughput;
+    float dVCM, dVC, dVM;
+    uint32_t path;      // global path index (= pixel index of the pair, = RNG stream id)
+    uint32_t length;    // mPathLength
+    bool finiteLight;   // mIsFiniteLight
+    bool specular;      // mSpecularPath
+    uint32_t extra;     // light: number of stored vertices; camera: target pixel
+    PathRng rng;
+};
+
+SVCM_D void loadSubPath(const PathQueue &q, uint32_t i, uint32_t key, SubPath &s)
+{
+    const float4 a = q.s0[i], b = q.s1[i], c = q.s2[i];
+    const uint4  d = q.s3[i];
+    s.origin = xyz(a); s.dVCM = a.w;
+    s.direction = xyz(b); s.dVC = b.w;
+    s.throughput = xyz(c); s.dVM = c.w;
+    s.path = d.x;
+    s.length = d.y & PATH_LEN_MASK;
+    s.finiteLight = (d.y & PATH_FLAG_FINITE) != 0u;
+    s.specular = (d.y & PATH_FLAG_SPECULAR) != 0u;
+    s.rng.key = key; s.rng.path = d.x; s.rng.draw = d.z;
+    s.extra = d.w;
+}
+SVCM_D void storeSubPath(const PathQueue &q, uint32_t i, const SubPath &s)
+{
+    q.s0[i] = mk4(s.origin, s.dVCM);
+    q.s1[i] = mk4(s.direction, s.dVC);
+    q.s2[i] = mk4(s.throughput, s.dVM);
+    q.s3[i] = make_uint4(s.path, s.length | (s.finiteLight ? PATH_FLAG_FINITE : 0u) |
+                         (s.specular ? PATH_FLAG_SPECULAR : 0u), s.rng.draw, s.extra);
+}
+
+// SampleScattering, reference src/vertexcm.hxx:938-1006. Returns false to terminate.
+template<bool kLight>
+SVCM_D bool sampleScattering(const DevScene &sc, const IterConst &ic, const Bsdf &bsdf, f3 hitPoint,
+                             SubPath &s)
+{
+    const float r0 = s.rng.next(), r1 = s.rng.next(), r2 = s.rng.next();
+    float bsdfDirPdfW, cosThetaOut;
+    uint32_t ev;
+    f3 dirOut = s.direction;
+    const f3 bsdfFactor = bsdfSample<kLight>(sc, bsdf, r0, r1, r2, dirOut, bsdfDirPdfW, cosThetaOut, ev);
+    if(iszero(bsdfFactor)) return false;
+
+    float bsdfRevPdfW = bsdfDirPdfW;
+    if((ev & EV_SPECULAR) == 0u) bsdfRevPdfW = bsdfReversePdf(sc, bsdf, dirOut);
+
+    const float contProb = bsdf.contProb;          // Russian roulette
+    if(s.rng.next() > contProb) return false;
+
+    bsdfDirPdfW *= contProb;
+    bsdfRevPdfW *= contProb;
+
+    if(ev & EV_SPECULAR)
+    {
+        s.dVCM = 0.f;                              // [tech. rep. (53)-(55)]
+        s.dVC *= cosThetaOut;
+        s.dVM *= cosThetaOut;
+    }
+    else
+    {
+        const float f = cosThetaOut / bsdfDirPdfW; // [tech. rep. (34)-(36)]
+        s.dVC = f * (s.dVC * bsdfRevPdfW + s.dVCM + ic.misVmWeightFactor);
+        s.dVM = f * (s.dVM * bsdfRevPdfW + s.dVCM * ic.misVcWeightFactor + 1.f);
+        s.dVCM = 1.f / bsdfDirPdfW;
+        s.specular = false;
+    }
+    s.origin = hitPoint;
+    s.direction = dirOut;
+    s.throughput = s.throughput * (bsdfFactor * (cosThetaOut / bsdfDirPdfW));
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// light pass
+// ------------------------------------------------------------------------------------------
+
+// GenerateLightSample, reference src/vertexcm.hxx:816-858
+SVCM_D void generateLightSample(const DevScene &sc, const IterConst &ic, SubPath &s)
+{
+    const int   lightCount = sc.numLights;
+    const float lightPickProb = 1.f / float(lightCount);
+    int lightID = int(s.rng.next() * float(lightCount));
+    const float dirX = s.rng.next(), dirY = s.rng.next();
+    const float posX = s.rng.next(), posY = s.rng.next();
+    lightID = min(lightID, lightCount - 1);                          // Scene::GetLightPtr clamp
+    const DevLight &light = sc.lights[lightID];
+
+    float emissionPdfW, directPdfA, cosLight;
+    s.throughput = lightEmit(sc, light, dirX, dirY, posX, posY, s.origin, s.direction,
+                             emissionPdfW, directPdfA, cosLight);
+    emissionPdfW *= lightPickProb;
+    directPdfA   *= lightPickProb;
+
+    s.throughput  = s.throughput / emissionPdfW;
+    s.length      = 1u;
+    s.finiteLight = lightIsFinite(light.type);
+    s.specular    = false;
+    s.dVCM = directPdfA / emissionPdfW;
+    if(!lightIsDelta(light.type))
+    {
+        const float usedCosLight = lightIsFinite(light.type) ? cosLight : 1.f;
+        s.dVC = usedCosLight / emissionPdfW;
+    }
+    else s.dVC = 0.f;
+    s.dVM = s.dVC * ic.misVcWeightFactor;
+    s.extra = 0u;
+}
+
+// ConnectToCamera, reference src/vertexcm.hxx:862-933: splat the light vertex onto the
+// image through the pinhole; float atomics because the target pixel is arbitrary.
+SVCM_D void connectToCamera(const DevScene &sc, const IterConst &ic, const SubPath &s, f3 hitPoint,
+                            const Bsdf &bsdf, float *accum, uint32_t &shadowRays)
+{
+    const f3 camPos = ld3(sc.camPos), camFwd = ld3(sc.camFwd);
+    f3 dirToCamera = camPos - hitPoint;
+    if(dot(camFwd, -dirToCamera) <= 0.f) return;
+
+    const f3 raster = transformPoint(sc.worldToRaster, hitPoint);      // Camera::WorldToRaster
+    if(!(raster.x >= 0.f && raster.y >= 0.f && raster.x < sc.resX && raster.y < sc.resY)) return;
+
+    const float distEye2 = lensqr(dirToCamera);
+    const float distance = sqrtf(distEye2);
+    dirToCamera = dirToCamera / distance;
+
+    float cosToCamera, bsdfDirPdfW, bsdfRevPdfW;
+    const f3 bsdfFactor = bsdfEvaluate(sc, bsdf, dirToCamera, cosToCamera, bsdfDirPdfW, bsdfRevPdfW);
+    if(iszero(bsdfFactor)) return;
+    bsdfRevPdfW *= bsdf.contProb;
+
+    const float cosAtCamera = dot(camFwd, -dirToCamera);
+    const float imagePointToCameraDist = sc.imagePlaneDist / cosAtCamera;
+    const float imageToSolidAngleFactor = sqr(imagePointToCameraDist) / cosAtCamera;
+    const float imageToSurfaceFactor = imageToSolidAngleFactor * fabsf(cosToCamera) / sqr(distance);
+    const float cameraPdfA = imageToSurfaceFactor;
+
+    const float wLight = (cameraPdfA / ic.lightSubPathCount) *
+        (ic.misVmWeightFactor + s.dVCM + s.dVC * bsdfRevPdfW);            // [tech. rep. (46)]
+    const float misWeight = ic.lightTraceOnly ? 1.f : (1.f / (wLight + 1.f));
+    const float surfaceToImageFactor = 1.f / imageToSurfaceFactor;
+
+    const f3 contrib = (misWeight * s.throughput * bsdfFactor) /
+        (ic.lightSubPathCount * surfaceToImageFactor);
+    if(iszero(contrib)) return;
+
+    shadowRays++;
+    if(sceneOccluded(sc, hitPoint, dirToCamera, distance)) return;
+    // Framebuffer::AddColor, reference src/framebuffer.hxx:43-57
+    const uint32_t pixel = uint32_t(int(raster.x)) + uint32_t(int(raster.y)) * uint32_t(ic.resX);
+    addPixel(accum, pixel, contrib);
+}
+
+// One bounce of every live light sub-path: reference src/vertexcm.hxx:328-393 (loop body)
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_lightBounce(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
+              const __grid_constant__ TraceArgs a, const uint32_t bounce)
+{
+    const uint32_t count = (bounce == 1u) ? ic.localPaths : a.queueCounts[bounce];
+    uint32_t nRays = 0u, nShadow = 0u;
+
+    for(uint32_t i0 = blockIdx.x * blockDim.x; i0 < count; i0 += gridDim.x * blockDim.x)
+    {
+        const uint32_t i = i0 + threadIdx.x;
+        bool alive = i < count;
+        SubPath s;
+        if(alive)
+        {
+            if(bounce == 1u)
+            {
+                s.path = localToGlobalPath(ic, i);
+                s.rng.key = ic.keyLight; s.rng.path = s.path; s.rng.draw = 0u;
+                generateLightSample(sc, ic, s);
+            }
+            else loadSubPath(a.in, i, ic.keyLight, s);
+        }
+
+        Hit hit;
+        Bsdf bsdf;
+        f3 hitPoint = mk3(0.f);
+        bool storeVertex = false;
+        if(alive)
+        {
+            // origin offset instead of tmin; dist extended after the hit point is known
+            const f3 org = mulAddUnfused(s.origin, s.direction, SVCM_EPS_RAY);
+            nRays++;
+            alive = sceneIntersect(sc, org, s.direction, hit);
+            if(alive)
+            {
+                hitPoint = mulAddUnfused(org, s.direction, hit.dist);
+                hit.dist += SVCM_EPS_RAY;
+                bsdfSetup(sc, s.direction, hit.normal, hit.matID, bsdf);
+                alive = bsdf.isValid();
+            }
+            if(alive)
+            {
+                // MIS quantities at the vertex [tech. rep. (31)-(33) / (34)-(36)]
+                if(s.length > 1u || s.finiteLight) s.dVCM *= sqr(hit.dist);
+                const float invCos = fabsf(bsdf.cosThetaFix());
+                s.dVCM /= invCos; s.dVC /= invCos; s.dVM /= invCos;
+                storeVertex = !bsdf.isDelta() && (ic.useVC || ic.useVM);
+            }
+        }
+
+        // store the light vertex (PathVertex<true>) unless purely specular
+        const uint32_t vidx = warpAppend64(a.counters + CNT_LIGHT_VERTS, storeVertex);
+        if(storeVertex)
+        {
+            if(vidx < a.verts.capacity)
+            {
+                a.verts.posLen[vidx]   = mk4(hitPoint, __uint_as_float(s.length));
+                a.verts.thrVcm[vidx]   = mk4(s.throughput, s.dVCM);
+                a.verts.dirVm[vidx]    = mk4(bsdf.worldDirFix(), s.dVM);
+                a.verts.contProb[vidx] = bsdf.contProb;
+                a.verts.nrmVc[vidx]    = mk4(bsdf.frame.z, s.dVC);
+                a.verts.ldfMat[vidx]   = mk4(bsdf.localDirFix, __int_as_float(bsdf.matID));
+                const uint32_t l = globalToLocalPath(ic, s.path);
+                a.verts.pathVerts[size_t(s.extra) * ic.localPaths + l] = int32_t(vidx);
+                s.extra++;
+                a.pathVertCount[l] = uint8_t(s.extra);
+            }
+            else atomicAdd(a.counters + CNT_OVERFLOW, 1ull);
+        }
+
+        if(alive)
+        {
+            if(!bsdf.isDelta() && (ic.useVC || ic.lightTraceOnly) && (s.length + 1u >= ic.minLen))
+                connectToCamera(sc, ic, s, hitPoint, bsdf, a.accum, nShadow);
+
+            // terminate if the path would become too long after scattering
+            if(s.length + 2u > ic.maxLen) alive = false;
+            else alive = sampleScattering<true>(sc, ic, bsdf, hitPoint, s);
+            s.length++;
+        }
+
+        const uint32_t slot = warpAppend(a.queueCounts + bounce + 1u, alive);
+        if(alive) storeSubPath(a.out, slot, s);
+    }
+
+    warpCount(a.counters + CNT_LIGHT_RAYS, nRays);
+    warpCount(a.counters + CNT_SHADOW_RAYS, nShadow);
+}
+
+// ------------------------------------------------------------------------------------------
+// camera pass
+// ------------------------------------------------------------------------------------------
+
+// GenerateCameraSample, reference src/vertexcm.hxx:564-606 + Camera::GenerateRay
+// (src/camera.hxx:108-117). Returns false if the jittered sample rounds outside the image
+// (Framebuffer::AddColor would drop the whole path's colour, src/framebuffer.hxx:47-51).
+SVCM_D bool generateCameraSample(const DevScene &sc, const IterConst &ic, SubPath &s)
+{
+    const uint32_t x = s.path % uint32_t(ic.resX), y = s.path / uint32_t(ic.resX);
+    const float jx = s.rng.next(), jy = s.rng.next();
+    const float sx = float(x) + jx, sy = float(y) + jy;
+
+    const f3 camPos = ld3(sc.camPos);
+    const f3 worldRaster = transformPoint(sc.rasterToWorld, mk3(sx, sy, 0.f));
+    const f3 dir = normalize(worldRaster - camPos);
+
+    const float cosAtCamera = dot(ld3(sc.camFwd), dir);
+    const float imagePointToCameraDist = sc.imagePlaneDist / cosAtCamera;
+    const float cameraPdfW = sqr(imagePointToCameraDist) / cosAtCamera;
+
+    s.origin = camPos; s.direction = dir; s.throughput = mk3(1.f);
+    s.length = 1u; s.specular = true; s.finiteLight = false;
+    s.dVCM = ic.lightSubPathCount / cameraPdfW;
+    s.dVC = 0.f; s.dVM = 0.f;
+
+    if(sx < 0.f || sx >= sc.resX || sy < 0.f || sy >= sc.resY) return false;
+    s.extra = uint32_t(int(sx)) + uint32_t(int(sy)) * uint32_t(ic.resX);
+    return true;
+}
+
+// GetLightRadiance, reference src/vertexcm.hxx:617-658
+SVCM_D f3 getLightRadiance(const DevScene &sc, const IterConst &ic, const DevLight &light,
+                           const SubPath &s, f3 rayDir)
+{
+    const float lightPickProb = 1.f / float(sc.numLights);
+    float directPdfA, emissionPdfW;
+    const f3 radiance = lightRadiance(sc, light, rayDir, directPdfA, emissionPdfW);
+    if(iszero(radiance)) return mk3(0.f);
+    if(s.length == 1u) return radiance;                       // seen directly: no weighting
+    if(ic.useVM && !ic.useVC) return s.specular ? radiance : mk3(0.f);
+    directPdfA   *= lightPickProb;
+    emissionPdfW *= lightPickProb;
+    const float wCamera = directPdfA * s.dVCM + emissionPdfW * s.dVC;   // [tech. rep. (43)]
+    return (1.f / (1.f + wCamera)) * radiance;
+}
+
+// DirectIllumination, reference src/vertexcm.hxx:663-738
+SVCM_D f3 directIllumination(const DevScene &sc, const IterConst &ic, SubPath &s, f3 hitPoint,
+                             const Bsdf &bsdf, uint32_t &shadowRays)
+{
+    const int   lightCount = sc.numLights;
+    const float lightPickProb = 1.f / float(lightCount);
+    int lightID = int(s.rng.next() * float(lightCount));
+    const float rx = s.rng.next(), ry = s.rng.next();
+    lightID = min(lightID, lightCount - 1);
+    const DevLight &light = sc.lights[lightID];
+
+    f3 dirToLight;
+    float distance, directPdfW, emissionPdfW, cosAtLight;
+    const f3 radiance = lightIlluminate(sc, light, hitPoint, rx, ry, dirToLight, distance,
+                                        directPdfW, emissionPdfW, cosAtLight);
+    if(iszero(radiance)) return mk3(0.f);
+
+    float bsdfDirPdfW, bsdfRevPdfW, cosToLight;
+    const f3 bsdfFactor = bsdfEvaluate(sc, bsdf, dirToLight, cosToLight, bsdfDirPdfW, bsdfRevPdfW);
+    if(iszero(bsdfFactor)) return mk3(0.f);
+
+    const float contProb = bsdf.contProb;
+    bsdfDirPdfW *= lightIsDelta(light.type) ? 0.f : contProb;
+    bsdfRevPdfW *= contProb;
+
+    const float wLight  = bsdfDirPdfW / (lightPickProb * directPdfW);                 // (44)
+    const float wCamera = (emissionPdfW * cosToLight / (directPdfW * cosAtLight)) *
+        (ic.misVmWeightFactor + s.dVCM + s.dVC * bsdfRevPdfW);                         // (45)
+    const float misWeight = 1.f / (wLight + 1.f + wCamera);
+
+    const f3 contrib = (misWeight * cosToLight / (lightPickProb * directPdfW)) * (radiance * bsdfFactor);
+    if(iszero(contrib)) return mk3(0.f);
+    shadowRays++;
+    if(sceneOccluded(sc, hitPoint, dirToLight, distance)) return mk3(0.f);
+    return contrib;
+}
+
+// ConnectVertices, reference src/vertexcm.hxx:743-809; the light vertex's BSDF is rebuilt
+// from its stored normal / local direction / material (what BSDF<true>::Setup computed).
+SVCM_D f3 connectVertices(const DevScene &sc, const IterConst &ic, f3 lvPos, const Bsdf &lvBsdf,
+                          float lvdVCM, float lvdVC, const Bsdf &camBsdf, f3 camHit,
+                          const SubPath &s, uint32_t &shadowRays)
+{
+    f3 direction = lvPos - camHit;
+    const float dist2 = lensqr(direction);
+    const float distance = sqrtf(dist2);
+    direction = direction / distance;
+
+    float cosCamera, camDirPdfW, camRevPdfW;
+    const f3 camFactor = bsdfEvaluate(sc, camBsdf, direction, cosCamera, camDirPdfW, camRevPdfW);
+    if(iszero(camFactor)) return mk3(0.f);
+    camDirPdfW *= camBsdf.contProb;
+    camRevPdfW *= camBsdf.contProb;
+
+    float cosLight, lightDirPdfW, lightRevPdfW;
+    const f3 lightFactor = bsdfEvaluate(sc, lvBsdf, -direction, cosLight, lightDirPdfW, lightRevPdfW);
+    if(iszero(lightFactor)) return mk3(0.f);
+    lightDirPdfW *= lvBsdf.contProb;
+    lightRevPdfW *= lvBsdf.contProb;
+
+    const float geometryTerm = cosLight * cosCamera / dist2;
+    if(geometryTerm < 0.f) return mk3(0.f);
+
+    const float camDirPdfA   = pdfWtoA(camDirPdfW, distance, cosLight);
+    const float lightDirPdfA = pdfWtoA(lightDirPdfW, distance, cosCamera);
+
+    const float wLight  = camDirPdfA * (ic.misVmWeightFactor + lvdVCM + lvdVC * lightRevPdfW);   // (40)
+    const float wCamera = lightDirPdfA * (ic.misVmWeightFactor + s.dVCM + s.dVC * camRevPdfW);    // (41)
+    const float misWeight = 1.f / (wLight + 1.f + wCamera);
+
+    const f3 contrib = ((misWeight * geometryTerm) * camFactor) * lightFactor;
+    if(iszero(contrib)) return mk3(0.f);
+    shadowRays++;
+    if(sceneOccluded(sc, camHit, direction, distance)) return mk3(0.f);
+    return contrib;
+}
+
+// One bounce of every live camera sub-path: reference src/vertexcm.hxx:423-542 (loop body).
+// Merging is deferred: a non-delta vertex inside the light-vertex bbox appends a query
+// record that k_merge resolves after the whole camera pass (merging draws no random
+// numbers and does not steer the walk, so the split changes nothing but summation order).
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
+               const __grid_constant__ TraceArgs a, const uint32_t bounce)
+{
+    const uint32_t count = (bounce == 1u) ? ic.localPaths : a.queueCounts[bounce];
+    uint32_t nRays = 0u, nShadow = 0u;
+
+    f3 bbMin = mk3(0.f), bbMax = mk3(0.f);
+    if(ic.useVM)
+    {
+        bbMin = mk3(orderedToFloat(a.bboxBits[0]), orderedToFloat(a.bboxBits[1]), orderedToFloat(a.bboxBits[2]));
+        bbMax = mk3(orderedToFloat(a.bboxBits[3]), orderedToFloat(a.bboxBits[4]), orderedToFloat(a.bboxBits[5]));
+    }
+
+    for(uint32_t i0 = blockIdx.x * blockDim.x; i0 < count; i0 += gridDim.x * blockDim.x)
+    {
+        const uint32_t i = i0 + threadIdx.x;
+        bool alive = i < count;
+        SubPath s;
+        if(alive)
+        {
+            if(bounce == 1u)
+            {
+                s.path = localToGlobalPath(ic, i);
+                s.rng.key = ic.keyCamera; s.rng.path = s.path; s.rng.draw = 0u;
+                alive = generateCameraSample(sc, ic, s);
+            }
+            else loadSubPath(a.in, i, ic.keyCamera, s);
+        }
+
+        f3 color = mk3(0.f);
+        Hit hit;
+        Bsdf bsdf;
+        f3 hitPoint = mk3(0.f);
+        bool emitQuery = false;
+
+        if(alive)
+        {
+            const f3 org = mulAddUnfused(s.origin, s.direction, SVCM_EPS_RAY);
+            nRays++;
+            if(!sceneIntersect(sc, org, s.direction, hit))
+            {
+                // environment: BEFORE the MIS update (src/vertexcm.hxx:434-447)
+                if(sc.background >= 0 && s.length >= ic.minLen)
+                    color = color + s.throughput *
+                        getLightRadiance(sc, ic, sc.lights[sc.background], s, s.direction);
+                alive = false;
+            }
+            else
+            {
+                hitPoint = mulAddUnfused(org, s.direction, hit.dist);
+                hit.dist += SVCM_EPS_RAY;
+                bsdfSetup(sc, s.direction, hit.normal, hit.matID, bsdf);
+                alive = bsdf.isValid();
+            }
+        }
+
+        if(alive)
+        {
+            s.dVCM *= sqr(hit.dist);
+            const float invCos = fabsf(bsdf.cosThetaFix());
+            s.dVCM /= invCos; s.dVC /= invCos; s.dVM /= invCos;
+
+            const int lightID = sc.matToLight[hit.matID];
+            if(lightID >= 0)
+            {
+                // hit an emitter: AFTER the MIS update; lights do not reflect (:468-479)
+                if(s.length >= ic.minLen)
+                    color = color + s.throughput *
+                        getLightRadiance(sc, ic, sc.lights[min(lightID, sc.numLights - 1)], s, s.direction);
+                alive = false;
+            }
+            else if(s.length >= ic.maxLen) alive = false;
+        }
+
+        if(alive && !bsdf.isDelta())
+        {
+            if(ic.useVC)
+            {
+                // vertex connection: to a light source ...
+                if(s.length + 1u >= ic.minLen)
+                    color = color + s.throughput * directIllumination(sc, ic, s, hitPoint, bsdf, nShadow);
+
+                // ... and to the vertices of this pixel's own light sub-path (:498-526)
+                const uint32_t l = globalToLocalPath(ic, s.path);
+                const uint32_t nv = a.pathVertCount[l];
+                for(uint32_t k = 0; k < nv; k++)
+                {
+                    const int32_t vi = a.verts.pathVerts[size_t(k) * ic.localPaths + l];
+                    const float4 pl = a.verts.posLen[vi];
+                    const uint32_t lvLen = __float_as_uint(pl.w);
+                    if(lvLen + 1u + s.length < ic.minLen) continue;
+                    if(lvLen + 1u + s.length > ic.maxLen) break;      // stored in increasing length
+                    const float4 tv = a.verts.thrVcm[vi];
+                    const float4 nv4 = a.verts.nrmVc[vi];
+                    const float4 lm = a.verts.ldfMat[vi];
+                    Bsdf lvBsdf;
+                    lvBsdf.frame.setFromZ(xyz(nv4));
+                    lvBsdf.localDirFix = xyz(lm);
+                    lvBsdf.diffProb = lvBsdf.phongProb = lvBsdf.reflProb = lvBsdf.refrProb = 0.f;
+                    bsdfFromLocal(sc, __float_as_int(lm.w), lvBsdf);
+                    const f3 c = connectVertices(sc, ic, xyz(pl), lvBsdf, tv.w, nv4.w, bsdf, hitPoint, s, nShadow);
+                    color = color + (s.throughput * xyz(tv)) * c;
+                }
+            }
+            if(ic.useVM)
+            {
+                // HashGrid::Process early-out: query outside the particle bbox
+                // (reference src/hashgrid.hxx:116-122)
+                const f3 dMin = hitPoint - bbMin, dMax = bbMax - hitPoint;
+                emitQuery = !(dMin.x < 0.f || dMax.x < 0.f || dMin.y < 0.f || dMax.y < 0.f ||
+                              dMin.z < 0.f || dMax.z < 0.f);
+            }
+        }
+
+        const uint32_t qidx = warpAppend64(a.counters + CNT_QUERIES, emitQuery);
+        if(emitQuery)
+        {
+            if(qidx < a.queries.capacity)
+            {
+                a.queries.q0[qidx] = mk4(hitPoint, __uint_as_float(s.extra));
+                a.queries.q1[qidx] = mk4(hit.normal, __uint_as_float(s.length | (uint32_t(hit.matID) << 16)));
+                a.queries.q2[qidx] = mk4(bsdf.localDirFix, s.dVCM);
+                a.queries.q3[qidx] = mk4(s.throughput * ic.vmNormalization, s.dVM);
+            }
+            else atomicAdd(a.counters + CNT_OVERFLOW, 1ull);
+        }
+
+        if(alive)
+        {
+            // PPM merges only at the first non-specular vertex from the camera (:537)
+            if(ic.ppm && ic.useVM && !bsdf.isDelta()) alive = false;
+            else alive = sampleScattering<false>(sc, ic, bsdf, hitPoint, s);
+            s.length++;
+        }
+
+        if(!iszero(color)) addPixel(a.accum, s.extra, color);
+
+        const uint32_t slot = warpAppend(a.queueCounts + bounce + 1u, alive);
+        if(alive) storeSubPath(a.out, slot, s);
+    }
+
+    warpCount(a.counters + CNT_CAMERA_RAYS, nRays);
+    warpCount(a.counters + CNT_SHADOW_RAYS, nShadow);
+}
+
+// ------------------------------------------------------------------------------------------
+// hash grid build (HashGrid::Build, reference src/hashgrid.hxx:41-107)
+// ------------------------------------------------------------------------------------------
+
+SVCM_D uint32_t mergeSetTotal(const MergeSet &set)
+{
+    if(set.singleCount) return uint32_t(min(*set.singleCount, (unsigned long long)set.capacity));
+    return set.numSegs * set.segStride;
+}
+SVCM_D bool mergeSetValid(const MergeSet &set, uint32_t i)
+{
+    if(set.singleCount) return true;
+    const uint32_t seg = i / set.segStride;
+    return (i - seg * set.segStride) < set.segCount[seg];
+}
+
+// HashGrid::GetCellIndex(Vec3i), reference src/hashgrid.hxx:179-187
+SVCM_D uint32_t cellHash(int32_t cx, int32_t cy, int32_t cz, uint32_t numCells)
+{
+    return ((uint32_t(cx) * 73856093u) ^ (uint32_t(cy) * 19349663u) ^ (uint32_t(cz) * 83492791u)) % numCells;
+}
+
+// bounding box of the particles (reference src/hashgrid.hxx:50-61)
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_gridBBox(const __grid_constant__ MergeSet set, int32_t *bboxBits)
+{
+    f3 mn = mk3(1e36f), mx = mk3(-1e36f);
+    const uint32_t total = mergeSetTotal(set);
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    {
+        if(!mergeSetValid(set, i)) continue;
+        const float4 p = set.posLen[i];
+        mn = mk3(fminf(mn.x, p.x), fminf(mn.y, p.y), fminf(mn.z, p.z));
+        mx = mk3(fmaxf(mx.x, p.x), fmaxf(mx.y, p.y), fmaxf(mx.z, p.z));
+    }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1)
+    {
+        mn.x = fminf(mn.x, __shfl_xor_sync(FULL_MASK, mn.x, o));
+        mn.y = fminf(mn.y, __shfl_xor_sync(FULL_MASK, mn.y, o));
+        mn.z = fminf(mn.z, __shfl_xor_sync(FULL_MASK, mn.z, o));
+        mx.x = fmaxf(mx.x, __shfl_xor_sync(FULL_MASK, mx.x, o));
+        mx.y = fmaxf(mx.y, __shfl_xor_sync(FULL_MASK, mx.y, o));
+        mx.z = fmaxf(mx.z, __shfl_xor_sync(FULL_MASK, mx.z, o));
+    }
+    if(laneId() == 0u)
+    {
+        atomicMin(bboxBits + 0, floatToOrdered(mn.x));
+        atomicMin(bboxBits + 1, floatToOrdered(mn.y));
+        atomicMin(bboxBits + 2, floatToOrdered(mn.z));
+        atomicMax(bboxBits + 3, floatToOrdered(mx.x));
+        atomicMax(bboxBits + 4, floatToOrdered(mx.y));
+        atomicMax(bboxBits + 5, floatToOrdered(mx.z));
+    }
+}
+
+// cell key of every particle + per-cell histogram (reference src/hashgrid.hxx:67-71,189-202)
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_gridKeys(const __grid_constant__ MergeSet set, const int32_t *bboxBits, float invCellSize,
+           uint32_t numCells, uint32_t *cellKey, uint32_t *cellCount)
+{
+    const f3 bbMin = mk3(orderedToFloat(bboxBits[0]), orderedToFloat(bboxBits[1]), orderedToFloat(bboxBits[2]));
+    const uint32_t total = mergeSetTotal(set);
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    {
+        uint32_t key = 0xFFFFFFFFu;
+        if(mergeSetValid(set, i))
+        {
+            const float4 p = set.posLen[i];
+            const f3 distMin = xyz(p) - bbMin;
+            key = cellHash(int32_t(floorf(invCellSize * distMin.x)), int32_t(floorf(invCellSize * distMin.y)),
+                           int32_t(floorf(invCellSize * distMin.z)), numCells);
+            atomicAdd(cellCount + key, 1u);
+        }
+        cellKey[i] = key;
+    }
+}
+
+// exclusive prefix sum over the histogram (reference src/hashgrid.hxx:75-81), three kernels:
+// per-tile scan + tile totals, scan of the totals, add-back.
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SVCM_BLOCK * SCAN_ITEMS)
+
+SVCM_D uint32_t blockExclusiveScan(uint32_t v, uint32_t *smem, uint32_t &total)
+{
+    // exclusive scan of one value per thread across the block; total = block sum
+    const uint32_t lane = laneId(), warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for(int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o);
+        if(lane >= uint32_t(o)) inc += t;
+    }
+    if(lane == 31u) smem[warp] = inc;
+    __syncthreads();
+    if(warp == 0u)
+    {
+        uint32_t w = (lane < (blockDim.x >> 5)) ? smem[lane] : 0u;
+        uint32_t winc = w;
+#pragma unroll
+        for(int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(FULL_MASK, winc, o);
+            if(lane >= uint32_t(o)) winc += t;
+        }
+        smem[lane] = winc - w;            // exclusive warp offsets
+        if(lane == 31u) smem[32] = winc;  // block total
+    }
+    __syncthreads();
+    total = smem[32];
+    const uint32_t res = smem[warp] + inc - v;
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_scanTiles(uint32_t *data, uint32_t n, uint32_t *tileSums)
+{
+    __shared__ uint32_t smem[33];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], sum = 0u;
+#pragma unroll
+    for(int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? data[base + k] : 0u; sum += v[k]; }
+    uint32_t total;
+    uint32_t run = blockExclusiveScan(sum, smem, total);
+#pragma unroll
+    for(int k = 0; k < SCAN_ITEMS; k++) { if(base + k < n) data[base + k] = run; run += v[k]; }
+    if(threadIdx.x == 0) tileSums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_scanSums(uint32_t *tileSums, uint32_t numTiles)
+{
+    __shared__ uint32_t smem[33];
+    uint32_t carry = 0u;
+    for(uint32_t start = 0; start < numTiles; start += SCAN_TILE)
+    {
+        const uint32_t base = start + threadIdx.x * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS], sum = 0u;
+#pragma unroll
+        for(int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < numTiles) ? tileSums[base + k] : 0u; sum += v[k]; }
+        uint32_t total;
+        uint32_t run = carry + blockExclusiveScan(sum, smem, total);
+#pragma unroll
+        for(int k = 0; k < SCAN_ITEMS; k++) { if(base + k < numTiles) tileSums[base + k] = run; run += v[k]; }
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_scanAdd(uint32_t *data, uint32_t n, const uint32_t *tileSums)
+{
+    const uint32_t add = tileSums[blockIdx.x];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for(int k = 0; k < SCAN_ITEMS; k++) if(base + k < n) data[base + k] += add;
+}
+
+// scatter into cell order (reference src/hashgrid.hxx:83-88) — but the RECORDS move, not
+// just indices, so a range query later streams contiguous 16-byte positions instead of
+// gathering 120-byte AoS vertices through mIndices. Like the reference, the cursor IS the
+// cell-start array: afterwards cellCount[c] is the END of cell c (mCellEnds).
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_gridScatter(const __grid_constant__ MergeSet set, const __grid_constant__ GridBuffers g)
+{
+    const uint32_t total = mergeSetTotal(set);
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t key = g.cellKey[i];
+        if(key == 0xFFFFFFFFu) continue;
+        const uint32_t dst = atomicAdd(g.cellCount + key, 1u);
+        g.sPosLen[dst]   = set.posLen[i];
+        g.sThrVcm[dst]   = set.thrVcm[i];
+        g.sDirVm[dst]    = set.dirVm[i];
+        g.sContProb[dst] = set.contProb[i];
+        g.sIndex[dst]    = int32_t(i);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// merge: HashGrid::Process (reference src/hashgrid.hxx:110-169) with RangeQuery::Process
+// (src/vertexcm.hxx:130-169) as the per-particle body. G lanes cooperate on one query: the
+// 8 candidate cells' ranges are fetched by 8 lanes, prefix-summed with shuffles into ONE
+// virtual candidate list, and the lanes stride over it — consecutive lanes read consecutive
+// 16-byte positions of the cell-sorted array.
+// ------------------------------------------------------------------------------------------
+template<int G>
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_merge(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
+        const __grid_constant__ QueryStore qs, const unsigned long long *queryCountPtr,
+        const uint32_t hostQueryCount, const __grid_constant__ GridBuffers g, float *accum,
+        float *contribOut, int32_t *countsOut, unsigned long long *counters)
+{
+    static_assert(G == 8 || G == 16 || G == 32, "group size");
+    uint32_t nq = hostQueryCount;
+    if(queryCountPtr) nq = uint32_t(min(*queryCountPtr, (unsigned long long)qs.capacity));
+
+    const uint32_t lane = laneId();
+    const uint32_t gl = lane & (G - 1);                       // lane within the group
+    const uint32_t gbase = lane & ~uint32_t(G - 1);           // first lane of the group
+    const uint32_t gmask = (G == 32) ? FULL_MASK : (((1u << G) - 1u) << gbase);
+    const uint32_t groupsPerBlock = SVCM_BLOCK / G;
+    const uint32_t groupInBlock = threadIdx.x / G;
+
+    const f3 bbMin = mk3(orderedToFloat(g.bboxBits[0]), orderedToFloat(g.bboxBits[1]), orderedToFloat(g.bboxBits[2]));
+    const f3 bbMax = mk3(orderedToFloat(g.bboxBits[3]), orderedToFloat(g.bboxBits[4]), orderedToFloat(g.bboxBits[5]));
+    uint32_t nCand = 0u, nAcc = 0u;
+
+    for(uint32_t q = blockIdx.x * groupsPerBlock + groupInBlock; q < nq; q += gridDim.x * groupsPerBlock)
+    {
+        const float4 q0 = qs.q0[q], q1 = qs.q1[q], q2 = qs.q2[q], q3 = qs.q3[q];
+        const f3 qpos = xyz(q0);
+        const uint32_t lenMat = __float_as_uint(q1.w);
+        const uint32_t camLen = lenMat & 0xFFFFu;
+        const float camdVCM = q2.w, camdVM = q3.w;
+
+        // camera BSDF: BSDF<false>::Setup from the stored normal / local direction / material
+        Bsdf bsdf;
+        bsdf.frame.setFromZ(xyz(q1));
+        bsdf.localDirFix = xyz(q2);
+        bsdf.diffProb = bsdf.phongProb = bsdf.reflProb = bsdf.refrProb = 0.f;
+        bsdfFromLocal(sc, int32_t(lenMat >> 16), bsdf);
+        const SvcmMaterial &mat = sc.mats[lenMat >> 16];
+
+        // the 8 cells: the query's cell and its neighbours on the near side of each axis
+        const f3 cellPt = mk3(ic.invCellSize * (qpos.x - bbMin.x), ic.invCellSize * (qpos.y - bbMin.y),
+                              ic.invCellSize * (qpos.z - bbMin.z));
+        const f3 coordF = mk3(floorf(cellPt.x), floorf(cellPt.y), floorf(cellPt.z));
+        const int px = int(coordF.x), py = int(coordF.y), pz = int(coordF.z);
+        const int pxo = px + ((cellPt.x - coordF.x) < 0.5f ? -1 : +1);
+        const int pyo = py + ((cellPt.y - coordF.y) < 0.5f ? -1 : +1);
+        const int pzo = pz + ((cellPt.z - coordF.z) < 0.5f ? -1 : +1);
+
+        // early-out of HashGrid::Process for a query outside the particle bbox
+        // (src/hashgrid.hxx:116-122); the camera pass already filters, the kernel-level
+        // entry point relies on this test
+        const bool inside = !(qpos.x - bbMin.x < 0.f || bbMax.x - qpos.x < 0.f ||
+                              qpos.y - bbMin.y < 0.f || bbMax.y - qpos.y < 0.f ||
+                              qpos.z - bbMin.z < 0.f || bbMax.z - qpos.z < 0.f);
+
+        uint32_t myStart = 0u, myCount = 0u;
+        if(gl < 8u && inside)
+        {
+            const uint32_t h = cellHash((gl & 4u) ? pxo : px, (gl & 2u) ? pyo : py, (gl & 1u) ? pzo : pz,
+                                        ic.numCells);
+            myStart = (h == 0u) ? 0u : g.cellCount[h - 1u];   // GetCellRange, src/hashgrid.hxx:173-177
+            myCount = g.cellCount[h] - myStart;
+        }
+        // inclusive prefix over the 8 cell counts, then broadcast all 8 (start, prefix) pairs
+        uint32_t inc = myCount;
+#pragma unroll
+        for(int o = 1; o < 8; o <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(gmask, inc, o, G);
+            if(gl >= uint32_t(o)) inc += t;
+        }
+        uint32_t st[8], pe[8];                                 // start, inclusive prefix (end)
+#pragma unroll
+        for(int j = 0; j < 8; j++)
+        {
+            st[j] = __shfl_sync(gmask, myStart, j, G);
+            pe[j] = __shfl_sync(gmask, inc, j, G);
+        }
+        const uint32_t total = pe[7];
+
+        f3 contrib = mk3(0.f);
+        uint32_t accepted = 0u;
+        for(uint32_t v = gl; v < total; v += G)
+        {
+            // which of the 8 ranges holds virtual candidate v
+            uint32_t j = 0u;
+#pragma unroll
+            for(int k = 0; k < 7; k++) j += (v >= pe[k]) ? 1u : 0u;
+            uint32_t sj = st[0], bj = 0u;
+#pragma unroll
+            for(int k = 1; k < 8; k++) if(j == uint32_t(k)) { sj = st[k]; bj = pe[k - 1]; }
+            const uint32_t idx = sj + (v - bj);
+
+            const float4 pl = g.sPosLen[idx];
+            // |q - p|^2 <= r^2 with the reference's exact (unfused) evaluation order, so the
+            // accept decision is bit-identical to src/hashgrid.hxx:162-165 for equal inputs
+            const float dx = qpos.x - pl.x, dy = qpos.y - pl.y, dz = qpos.z - pl.z;
+            const float distSqr = __fadd_rn(__fadd_rn(__fadd_rn(0.f, __fmul_rn(dx, dx)), __fmul_rn(dy, dy)),
+                                            __fmul_rn(dz, dz));
+            if(distSqr <= ic.radiusSqr)
+            {
+                accepted++;
+                // RangeQuery::Process, reference src/vertexcm.hxx:130-169
+                const uint32_t lvLen = __float_as_uint(pl.w);
+                if(!((lvLen + camLen > ic.maxLen) || (lvLen + camLen < ic.minLen)))
+                {
+                    const float4 dv = g.sDirVm[idx];
+                    const f3 localDirGen = bsdf.frame.toLocal(xyz(dv));
+                    if(!(localDirGen.z * bsdf.localDirFix.z < 0.f))
+                    {
+                        float camDirPdfW, camRevPdfW;
+                        const f3 f = bsdfEvaluateLocal(mat, bsdf, localDirGen, camDirPdfW, camRevPdfW);
+                        if(!iszero(f))
+                        {
+                            const float4 tv = g.sThrVcm[idx];
+                            camDirPdfW *= bsdf.contProb;
+                            camRevPdfW *= g.sContProb[idx];      // the LIGHT vertex's RR probability
+                            const float wLight  = tv.w * ic.misVcWeightFactor + dv.w * camDirPdfW;       // (38)
+                            const float wCamera = camdVCM * ic.misVcWeightFactor + camdVM * camRevPdfW;  // (39)
+                            const float misWeight = ic.ppm ? 1.f : 1.f / (wLight + 1.f + wCamera);
+                            contrib = contrib + (misWeight * f) * xyz(tv);
+                        }
+                    }
+                }
+            }
+        }
+
+        // reduce over the group
+#pragma unroll
+        for(int o = G / 2; o > 0; o >>= 1)
+        {
+            contrib.x += __shfl_xor_sync(gmask, contrib.x, o, G);
+            contrib.y += __shfl_xor_sync(gmask, contrib.y, o, G);
+            contrib.z += __shfl_xor_sync(gmask, contrib.z, o, G);
+            accepted  += __shfl_xor_sync(gmask, accepted, o, G);
+        }
+        if(gl == 0u)
+        {
+            nCand += total; nAcc += accepted;
+            if(contribOut)
+            {
+                contribOut[3ull * q + 0] = contrib.x; contribOut[3ull * q + 1] = contrib.y;
+                contribOut[3ull * q + 2] = contrib.z;
+            }
+            if(countsOut) { countsOut[2ull * q] = int32_t(total); countsOut[2ull * q + 1] = int32_t(accepted); }
+            // color += cameraState.mThroughput * mVmNormalization * query.GetContrib()  (:534)
+            if(accum) addPixel(accum, __float_as_uint(q0.w), xyz(q3) * contrib);
+        }
+    }
+
+    if(counters)
+    {
+        warpCount(counters + CNT_CANDIDATES, nCand);
+        warpCount(counters + CNT_ACCEPTED, nAcc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel-level batch kernels (parity tests call the same device functions as the path)
+// ------------------------------------------------------------------------------------------
+__global__ void k_intersectBatch(const __grid_constant__ DevScene sc, const float *rays, int64_t count,
+                                 int32_t *hitOut, float *dist, float *normal, int32_t *matID, int32_t *lightID)
+{
+    for(int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x)
+    {
+        Hit hit;
+        const bool found = sceneIntersect(sc, ld3(rays + 6 * i), ld3(rays + 6 * i + 3), hit);
+        hitOut[i] = found ? hit.prim : -1;
+        dist[i] = found ? hit.dist : 1e36f;
+        normal[3 * i + 0] = found ? hit.normal.x : 0.f;
+        normal[3 * i + 1] = found ? hit.normal.y : 0.f;
+        normal[3 * i + 2] = found ? hit.normal.z : 0.f;
+        matID[i] = found ? hit.matID : -1;
+        lightID[i] = found ? sc.matToLight[hit.matID] : -1;
+    }
+}
+
+__global__ void k_occludedBatch(const __grid_constant__ DevScene sc, const float *seg, int64_t count, int32_t *occ)
+{
+    for(int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x)
+        occ[i] = sceneOccluded(sc, ld3(seg + 7 * i), ld3(seg + 7 * i + 3), seg[7 * i + 6]) ? 1 : 0;
+}
+
+__global__ void k_bsdfEvaluateBatch(const __grid_constant__ DevScene sc, const float *in, int64_t count, float *out)
+{
+    for(int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x)
+    {
+        const float *p = in + 10 * i; float *r = out + 8 * i;
+        Bsdf b;
+        bsdfSetup(sc, -ld3(p + 3), ld3(p), __float_as_int(p[9]), b);
+        for(int k = 0; k < 8; k++) r[k] = 0.f;
+        if(!b.isValid()) continue;
+        float cosGen, dirPdf, revPdf;
+        const f3 f = bsdfEvaluate(sc, b, ld3(p + 6), cosGen, dirPdf, revPdf);
+        r[0] = f.x; r[1] = f.y; r[2] = f.z;
+        r[3] = iszero(f) ? 0.f : cosGen;
+        r[4] = dirPdf; r[5] = revPdf; r[6] = b.contProb;
+        r[7] = float(1 | (b.isDelta() ? 2 : 0));
+    }
+}
+
+template<bool kLight>
+__global__ void k_bsdfSampleBatch(const __grid_constant__ DevScene sc, const float *in, int64_t count,
+                                  float *out, uint32_t *events)
+{
+    for(int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x)
+    {
+        const float *p = in + 10 * i; float *r = out + 8 * i;
+        Bsdf b;
+        bsdfSetup(sc, -ld3(p + 3), ld3(p), __float_as_int(p[9]), b);
+        for(int k = 0; k < 8; k++) r[k] = 0.f;
+        events[i] = 0u;
+        if(!b.isValid()) continue;
+        f3 dirGen = mk3(0.f); float pdfW, cosGen; uint32_t ev;
+        const f3 f = bsdfSample<kLight>(sc, b, p[6], p[7], p[8], dirGen, pdfW, cosGen, ev);
+        if(iszero(f)) continue;
+        r[0] = f.x; r[1] = f.y; r[2] = f.z; r[3] = dirGen.x; r[4] = dirGen.y; r[5] = dirGen.z;
+        r[6] = pdfW; r[7] = cosGen;
+        events[i] = ev;
+    }
+}
+
+__global__ void k_rngStream(uint32_t key, uint32_t firstPath, int paths, int draws, float *out)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if(p >= paths) return;
+    PathRng rng; rng.key = key; rng.path = firstPath + uint32_t(p); rng.draw = 0u;
+    for(int k = 0; k < draws; k++) out[size_t(p) * draws + k] = rng.next();
+}
+
+__global__ void k_packMergeVertices(const SvcmMergeVertex *v, int64_t count, float4 *posLen, float4 *thrVcm,
+                                    float4 *dirVm, float *contProb)
+{
+    for(int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x)
+    {
+        posLen[i] = make_float4(v[i].position[0], v[i].position[1], v[i].position[2], __uint_as_float(v[i].pathLength));
+        thrVcm[i] = make_float4(v[i].throughput[0], v[i].throughput[1], v[i].throughput[2], v[i].dVCM);
+        dirVm[i]  = make_float4(v[i].dirFix[0], v[i].dirFix[1], v[i].dirFix[2], v[i].dVM);
+        contProb[i] = v[i].contProb;
+    }
+}
+
+__global__ void k_packMergeQueries(const __grid_constant__ DevScene sc, const SvcmMergeQuery *q, int64_t count,
+                                   const __grid_constant__ QueryStore store)
+{
+    for(int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x)
+    {
+        // BSDF<false>::Setup exactly as the camera pass does it at a hit (ray.dir = -dirFix)
+        Bsdf b;
+        bsdfSetup(sc, -ld3(q[i].dirFix), ld3(q[i].normal), q[i].matID, b);
+        const bool usable = b.isValid() && !b.isDelta();
+        // an unusable vertex never issues a query in the path; here it must yield zero:
+        // park it outside any bbox
+        const f3 pos = usable ? ld3(q[i].position) : mk3(3e37f);
+        store.q0[i] = mk4(pos, __uint_as_float(uint32_t(i)));
+        store.q1[i] = mk4(ld3(q[i].normal), __uint_as_float(q[i].pathLength | (uint32_t(q[i].matID) << 16)));
+        store.q2[i] = mk4(b.localDirFix, q[i].dVCM);
+        store.q3[i] = mk4(mk3(1.f), q[i].dVM);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+static int g_numSMs = 0;
+static int numSMs()
+{
+    if(g_numSMs == 0)
+    {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_numSMs, cudaDevAttrMultiProcessorCount, dev);
+        if(g_numSMs <= 0) g_numSMs = 148;
+    }
+    return g_numSMs;
+}
+// persistent-style grid: a multiple of the SM count, capped by the work available
+static uint32_t gridFor(uint64_t items, int perBlock, int blocksPerSM)
+{
+    const uint64_t need = (items + uint64_t(perBlock) - 1) / uint64_t(perBlock);
+    const uint64_t cap = uint64_t(numSMs()) * uint64_t(blocksPerSM);
+    return uint32_t(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+void launchLightBounce(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t bounce,
+                       uint32_t maxItems, cudaStream_t stream)
+{
+    k_lightBounce<<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
+}
+
+void launchCameraBounce(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t bounce,
+                        uint32_t maxItems, cudaStream_t stream)
+{
+    k_cameraBounce<<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
+}
+
+int launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers &grid, cudaStream_t stream)
+{
+    const uint32_t n = ic.numCells + 1u;
+    // bbox init: (+1e36, -1e36) like the reference (src/hashgrid.hxx:50-51)
+    cudaMemcpyAsync(grid.bboxBits, grid.bboxInit, sizeof(int32_t) * 6, cudaMemcpyDeviceToDevice, stream);
+    cudaMemsetAsync(grid.cellCount, 0, sizeof(uint32_t) * n, stream);
+    int launches = 0;
+    const uint32_t maxTotal = set.singleCount ? set.capacity : set.numSegs * set.segStride;
+    if(maxTotal > 0)
+    {
+        const uint32_t gridN = gridFor(maxTotal, SVCM_BLOCK, 8);
+        k_gridBBox<<<gridN, SVCM_BLOCK, 0, stream>>>(set, grid.bboxBits);
+        k_gridKeys<<<gridN, SVCM_BLOCK, 0, stream>>>(set, grid.bboxBits, ic.invCellSize, ic.numCells,
+                                                     grid.cellKey, grid.cellCount);
+        launches += 2;
+    }
+    const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scanTiles<<<tiles, SVCM_BLOCK, 0, stream>>>(grid.cellCount, n, grid.blockSums);
+    k_scanSums<<<1, SVCM_BLOCK, 0, stream>>>(grid.blockSums, tiles);
+    k_scanAdd<<<tiles, SVCM_BLOCK, 0, stream>>>(grid.cellCount, n, grid.blockSums);
+    launches += 3;
+    if(maxTotal > 0)
+    {
+        k_gridScatter<<<gridFor(maxTotal, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(set, grid);
+        launches++;
+    }
+    return launches;
+}
+
+void launchMerge(const DevScene &sc, const IterConst &ic, const QueryStore &queries,
+                 const unsigned long long *queryCount, uint32_t hostQueryCount, const GridBuffers &grid,
+                 float *accum, float *contribOut, int32_t *countsOut, unsigned long long *counters,
+                 int groupSize, cudaStream_t stream)
+{
+    const uint64_t maxQueries = queryCount ? queries.capacity : hostQueryCount;
+    if(maxQueries == 0) return;
+    const uint32_t gridN = gridFor(maxQueries * uint64_t(groupSize), SVCM_BLOCK, 8);
+    if(groupSize == 32)
+        k_merge<32><<<gridN, SVCM_BLOCK, 0, stream>>>(sc, ic, queries, queryCount, hostQueryCount, grid, accum,
+                                                       contribOut, countsOut, counters);
+    else if(groupSize == 16)
+        k_merge<16><<<gridN, SVCM_BLOCK, 0, stream>>>(sc, ic, queries, queryCount, hostQueryCount, grid, accum,
+                                                       contribOut, countsOut, counters);
+    else
+        k_merge<8><<<gridN, SVCM_BLOCK, 0, stream>>>(sc, ic, queries, queryCount, hostQueryCount, grid, accum,
+                                                      contribOut, countsOut, counters);
+}
+
+void launchIntersectBatch(const DevScene &sc, const float *rays, int64_t count, int32_t *hit, float *dist,
+                          float *normal, int32_t *matID, int32_t *lightID, cudaStream_t stream)
+{
+    if(count <= 0) return;
+    k_intersectBatch<<<gridFor(count, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, rays, count, hit, dist, normal, matID, lightID);
+}
+void launchOccludedBatch(const DevScene &sc, const float *segments, int64_t count, int32_t *occluded, cudaStream_t stream)
+{
+    if(count <= 0) return;
+    k_occludedBatch<<<gridFor(count, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, segments, count, occluded);
+}
+void launchBsdfEvaluateBatch(const DevScene &sc, const float *in, int64_t count, int fixIsLight, float *out,
+                             cudaStream_t stream)
+{
+    (void)fixIsLight;   // Evaluate does not depend on the tracing direction (only SampleRefract does)
+    if(count <= 0) return;
+    k_bsdfEvaluateBatch<<<gridFor(count, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, in, count, out);
+}
+void launchBsdfSampleBatch(const DevScene &sc, const float *in, int64_t count, int fixIsLight, float *out,
+                           uint32_t *events, cudaStream_t stream)
+{
+    if(count <= 0) return;
+    const uint32_t gridN = gridFor(count, SVCM_BLOCK, 8);
+    if(fixIsLight) k_bsdfSampleBatch<true><<<gridN, SVCM_BLOCK, 0, stream>>>(sc, in, count, out, events);
+    else           k_bsdfSampleBatch<false><<<gridN, SVCM_BLOCK, 0, stream>>>(sc, in, count, out, events);
+}
+void launchRngStream(uint32_t key, uint32_t firstPath, int paths, int draws, float *out, cudaStream_t stream)
+{
+    if(paths <= 0) return;
+    k_rngStream<<<(paths + 127) / 128, 128, 0, stream>>>(key, firstPath, paths, draws, out);
+}
+void launchPackMergeVertices(const SvcmMergeVertex *verts, int64_t count, float4 *posLen, float4 *thrVcm,
+                             float4 *dirVm, float *contProb, cudaStream_t stream)
+{
+    if(count <= 0) return;
+    k_packMergeVertices<<<gridFor(count, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(verts, count, posLen, thrVcm, dirVm, contProb);
+}
+void launchPackMergeQueries(const DevScene &sc, const SvcmMergeQuery *queries, int64_t count, QueryStore store,
+                            cudaStream_t stream)
+{
+    if(count <= 0) return;
+    k_packMergeQueries<<<gridFor(count, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, queries, count, store);
+}
+
+} // namespace svcm

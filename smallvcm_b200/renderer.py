@@ -1,0 +1,291 @@
+"""ctypes host layer over libsvcm.so (include/svcm.h).
+
+Mirrors, name for name, what a user of the reference touches on this path:
+
+    reference (C++)                                   here
+    ------------------------------------------------  -----------------------------------------
+    Scene::LoadCornellBox + BuildSceneSphere          Scene.cornell_box(scene_id, w, h)
+      (src/scene.hxx:132,387; g_SceneConfigs          (svcm_scene_cornell_box)
+       src/config.hxx:146-151)
+    new VertexCM(scene, alg, radiusFactor,            VertexCM(scene, algorithm, radius_factor,
+                 radiusAlpha, seed)                            radius_alpha, seed)
+      (src/vertexcm.hxx:208-214)
+    renderer->mMaxPathLength / mMinPathLength         .max_path_length / .min_path_length
+      (assigned after construction, smallvcm.cxx:70)
+    renderer->RunIteration(i)   (vertexcm.hxx:284)    .run_iteration(i)
+    renderer->GetFramebuffer(fb) (renderer.hxx:49)    .get_framebuffer()  (accum / iterations)
+    renderer->WasUsed()          (renderer.hxx:58)    .was_used()
+
+There is no CPU fallback: if the library is missing or no CUDA device is present every
+computing call raises SvcmError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+SCENE_NAMES = {
+    0: "glossy small spheres + sun (directional)",
+    1: "glossy large mirror sphere + ceiling (area)",
+    2: "glossy small spheres + point",
+    3: "glossy small spheres + background (env. lighting)",
+}
+
+
+class SvcmError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("svcm error %d: %s" % (code, message))
+        self.code = code
+
+
+def library_path():
+    return os.environ.get("SVCM_LIBRARY", os.path.join(_HERE, "lib", "libsvcm.so"))
+
+
+def load_library():
+    """Loads libsvcm.so and binds every symbol of include/svcm.h. Raises if it is missing —
+    build it with `python -c "import __graft_entry__ as g; g.build()"` or
+    `make -C smallvcm_b200/csrc`."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise SvcmError(abi.E_STATE, "CUDA library not built: %s is missing (run make -C smallvcm_b200/csrc)" % path)
+        _LIB = abi.bind(C.CDLL(path))
+    return _LIB
+
+
+def _check(rc, handle=None):
+    if rc != 0:
+        msg = load_library().svcm_last_error(handle)
+        raise SvcmError(rc, msg.decode() if msg else "?")
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Scene:
+    """A flat scene (SvcmSceneDesc) and whatever owns its arrays."""
+
+    def __init__(self, desc, owner=None, free=None):
+        self.desc = desc
+        self._owner = owner
+        self._free = free
+
+    @classmethod
+    def cornell_box(cls, scene_id, width, height, mask=None):
+        """g_SceneConfigs[scene_id] (or an explicit BoxMask) at width x height."""
+        lib = load_library()
+        if mask is None:
+            mask = lib.svcm_scene_config_mask(scene_id)
+            if mask == 0:
+                raise SvcmError(abi.E_INVALID, "unknown scene id %r" % (scene_id,))
+        handle = C.c_void_p()
+        pdesc = abi.PSD()
+        _check(lib.svcm_scene_cornell_box(mask, width, height, C.byref(handle), C.byref(pdesc)))
+        return cls(pdesc.contents, owner=handle, free=lib.svcm_scene_free)
+
+    @property
+    def width(self):
+        return int(self.desc.camera.resolution[0])
+
+    @property
+    def height(self):
+        return int(self.desc.camera.resolution[1])
+
+    def __del__(self):
+        if self._free is not None and self._owner:
+            try:
+                self._free(self._owner)
+            except Exception:
+                pass
+            self._owner = None
+
+
+class VertexCM:
+    """The reference's VertexCM renderer interface on top of the C-ABI."""
+
+    def __init__(self, scene, algorithm, radius_factor=0.003, radius_alpha=0.75, seed=1234,
+                 device=0, rank=0, world_size=1):
+        self._lib = load_library()
+        self.scene = scene
+        if isinstance(algorithm, str):
+            algorithm = abi.ALGORITHMS[algorithm]
+        p = abi.Params()
+        p.algorithm, p.radiusFactor, p.radiusAlpha, p.seed = int(algorithm), radius_factor, radius_alpha, seed
+        p.device, p.rank, p.worldSize = device, rank, world_size
+        self._h = C.c_void_p()
+        _check(self._lib.svcm_create(C.byref(scene.desc), C.byref(p), C.byref(self._h)))
+        self.width, self.height = scene.width, scene.height
+        # AbstractRenderer's defaults (src/renderer.hxx:39-40); the driver overrides them
+        self.max_path_length = 2
+        self.min_path_length = 0
+        self.algorithm = int(algorithm)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.svcm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- the hot path ---------------------------------------------------------------------
+    def run_iteration(self, iteration):
+        self.run_iterations(iteration, 1)
+
+    def run_iterations(self, first, count):
+        _check(self._lib.svcm_run_iterations(self._h, first, count, self.min_path_length,
+                                             self.max_path_length), self._h)
+
+    def synchronize(self):
+        _check(self._lib.svcm_synchronize(self._h), self._h)
+
+    def accum(self, out=None):
+        """(accumulated image [H, W, 3] float32, iterations it holds)."""
+        if out is None:
+            out = np.empty((self.height, self.width, 3), np.float32)
+        n = C.c_int32()
+        _check(self._lib.svcm_download_accum(self._h, _ptr(out), C.byref(n)), self._h)
+        return out, n.value
+
+    def get_framebuffer(self):
+        img, n = self.accum()
+        if n > 0:
+            img *= np.float32(1.0 / n)
+        return img
+
+    def was_used(self):
+        return self.accum()[1] > 0
+
+    def clear(self):
+        _check(self._lib.svcm_clear_accum(self._h), self._h)
+
+    def stats(self):
+        s = abi.Stats()
+        _check(self._lib.svcm_get_stats(self._h, C.byref(s)), self._h)
+        return {name: getattr(s, name) for name, _ in abi.Stats._fields_}
+
+    def event_record(self, slot):
+        _check(self._lib.svcm_event_record(self._h, slot), self._h)
+
+    def event_elapsed_ms(self, start_slot, stop_slot):
+        ms = C.c_float()
+        _check(self._lib.svcm_event_elapsed_ms(self._h, start_slot, stop_slot, C.byref(ms)), self._h)
+        return ms.value
+
+    def set_option(self, option, value):
+        _check(self._lib.svcm_set_option(self._h, option, value), self._h)
+
+    # --- multi-GPU ------------------------------------------------------------------------
+    def comm_init(self, unique_id):
+        buf = (C.c_uint8 * abi.COMM_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        _check(self._lib.svcm_comm_init(self._h, buf), self._h)
+
+    def reduce_accum(self, root=0):
+        _check(self._lib.svcm_reduce_accum(self._h, root), self._h)
+
+
+def comm_unique_id():
+    buf = (C.c_uint8 * abi.COMM_ID_BYTES)()
+    _check(load_library().svcm_comm_unique_id(buf))
+    return bytes(buf)
+
+
+# ------------------------------------------------------------------------------------------
+# kernel-level entry points
+# ------------------------------------------------------------------------------------------
+class HashGrid:
+    def __init__(self, handle, count, num_cells):
+        self._h, self.count, self.num_cells = handle, count, num_cells
+        self._lib = load_library()
+
+    def download(self):
+        bbox = np.zeros(6, np.float32)
+        ends = np.zeros(self.num_cells, np.int32)
+        idx = np.zeros(self.count, np.int32)
+        _check(self._lib.svcm_hashgrid_download(self._h, _ptr(bbox), _ptr(ends), _ptr(idx)))
+        return bbox, ends, idx
+
+    def query(self, scene, queries, min_path_length, max_path_length, mis_vc_weight_factor, ppm,
+              want_counts=True):
+        q = np.ascontiguousarray(queries, abi.MERGE_QUERY_DTYPE)
+        contrib = np.zeros((len(q), 3), np.float32)
+        counts = np.zeros((len(q), 2), np.int32) if want_counts else None
+        _check(self._lib.svcm_hashgrid_query(self._h, C.byref(scene.desc), _ptr(q), len(q), min_path_length,
+                                             max_path_length, mis_vc_weight_factor, int(ppm), _ptr(contrib),
+                                             _ptr(counts)))
+        return (contrib, counts) if want_counts else contrib
+
+    def close(self):
+        if self._h:
+            self._lib.svcm_hashgrid_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def hashgrid_build(vertices, radius, num_cells, device=0):
+    v = np.ascontiguousarray(vertices, abi.MERGE_VERTEX_DTYPE)
+    h = C.c_void_p()
+    _check(load_library().svcm_hashgrid_build(_ptr(v), len(v), radius, num_cells, device, C.byref(h)))
+    return HashGrid(h, len(v), num_cells)
+
+
+def intersect_batch(scene, rays, device=0):
+    rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+    n = len(rays)
+    hit = np.zeros(n, np.int32); dist = np.zeros(n, np.float32); normal = np.zeros((n, 3), np.float32)
+    mat = np.zeros(n, np.int32); light = np.zeros(n, np.int32)
+    _check(load_library().svcm_intersect_batch(C.byref(scene.desc), _ptr(rays), n, device, _ptr(hit), _ptr(dist),
+                                               _ptr(normal), _ptr(mat), _ptr(light)))
+    return hit, dist, normal, mat, light
+
+
+def occluded_batch(scene, segments, device=0):
+    seg = np.ascontiguousarray(segments, np.float32).reshape(-1, 7)
+    occ = np.zeros(len(seg), np.int32)
+    _check(load_library().svcm_occluded_batch(C.byref(scene.desc), _ptr(seg), len(seg), device, _ptr(occ)))
+    return occ
+
+
+def bsdf_evaluate_batch(scene, items, fix_is_light, device=0):
+    items = np.ascontiguousarray(items, np.float32).reshape(-1, 10)
+    out = np.zeros((len(items), 8), np.float32)
+    _check(load_library().svcm_bsdf_evaluate_batch(C.byref(scene.desc), _ptr(items), len(items), int(fix_is_light),
+                                                   device, _ptr(out)))
+    return out
+
+
+def bsdf_sample_batch(scene, items, fix_is_light, device=0):
+    items = np.ascontiguousarray(items, np.float32).reshape(-1, 10)
+    out = np.zeros((len(items), 8), np.float32)
+    ev = np.zeros(len(items), np.uint32)
+    _check(load_library().svcm_bsdf_sample_batch(C.byref(scene.desc), _ptr(items), len(items), int(fix_is_light),
+                                                 device, _ptr(out), _ptr(ev)))
+    return out, ev
+
+
+def rng_stream(seed, iteration, phase, first_path, paths, draws):
+    out = np.zeros((paths, draws), np.float32)
+    _check(load_library().svcm_rng_stream(seed, iteration, phase, first_path, paths, draws, _ptr(out)))
+    return out
+
+
+def rng_stream_device(seed, iteration, phase, first_path, paths, draws, device=0):
+    out = np.zeros((paths, draws), np.float32)
+    _check(load_library().svcm_rng_stream_device(seed, iteration, phase, first_path, paths, draws, device, _ptr(out)))
+    return out
