@@ -166,16 +166,26 @@ SVCM_D bool hitTriangle(const DevPrim &t, f3 org, f3 dir, float tmax, float &oDi
     return false;
 }
 
+// dot product evaluated like the reference's Dot (src/math.hxx:129-130): ((0 + x) + y) + z
+// with every product and sum rounded on its own (no FMA contraction)
+SVCM_D float dotUnfused(f3 a, f3 b)
+{
+    return __fadd_rn(__fadd_rn(__fadd_rn(0.f, __fmul_rn(a.x, b.x)), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
+
 // Sphere::Intersect, reference src/geometry.hxx:198-237: A, B, C and the discriminant in
-// float, the roots in double (the reference's fix for grazing-ray epsilon leaks)
+// float, the roots in double (the reference's fix for grazing-ray epsilon leaks). The float
+// part is evaluated unfused, in the reference's order: B*B - 4*A*C cancels catastrophically
+// for grazing rays, so a contracted evaluation would move those hits by far more than an ulp
+// (there are at most two spheres per scene, the extra instructions are noise).
 SVCM_D bool hitSphere(const DevPrim &s, f3 org, f3 dir, float tmax, float &oDist)
 {
     const f3 to = org - ld3(s.v);
     const float radius = s.v[3];
-    const float A = dot(dir, dir);
-    const float B = 2.f * dot(dir, to);
-    const float C = dot(to, to) - (radius * radius);
-    const float discF = B * B - 4.f * A * C;
+    const float A = dotUnfused(dir, dir);
+    const float B = __fmul_rn(2.f, dotUnfused(dir, to));
+    const float C = __fsub_rn(dotUnfused(to, to), __fmul_rn(radius, radius));
+    const float discF = __fsub_rn(__fmul_rn(B, B), __fmul_rn(__fmul_rn(4.f, A), C));
     if(discF < 0.f) return false;
     const double discSqrt = sqrt(double(discF));
     const double q = (B < 0.f) ? ((-double(B) - discSqrt) / 2.0) : ((-double(B) + discSqrt) / 2.0);
@@ -209,7 +219,11 @@ SVCM_D bool sceneIntersect(const DevScene &sc, f3 org, f3 dir, Hit &hit)
     if(sc.prims[prim].type == SVCM_PRIM_TRIANGLE)
         hit.normal = ld3(sc.prims[prim].v + 9);
     else
-        hit.normal = normalize((org - ld3(sc.prims[prim].v)) + mk3(best) * dir);
+    {
+        // Normalize(transformedOrigin + Vec3f(resT) * aRay.dir), src/geometry.hxx:235 (unfused)
+        const f3 n = mulAddUnfused(org - ld3(sc.prims[prim].v), dir, best);
+        hit.normal = n / sqrtf(dotUnfused(n, n));
+    }
     return true;
 }
 
