@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — the headline benchmark: VCM Mpaths/s on the built-in Cornell box (BASELINE.json).
+
+Workload (config.workload): scene 1 (glossy floor, large mirror sphere, ceiling area light),
+algorithm vcm, 1024 x 1024, maxPathLength 10, radiusFactor 0.003, radiusAlpha 0.75, seed 1234 —
+the configuration BASELINE.json's metric is quoted on. One "step" = one VertexCM::RunIteration
+= W*H light sub-paths + W*H camera sub-paths; one "path" = one such pair (the reference's own
+unit, src/vertexcm.hxx:290-292). Mpaths/s = W*H*steps / seconds / 1e6.
+
+Our arm (default):
+  value     K iterations enqueued back to back on the renderer's stream, timed with CUDA events
+            on THAT stream (svcm_event_record), state resident in HBM, max over ranks.
+  e2e       the same metric through the reference-facing call sequence of
+            VertexCMGpu::RunIteration: svcm_run_iterations(1) + svcm_download_accum into a host
+            buffer every step (the non-virtual GetFramebuffer forces that copy), wall clock.
+  roofline  k_merge (the hash-grid range query + merge): algorithmic bytes
+            N_q*140 + N_cand*12 + N_acc*40 per launch over its CUDA-event time.
+  cpu_baseline  the reference's own OpenMP path (oracle/_ref/libsvcm_ref.so -> render(),
+            src/smallvcm.cxx:52) timed on this host's cores on a bounded sample; rank 0, N=1.
+N > 1 (torchrun): every iteration is pixel-sharded over the ranks (rows round-robin) with one
+  NCCL all-gather of the light vertices before the grid build; a step is N iterations, so each
+  GPU still traces W*H paths per step ("weak": per-GPU work fixed).
+
+--impl reference: times the UNMODIFIED reference's CPU implementation of the same path on the
+  same workload with all host threads (one private renderer per thread, one iteration each per
+  step — its own parallel model), or the oracle port if oracle/_ref was not built.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SCENE, ALG, WIDTH, HEIGHT, MAXLEN, MINLEN = 1, "vcm", 1024, 1024, 10, 0
+RADIUS_FACTOR, RADIUS_ALPHA, SEED = 0.003, 0.75, 1234
+WORKLOAD = "scene 1 (glossy large mirror sphere + ceiling area light) -a vcm %dx%d maxPathLength %d" % (WIDTH, HEIGHT, MAXLEN)
+METRIC, UNIT = "VCM Mpaths/s at 1024^2 scene 1", "Mpaths/s"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md recipe) sampled while the timed region runs
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def merge_algorithmic_bytes(nq, ncand, nacc):
+    """query record 64 B + 8 cell ranges x 8 B + result 12 B per query, 12 B per
+    distance test, 40 B of merge payload per accepted particle."""
+    return nq * 140 + ncand * 12 + nacc * 40
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own path on the host cores
+# ------------------------------------------------------------------------------------------------
+def host_threads():
+    cores = os.cpu_count() or 1
+    try:
+        avail_kb = [int(l.split()[1]) for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
+        # one private renderer per thread: ~0.6 GB at 1024^2 (vertices 120 B x 2.2 M + vectors + framebuffer)
+        cores = max(1, min(cores, int(avail_kb / 1024 / 1024 * 0.5 / 0.6)))
+    except Exception:
+        pass
+    return cores
+
+
+def cpu_reference_step(threads, iterations):
+    """One bounded sample: `iterations` iterations of the workload on `threads` threads.
+    Returns (Mpaths/s, seconds, kind)."""
+    import oracle_api as oa
+    if oa.have_ref():
+        secs, _ = oa.ref_render(SCENE, ALG, WIDTH, HEIGHT, iterations, threads=threads, base_seed=SEED,
+                                max_path_length=MAXLEN, min_path_length=MINLEN, radius_factor=RADIUS_FACTOR,
+                                radius_alpha=RADIUS_ALPHA, want_image=False)
+        kind = "reference"
+    else:
+        import smallvcm_b200 as sv
+        scene = sv.Scene.cornell_box(SCENE, WIDTH, HEIGHT)
+        secs, _ = oa.oracle_render(scene, sv.abi.ALGORITHMS[ALG], iterations, threads, base_seed=SEED, rng_mode=0,
+                                   max_path_length=MAXLEN, min_path_length=MINLEN, radius_factor=RADIUS_FACTOR,
+                                   radius_alpha=RADIUS_ALPHA, want_image=False)
+        kind = "port"
+    return WIDTH * HEIGHT * iterations / secs / 1e6, secs, kind
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    threads = host_threads()
+    # the reference parallelises over ITERATIONS (src/smallvcm.cxx:99-108): one step = one
+    # render() call with one iteration per thread
+    iters = threads
+    for _ in range(args.warmup):
+        cpu_reference_step(threads, iters)
+    t0 = time.perf_counter()
+    kind = "reference"
+    for _ in range(args.steps):
+        _, _, kind = cpu_reference_step(threads, iters)
+    secs = time.perf_counter() - t0
+    value = WIDTH * HEIGHT * iters * args.steps / secs / 1e6
+    sample = "%d iterations of the full %dx%d workload per step, one private renderer per thread (%s)" % (
+        iters, WIDTH, HEIGHT, "reference render(), src/smallvcm.cxx:52" if kind == "reference" else "oracle port")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3 / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "paths_per_step": WIDTH * HEIGHT * iters, "seed": SEED,
+                       "radiusFactor": RADIUS_FACTOR, "radiusAlpha": RADIUS_ALPHA},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import numpy as np
+    import smallvcm_b200 as sv
+    from smallvcm_b200 import abi, dist as D
+
+    rank, local_rank, world = D.env_rank()
+    if world != args.gpus and world > 1:
+        raise SystemExit("WORLD_SIZE %d != --gpus %d" % (world, args.gpus))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("--gpus %d needs one process per GPU: launch with torch.distributed.run" % args.gpus)
+    device = local_rank
+    tdev = None
+    if world > 1:
+        import torch
+        torch.cuda.set_device(device)
+        tdev = "cuda:%d" % device
+        D.init_process_group("nccl")
+
+    scene = sv.Scene.cornell_box(SCENE, WIDTH, HEIGHT)
+    r = sv.VertexCM(scene, ALG, radius_factor=RADIUS_FACTOR, radius_alpha=RADIUS_ALPHA, seed=SEED, device=device,
+                    rank=rank, world_size=world)
+    r.max_path_length, r.min_path_length = MAXLEN, MINLEN
+    r.set_option(abi.OPT_PROFILE, 1)
+    if world > 1:
+        uid = sv.comm_unique_id() if rank == 0 else None
+        r.comm_init(D.broadcast_bytes(uid, abi.COMM_ID_BYTES, 0, tdev))
+
+    iters_per_step = world            # weak scaling: every GPU traces W*H paths per step
+    paths_per_step = WIDTH * HEIGHT * iters_per_step
+    next_iter = 0
+
+    def run_steps(n):
+        nonlocal next_iter
+        r.run_iterations(next_iter, n * iters_per_step)
+        next_iter += n * iters_per_step
+
+    def sync_all():
+        r.synchronize()
+        if world > 1:
+            D.barrier(tdev)
+
+    # ---- warm-up -------------------------------------------------------------------------------
+    run_steps(args.warmup)
+    sync_all()
+    r.profile()                        # drop warm-up from the accumulated profile
+
+    # ---- timed: K steps, device time on the launching stream, max over ranks -------------------
+    clocks = ClockSampler(device)
+    if rank == 0:
+        clocks.start()
+    sync_all()
+    r.event_record(0)
+    run_steps(args.steps)
+    r.event_record(1)
+    ms = r.event_elapsed_ms(0, 1)
+    sync_all()
+    clk = clocks.stop() if rank == 0 else None
+    prof = r.profile()
+    if world > 1:
+        ms = D.max_over_ranks(ms, tdev)
+    value = paths_per_step * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- roofline of the merge kernel (per launch = per iteration) ------------------------------
+    n = max(1, prof["timedIterations"])
+    nq, ncand, nacc = prof["mergeQueries"] / n, prof["mergeCandidates"] / n, prof["mergeAccepted"] / n
+    merge_ms = prof["msMerge"] / n
+    peak, peak_kind = measured_peak_gbs()
+    achieved = merge_algorithmic_bytes(nq, ncand, nacc) / (merge_ms * 1e-3) / 1e9 if merge_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "merge_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"kernel": "k_merge (HashGrid::Process + RangeQuery::Process)", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
+                "ms_per_launch": merge_ms, "queries": nq, "candidates": ncand, "accepted": nacc,
+                "algorithmic_bytes_per_launch": merge_algorithmic_bytes(nq, ncand, nacc),
+                "stage_ms_per_iteration": {k: prof[k] / n for k in ("msLightTrace", "msGather", "msGridBuild",
+                                                                     "msCameraTrace", "msMerge", "msTotal")}}
+    launches = prof["kernelLaunches"]
+
+    # ---- e2e: the plugin's call sequence with a HOST framebuffer every step ---------------------
+    host_fb = np.empty((HEIGHT, WIDTH, 3), np.float32)
+    lib = sv.load_library()
+    lib.svcm_host_register(host_fb.ctypes.data, host_fb.nbytes)     # what VertexCMGpu does once
+    st = r.stats()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(iters_per_step):
+            r.run_iterations(next_iter, 1)
+            next_iter += 1
+            r.accum(host_fb)                                          # D2H of the accumulated image
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        e2e_s = D.max_over_ranks(e2e_s, tdev)
+    lib.svcm_host_unregister(host_fb.ctypes.data)
+    e2e = {"value": paths_per_step * args.steps / e2e_s / 1e6, "unit": UNIT,
+           "h2d_bytes_per_step": int(st["kernelLaunches"] * st["paramBytesPerLaunch"] * iters_per_step),
+           "d2h_bytes_per_step": int((host_fb.nbytes + 64) * iters_per_step),
+           "note": "svcm_run_iterations(1) + svcm_download_accum per iteration, as VertexCMGpu::RunIteration; "
+                   "inputs of a step are the iteration index and the kernel parameter blocks (scene + constants)"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
+        v, secs, kind = cpu_reference_step(threads, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": "%d iterations of the full %dx%d workload, one private renderer and one iteration per "
+                         "thread (the reference's own OpenMP model, src/smallvcm.cxx:61-108), %.1f s wall"
+                         % (threads, WIDTH, HEIGHT, secs)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "paths_per_step": paths_per_step,
+                           "iterations_per_step": iters_per_step, "seed": SEED, "radiusFactor": RADIUS_FACTOR,
+                           "radiusAlpha": RADIUS_ALPHA,
+                           "parallelism": "1 GPU" if world == 1 else
+                           "pixel rows sharded over %d GPUs, NCCL all-gather of light vertices per iteration" % world,
+                           "l2": "per-iteration working set (path state, light vertices, queries, grid: ~0.6 GB) exceeds the 126 MB L2; no flush needed"},
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    r.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -192,12 +192,30 @@ typedef struct SvcmStats {
     float   msCameraTrace;
     float   msMerge;
     float   msTotal;
-    int32_t kernelLaunches;   /* kernels launched for that iteration                   */
+    int32_t kernelLaunches;   /* this library's kernels launched for that iteration    */
+    int32_t paramBytesPerLaunch; /* bytes of kernel parameters (scene + constants) a trace
+                                    kernel launch carries host -> device               */
 } SvcmStats;
+
+/* Sums over every iteration run since the previous svcm_get_profile call (at most the last
+ * SVCM_PROFILE_RING iterations are retained): workload counters always, stage times only
+ * while SVCM_OPT_PROFILE is on. Lets a caller time K iterations without synchronising
+ * between them and still get per-kernel averages for the roofline arithmetic. */
+#define SVCM_PROFILE_RING 256
+typedef struct SvcmProfile {
+    int32_t iterations;       /* iterations summed here                                */
+    int32_t timedIterations;  /* of which carried stage timings                        */
+    int64_t lightVertices, mergeQueries, mergeCandidates, mergeAccepted;
+    int64_t lightRays, cameraRays, shadowRays;
+    int64_t kernelLaunches;
+    double  msLightTrace, msGather, msGridBuild, msCameraTrace, msMerge, msTotal;
+} SvcmProfile;
 
 enum {
     SVCM_OPT_PROFILE       = 1, /* 0/1: record per-stage CUDA events                   */
-    SVCM_OPT_MERGE_GROUP   = 2, /* lanes cooperating on one range query: 8, 16 or 32   */
+    SVCM_OPT_MERGE_GROUP   = 2, /* merge kernel: 1 = one lane per range query with warp
+                                   compaction of accepted pairs (default); 8, 16, 32 =
+                                   that many lanes cooperating on one query            */
     SVCM_OPT_COUNTERS      = 3  /* 0/1: maintain N_cand/N_acc counters (small cost)    */
 };
 
@@ -251,6 +269,7 @@ SVCM_API int svcm_download_accum(svcm_renderer *r, float *rgb, int32_t *iteratio
 SVCM_API int svcm_clear_accum(svcm_renderer *r);
 
 SVCM_API int svcm_get_stats(svcm_renderer *r, SvcmStats *out);
+SVCM_API int svcm_get_profile(svcm_renderer *r, SvcmProfile *out);
 
 /* Page-locks / releases caller memory (cudaHostRegister) so that svcm_download_accum into it
  * runs at DMA speed; optional. svcm_device_count returns the number of CUDA devices (0 if

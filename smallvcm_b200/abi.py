@@ -70,7 +70,16 @@ class Stats(C.Structure):
                 ("lightRays", i64), ("shadowRays", i64), ("radius", f32),
                 ("msLightTrace", f32), ("msGather", f32), ("msGridBuild", f32),
                 ("msCameraTrace", f32), ("msMerge", f32), ("msTotal", f32),
-                ("kernelLaunches", i32)]
+                ("kernelLaunches", i32), ("paramBytesPerLaunch", i32)]
+
+
+class Profile(C.Structure):
+    _fields_ = [("iterations", i32), ("timedIterations", i32), ("lightVertices", i64),
+                ("mergeQueries", i64), ("mergeCandidates", i64), ("mergeAccepted", i64),
+                ("lightRays", i64), ("cameraRays", i64), ("shadowRays", i64),
+                ("kernelLaunches", i64), ("msLightTrace", C.c_double), ("msGather", C.c_double),
+                ("msGridBuild", C.c_double), ("msCameraTrace", C.c_double),
+                ("msMerge", C.c_double), ("msTotal", C.c_double)]
 
 
 class MergeVertex(C.Structure):
@@ -108,6 +117,7 @@ PROTOTYPES = {
     "svcm_download_accum": (i32, [VP, VP, C.POINTER(i32)]),
     "svcm_clear_accum": (i32, [VP]),
     "svcm_get_stats": (i32, [VP, C.POINTER(Stats)]),
+    "svcm_get_profile": (i32, [VP, C.POINTER(Profile)]),
     "svcm_host_register": (i32, [VP, C.c_size_t]),
     "svcm_host_unregister": (i32, [VP]),
     "svcm_device_count": (i32, []),

@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 #include <mutex>
+#include <chrono>
 #include "svcm.h"
 #include "svcm_internal.h"
 
@@ -97,8 +98,13 @@ struct svcm_renderer
     uint32_t  vertSlots;            // rows of verts.pathVerts
     uint8_t  *pathVertCount;
     QueryStore queries;
+    ShadowQueue shadow;             // counts: [2 * countsAlloc] (light bounces, then camera bounces)
     unsigned long long *counters;   // CNT_WORDS
-    unsigned long long *hostCounters; // pinned mirror of the last iteration
+    unsigned long long *hostCounters; // pinned ring [SVCM_PROFILE_RING][CNT_WORDS]
+    int       ringLaunches[SVCM_PROFILE_RING];
+    bool      ringTimed[SVCM_PROFILE_RING];
+    long long ringHead;             // iterations recorded so far
+    long long ringTail;             // first iteration not yet returned by svcm_get_profile
     float    *accum;
     GridBuffers grid;
     uint32_t  gridCells, gridCapacity;
@@ -113,9 +119,8 @@ struct svcm_renderer
     int  iterationsDone;
     int  mergeGroup;
     bool profile;
-    cudaEvent_t ev[6];
+    cudaEvent_t (*ev)[6];          // [SVCM_PROFILE_RING][6], created when profiling is enabled
     cudaEvent_t userEv[SVCM_NUM_USER_EVENTS];
-    bool evValid;
     SvcmStats stats;
     bool statsPending;
     int  lastLaunches;
@@ -290,10 +295,22 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
     const uint32_t needCounts = camBounces + 3u;
     if(needCounts > r->countsAlloc)
     {
-        devFree(r->queueCountsLight); devFree(r->queueCountsCamera);
+        devFree(r->queueCountsLight); devFree(r->queueCountsCamera); devFree(r->shadow.counts);
         if((rc = devAlloc(r, &r->queueCountsLight, needCounts))) return rc;
         if((rc = devAlloc(r, &r->queueCountsCamera, needCounts))) return rc;
+        if((rc = devAlloc(r, &r->shadow.counts, size_t(needCounts) * 2))) return rc;
         r->countsAlloc = needCounts;
+    }
+    if(r->shadow.capacity == 0 && (r->useVC || r->lightTraceOnly))
+    {
+        // one bounce queues at most (1 + stored vertices of the path) segments per camera path
+        // and one per light path; 4 per path covers the measured mix (scene 1 vcm: 3.0 on the
+        // first bounce), anything beyond is traced inline by the producer
+        const uint64_t cap = std::min<uint64_t>(uint64_t(r->localPaths) * 4u, 0xFFFFFF00u);
+        if((rc = devAlloc(r, &r->shadow.r0, cap))) return rc;
+        if((rc = devAlloc(r, &r->shadow.r1, cap))) return rc;
+        if((rc = devAlloc(r, &r->shadow.r2, cap))) return rc;
+        r->shadow.capacity = uint32_t(cap);
     }
 
     size_t freeB = 0, totalB = 0;
@@ -445,24 +462,37 @@ int gatherLightVertices(svcm_renderer *r, MergeSet &set)
 }
 
 // One iteration: the kernel schedule that replaces the two serial per-pixel loops
+static double hostNowMs()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t maxLen)
 {
+    static const bool traceHost = getenv("SVCM_TRACE_HOST") != NULL;
+    double th[8] = { 0 }; th[0] = hostNowMs();
     IterConst ic;
     iterationConstants(r, iteration, minLen, maxLen, ic);
     cudaStream_t st = r->stream;
     int launches = 0;
+    const int slot = int(r->ringHead % SVCM_PROFILE_RING);
+    const bool timed = r->profile && r->ev != NULL;
+    cudaEvent_t *ev = timed ? r->ev[slot] : NULL;
 
     SVCM_CUDA(r, cudaMemsetAsync(r->counters, 0, sizeof(unsigned long long) * CNT_WORDS, st));
     SVCM_CUDA(r, cudaMemsetAsync(r->queueCountsLight, 0, sizeof(uint32_t) * r->countsAlloc, st));
     SVCM_CUDA(r, cudaMemsetAsync(r->queueCountsCamera, 0, sizeof(uint32_t) * r->countsAlloc, st));
+    SVCM_CUDA(r, cudaMemsetAsync(r->shadow.counts, 0, sizeof(uint32_t) * 2 * r->countsAlloc, st));
     if(r->useVC) SVCM_CUDA(r, cudaMemsetAsync(r->pathVertCount, 0, r->localPaths, st));
-    if(r->profile) cudaEventRecord(r->ev[0], st);
+    if(timed) cudaEventRecord(ev[0], st);
+    th[1] = hostNowMs();
 
     TraceArgs a;
     memset(&a, 0, sizeof(a));
     a.verts = r->verts;
     a.pathVertCount = r->pathVertCount;
     a.queries = r->queries;
+    a.shadow = r->shadow;
     a.counters = r->counters;
     a.accum = r->accum;
     a.bboxBits = r->grid.bboxBits;
@@ -475,11 +505,17 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
         a.in = r->queue[(b + 1) & 1]; a.out = r->queue[b & 1];
         launchLightBounce(r->scene, ic, a, b, r->localPaths, st);
         launches++;
+        if(r->useVC || r->lightTraceOnly)
+        {
+            launchShadow(r->scene, ic, a, b, r->localPaths, st);
+            launches++;
+        }
     }
-    if(r->profile) cudaEventRecord(r->ev[1], st);
+    if(timed) cudaEventRecord(ev[1], st);
+    th[2] = hostNowMs();
 
     // ---- hash grid over ALL light vertices (src/vertexcm.hxx:403-408) ----------------------
-    if(r->profile) cudaEventRecord(r->ev[2], st);
+    if(timed) cudaEventRecord(ev[2], st);
     if(r->useVM)
     {
         MergeSet set;
@@ -487,8 +523,7 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
         {
             const int rc = gatherLightVertices(r, set);
             if(rc) return rc;
-            launches++;
-            if(r->profile) cudaEventRecord(r->ev[2], st);
+            if(timed) cudaEventRecord(ev[2], st);
         }
         else
         {
@@ -501,35 +536,50 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
         }
         launches += launchGridBuild(ic, set, r->grid, st);
     }
-    if(r->profile) cudaEventRecord(r->ev[3], st);
+    if(timed) cudaEventRecord(ev[3], st);
+    th[3] = hostNowMs();
 
     // ---- camera sub-paths (src/vertexcm.hxx:415-545) ---------------------------------------
     if(!r->lightTraceOnly)
     {
         const uint32_t camBounces = std::max(1u, maxLen);
         a.queueCounts = r->queueCountsCamera;
+        a.shadow.counts = r->shadow.counts + r->countsAlloc;
         for(uint32_t b = 1; b <= camBounces; b++)
         {
             a.in = r->queue[(b + 1) & 1]; a.out = r->queue[b & 1];
             launchCameraBounce(r->scene, ic, a, b, r->localPaths, st);
             launches++;
+            if(r->useVC && b < camBounces)     // the last camera bounce cannot connect (length == maxLen)
+            {
+                launchShadow(r->scene, ic, a, b, r->shadow.capacity, st);
+                launches++;
+            }
         }
     }
-    if(r->profile) cudaEventRecord(r->ev[4], st);
+    if(timed) cudaEventRecord(ev[4], st);
+    th[4] = hostNowMs();
 
     // ---- deferred merging of all queued camera vertices ------------------------------------
     if(r->useVM && !r->lightTraceOnly)
     {
         launchMerge(r->scene, ic, r->queries, r->counters + CNT_QUERIES, 0, r->grid, r->accum, NULL, NULL,
-                    r->counters, r->mergeGroup, st);
+                    r->counters, r->mergeGroup, r->gridCapacity, st);
         launches++;
     }
-    if(r->profile) cudaEventRecord(r->ev[5], st);
+    if(timed) cudaEventRecord(ev[5], st);
 
-    SVCM_CUDA(r, cudaMemcpyAsync(r->hostCounters, r->counters, sizeof(unsigned long long) * CNT_WORDS,
-                                 cudaMemcpyDeviceToHost, st));
+    SVCM_CUDA(r, cudaMemcpyAsync(r->hostCounters + size_t(slot) * CNT_WORDS, r->counters,
+                                 sizeof(unsigned long long) * CNT_WORDS, cudaMemcpyDeviceToHost, st));
     SVCM_CUDA(r, cudaGetLastError());
-    r->evValid = r->profile;
+    th[5] = hostNowMs();
+    if(traceHost)
+        fprintf(stderr, "[svcm host] it %d: setup %.3f light %.3f grid %.3f camera %.3f merge+copy %.3f ms\n", iteration,
+                th[1] - th[0], th[2] - th[1], th[3] - th[2], th[4] - th[3], th[5] - th[4]);
+    r->ringLaunches[slot] = launches;
+    r->ringTimed[slot] = timed;
+    r->ringHead++;
+    if(r->ringHead - r->ringTail > SVCM_PROFILE_RING) r->ringTail = r->ringHead - SVCM_PROFILE_RING;
     r->stats.radius = ic.radius;
     r->statsPending = true;
     r->lastLaunches = launches;
@@ -540,7 +590,8 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
 int finishStats(svcm_renderer *r)
 {
     if(!r->statsPending) return SVCM_OK;
-    const unsigned long long *c = r->hostCounters;
+    const int slot = int((r->ringHead - 1) % SVCM_PROFILE_RING);
+    const unsigned long long *c = r->hostCounters + size_t(slot) * CNT_WORDS;
     SvcmStats &s = r->stats;
     s.paths = r->paths; s.localPaths = r->localPaths;
     s.localLightVertices = (int64_t)c[CNT_LIGHT_VERTS];
@@ -557,19 +608,25 @@ int finishStats(svcm_renderer *r)
     s.cameraRays = (int64_t)c[CNT_CAMERA_RAYS];
     s.shadowRays = (int64_t)c[CNT_SHADOW_RAYS];
     s.kernelLaunches = r->lastLaunches;
-    if(r->evValid)
+    s.paramBytesPerLaunch = int32_t(sizeof(DevScene) + sizeof(IterConst) + sizeof(TraceArgs) + 4);
+    if(r->ringTimed[slot])
     {
-        cudaEventElapsedTime(&s.msLightTrace, r->ev[0], r->ev[1]);
-        cudaEventElapsedTime(&s.msGather, r->ev[1], r->ev[2]);
-        cudaEventElapsedTime(&s.msGridBuild, r->ev[2], r->ev[3]);
-        cudaEventElapsedTime(&s.msCameraTrace, r->ev[3], r->ev[4]);
-        cudaEventElapsedTime(&s.msMerge, r->ev[4], r->ev[5]);
-        cudaEventElapsedTime(&s.msTotal, r->ev[0], r->ev[5]);
+        cudaEvent_t *ev = r->ev[slot];
+        cudaEventElapsedTime(&s.msLightTrace, ev[0], ev[1]);
+        cudaEventElapsedTime(&s.msGather, ev[1], ev[2]);
+        cudaEventElapsedTime(&s.msGridBuild, ev[2], ev[3]);
+        cudaEventElapsedTime(&s.msCameraTrace, ev[3], ev[4]);
+        cudaEventElapsedTime(&s.msMerge, ev[4], ev[5]);
+        cudaEventElapsedTime(&s.msTotal, ev[0], ev[5]);
     }
     r->statsPending = false;
-    if(c[CNT_OVERFLOW])
+    // any iteration of the ring that dropped records poisons the image: report it
+    unsigned long long overflow = 0;
+    for(long long it = r->ringTail; it < r->ringHead; it++)
+        overflow += r->hostCounters[size_t(it % SVCM_PROFILE_RING) * CNT_WORDS + CNT_OVERFLOW];
+    if(overflow)
         return fail(r, SVCM_E_NOMEM, "light-vertex or query store overflowed (%llu records dropped): "
-                    "not enough device memory for this resolution / path length", c[CNT_OVERFLOW]);
+                    "not enough device memory for this resolution / path length", overflow);
     return SVCM_OK;
 }
 
@@ -603,12 +660,15 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     r->queueCountsLight = r->queueCountsCamera = NULL; r->countsAlloc = 0;
     memset(&r->verts, 0, sizeof(r->verts)); r->vertSlots = 0; r->pathVertCount = NULL;
     memset(&r->queries, 0, sizeof(r->queries));
+    memset(&r->shadow, 0, sizeof(r->shadow));
     r->counters = NULL; r->hostCounters = NULL; r->accum = NULL;
     memset(&r->grid, 0, sizeof(r->grid)); r->gridCells = 0; r->gridCapacity = 0; r->bboxInit = NULL;
     r->comm = NULL; r->gPosLen = r->gThrVcm = r->gDirVm = NULL; r->gContProb = NULL; r->gatherCapacity = 0;
     r->devCounts = NULL; r->hostCounts = NULL;
-    r->iterationsDone = 0; r->mergeGroup = 8; r->profile = false; r->evValid = false;
-    memset(r->ev, 0, sizeof(r->ev)); memset(r->userEv, 0, sizeof(r->userEv)); memset(&r->stats, 0, sizeof(r->stats));
+    r->iterationsDone = 0; r->mergeGroup = 1; r->profile = false;
+    r->ev = NULL; r->ringHead = r->ringTail = 0;
+    memset(r->ringLaunches, 0, sizeof(r->ringLaunches)); memset(r->ringTimed, 0, sizeof(r->ringTimed));
+    memset(r->userEv, 0, sizeof(r->userEv)); memset(&r->stats, 0, sizeof(r->stats));
     r->statsPending = false; r->lastLaunches = 0;
     r->params = *params;
 
@@ -653,7 +713,6 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
         SVCM_CREATE_FAIL(e_ == cudaErrorMemoryAllocation ? SVCM_E_NOMEM : SVCM_E_CUDA); } } while(0)
     SVCM_TRY(cudaSetDevice(r->device));
     SVCM_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
-    for(int i = 0; i < 6; i++) SVCM_TRY(cudaEventCreate(&r->ev[i]));
     for(int i = 0; i < SVCM_NUM_USER_EVENTS; i++) SVCM_TRY(cudaEventCreate(&r->userEv[i]));
     for(int i = 0; i < 2; i++) if((rc = allocQueue(r, r->queue[i], r->localPaths))) SVCM_CREATE_FAIL(rc);
     if((rc = devAlloc(r, &r->pathVertCount, r->localPaths))) SVCM_CREATE_FAIL(rc);
@@ -662,9 +721,9 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     if((rc = devAlloc(r, &r->grid.bboxBits, 6))) SVCM_CREATE_FAIL(rc);
     if((rc = devAlloc(r, &r->bboxInit, 6))) SVCM_CREATE_FAIL(rc);
     if((rc = devAlloc(r, &r->devCounts, 8))) SVCM_CREATE_FAIL(rc);
-    SVCM_TRY(cudaMallocHost((void**)&r->hostCounters, sizeof(unsigned long long) * CNT_WORDS));
+    SVCM_TRY(cudaMallocHost((void**)&r->hostCounters, sizeof(unsigned long long) * CNT_WORDS * SVCM_PROFILE_RING));
     SVCM_TRY(cudaMallocHost((void**)&r->hostCounts, sizeof(uint32_t) * 16));
-    memset(r->hostCounters, 0, sizeof(unsigned long long) * CNT_WORDS);
+    memset(r->hostCounters, 0, sizeof(unsigned long long) * CNT_WORDS * SVCM_PROFILE_RING);
     memset(r->hostCounts, 0, sizeof(uint32_t) * 16);
     const int32_t init[6] = { floatToOrdered(1e36f), floatToOrdered(1e36f), floatToOrdered(1e36f),
                               floatToOrdered(-1e36f), floatToOrdered(-1e36f), floatToOrdered(-1e36f) };
@@ -687,13 +746,18 @@ void svcm_destroy(svcm_renderer *r)
     if(r->comm && ncclApi()->lib) ncclApi()->CommDestroy(r->comm);
     freeQueue(r->queue[0]); freeQueue(r->queue[1]);
     devFree(r->queueCountsLight); devFree(r->queueCountsCamera);
+    devFree(r->shadow.r0); devFree(r->shadow.r1); devFree(r->shadow.r2); devFree(r->shadow.counts);
     freeVerts(r); freeQueries(r); freeGridSorted(r); freeGather(r);
     devFree(r->pathVertCount); devFree(r->counters); devFree(r->accum);
     devFree(r->grid.cellCount); devFree(r->grid.blockSums); devFree(r->grid.bboxBits);
     devFree(r->bboxInit); devFree(r->devCounts);
     if(r->hostCounters) cudaFreeHost(r->hostCounters);
     if(r->hostCounts) cudaFreeHost(r->hostCounts);
-    for(int i = 0; i < 6; i++) if(r->ev[i]) cudaEventDestroy(r->ev[i]);
+    if(r->ev)
+    {
+        for(int k = 0; k < SVCM_PROFILE_RING; k++) for(int i = 0; i < 6; i++) if(r->ev[k][i]) cudaEventDestroy(r->ev[k][i]);
+        delete[] r->ev;
+    }
     for(int i = 0; i < SVCM_NUM_USER_EVENTS; i++) if(r->userEv[i]) cudaEventDestroy(r->userEv[i]);
     if(r->stream) cudaStreamDestroy(r->stream);
     delete r;
@@ -704,9 +768,19 @@ int svcm_set_option(svcm_renderer *r, int32_t option, int64_t value)
     if(!r) return SVCM_E_INVALID;
     switch(option)
     {
-    case SVCM_OPT_PROFILE: r->profile = value != 0; return SVCM_OK;
+    case SVCM_OPT_PROFILE:
+        if(value != 0 && !r->ev)
+        {
+            SVCM_CUDA(r, cudaSetDevice(r->device));
+            r->ev = new cudaEvent_t[SVCM_PROFILE_RING][6];
+            memset(r->ev, 0, sizeof(cudaEvent_t) * 6 * SVCM_PROFILE_RING);
+            for(int k = 0; k < SVCM_PROFILE_RING; k++) for(int i = 0; i < 6; i++) SVCM_CUDA(r, cudaEventCreate(&r->ev[k][i]));
+        }
+        r->profile = value != 0;
+        return SVCM_OK;
     case SVCM_OPT_MERGE_GROUP:
-        if(value != 8 && value != 16 && value != 32) return fail(r, SVCM_E_INVALID, "merge group must be 8, 16 or 32");
+        if(value != 1 && value != 8 && value != 16 && value != 32)
+            return fail(r, SVCM_E_INVALID, "merge group must be 1 (lane per query), 8, 16 or 32");
         r->mergeGroup = int(value); return SVCM_OK;
     case SVCM_OPT_COUNTERS: return SVCM_OK;   // counters are always maintained
     default: return fail(r, SVCM_E_INVALID, "unknown option %d", option);
@@ -765,6 +839,40 @@ int svcm_get_stats(svcm_renderer *r, SvcmStats *out)
     if(!r || !out) return SVCM_E_INVALID;
     const int rc = svcm_synchronize(r);
     *out = r->stats;
+    return rc;
+}
+
+int svcm_get_profile(svcm_renderer *r, SvcmProfile *out)
+{
+    if(!r || !out) return SVCM_E_INVALID;
+    const int rc = svcm_synchronize(r);
+    memset(out, 0, sizeof(*out));
+    for(long long it = r->ringTail; it < r->ringHead; it++)
+    {
+        const int slot = int(it % SVCM_PROFILE_RING);
+        const unsigned long long *c = r->hostCounters + size_t(slot) * CNT_WORDS;
+        out->iterations++;
+        out->lightVertices += (int64_t)c[CNT_LIGHT_VERTS];
+        out->mergeQueries += (int64_t)c[CNT_QUERIES];
+        out->mergeCandidates += (int64_t)c[CNT_CANDIDATES];
+        out->mergeAccepted += (int64_t)c[CNT_ACCEPTED];
+        out->lightRays += (int64_t)c[CNT_LIGHT_RAYS];
+        out->cameraRays += (int64_t)c[CNT_CAMERA_RAYS];
+        out->shadowRays += (int64_t)c[CNT_SHADOW_RAYS];
+        out->kernelLaunches += r->ringLaunches[slot];
+        if(r->ringTimed[slot])
+        {
+            cudaEvent_t *ev = r->ev[slot];
+            float ms[6] = { 0, 0, 0, 0, 0, 0 };
+            cudaEventElapsedTime(&ms[0], ev[0], ev[1]); cudaEventElapsedTime(&ms[1], ev[1], ev[2]);
+            cudaEventElapsedTime(&ms[2], ev[2], ev[3]); cudaEventElapsedTime(&ms[3], ev[3], ev[4]);
+            cudaEventElapsedTime(&ms[4], ev[4], ev[5]); cudaEventElapsedTime(&ms[5], ev[0], ev[5]);
+            out->msLightTrace += ms[0]; out->msGather += ms[1]; out->msGridBuild += ms[2];
+            out->msCameraTrace += ms[3]; out->msMerge += ms[4]; out->msTotal += ms[5];
+            out->timedIterations++;
+        }
+    }
+    r->ringTail = r->ringHead;
     return rc;
 }
 
@@ -1038,7 +1146,11 @@ int svcm_hashgrid_query(svcm_hashgrid *g, const SvcmSceneDesc *scene, const Svcm
         ic.numCells = g->numCells; ic.minLen = minPathLength; ic.maxLen = maxPathLength;
         ic.misVcWeightFactor = misVcWeightFactor; ic.ppm = ppm != 0; ic.useVM = 1;
         launchPackMergeQueries(sc, dq, count, qs, 0);
-        launchMerge(sc, ic, qs, NULL, uint32_t(count), g->grid, NULL, dContrib, dCounts, NULL, 8, 0);
+        // the parity tests exercise both merge kernels: the environment picks the variant
+        const char *variant = getenv("SVCM_MERGE_GROUP");
+        const int group = variant ? atoi(variant) : 1;
+        launchMerge(sc, ic, qs, NULL, uint32_t(count), g->grid, NULL, dContrib, dCounts, NULL,
+                    (group == 8 || group == 16 || group == 32) ? group : 1, uint32_t(g->count), 0);
         e = cudaMemcpy(contrib, dContrib, sizeof(float) * 3 * size_t(count), cudaMemcpyDeviceToHost);
         if(e == cudaSuccess && counts) e = cudaMemcpy(counts, dCounts, sizeof(int32_t) * 2 * size_t(count), cudaMemcpyDeviceToHost);
     }

@@ -94,6 +94,18 @@ struct QueryStore
     uint32_t capacity;
 };
 
+// Deferred shadow rays (Scene::Occluded calls of ConnectToCamera, DirectIllumination and
+// ConnectVertices: src/vertexcm.hxx:928,734,805). The bounce kernels only EVALUATE the
+// connection and append (segment, contribution, pixel); k_shadow then runs the any-hit test
+// for a whole bounce with every lane busy and splats the unoccluded contributions.
+//   r0 = point.xyz | tMax      r1 = direction.xyz | pixel (bits)      r2 = contribution.xyz | -
+struct ShadowQueue
+{
+    float4 *r0, *r1, *r2;
+    uint32_t *counts;       // [bounce index] rays queued by that bounce
+    uint32_t capacity;      // a full queue makes the producer trace its ray inline instead
+};
+
 // device-side counters (one block of 64-bit words, zeroed per iteration)
 enum {
     CNT_LIGHT_VERTS = 0, CNT_QUERIES, CNT_CANDIDATES, CNT_ACCEPTED, CNT_LIGHT_RAYS,
@@ -107,6 +119,7 @@ struct TraceArgs
     VertexStore verts;
     uint8_t    *pathVertCount;   // [local path] number of stored vertices
     QueryStore  queries;
+    ShadowQueue shadow;
     unsigned long long *counters; // CNT_*
     float      *accum;           // W*H*3 accumulated image
     const int32_t *bboxBits;     // light-vertex bbox (camera pass: early reject of queries)
@@ -138,6 +151,9 @@ void launchLightBounce(const DevScene &sc, const IterConst &ic, const TraceArgs 
                        uint32_t bounce, uint32_t maxItems, cudaStream_t stream);
 void launchCameraBounce(const DevScene &sc, const IterConst &ic, const TraceArgs &args,
                         uint32_t bounce, uint32_t maxItems, cudaStream_t stream);
+// any-hit tests + splats for the rays queued by `bounce` (count read on the device)
+void launchShadow(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t bounce,
+                  uint32_t maxItems, cudaStream_t stream);
 // HashGrid::Build: bbox -> keys + histogram -> exclusive scan -> scatter. Returns the
 // number of kernels launched.
 int  launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers &grid,
@@ -147,7 +163,7 @@ int  launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers
 void launchMerge(const DevScene &sc, const IterConst &ic, const QueryStore &queries,
                  const unsigned long long *queryCount, uint32_t hostQueryCount,
                  const GridBuffers &grid, float *accum, float *contribOut, int32_t *countsOut,
-                 unsigned long long *counters, int groupSize, cudaStream_t stream);
+                 unsigned long long *counters, int groupSize, uint32_t particleCapacity, cudaStream_t stream);
 
 // kernel-level batch entry points (device pointers)
 void launchIntersectBatch(const DevScene &sc, const float *rays, int64_t count, int32_t *hit,

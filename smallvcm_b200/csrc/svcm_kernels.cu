@@ -47,6 +47,18 @@ SVCM_D uint32_t warpAppend64(unsigned long long *counter, bool pred)
     return uint32_t(base) + uint32_t(__popc(m & ((1u << laneId()) - 1u)));
 }
 
+// Opportunistic aggregation for appends issued from divergent code: the lanes that happen to
+// be converged here share one atomicAdd.
+SVCM_D uint32_t activeAppend(uint32_t *counter)
+{
+    const uint32_t m = __activemask();
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0u;
+    if(int(laneId()) == leader) base = atomicAdd(counter, uint32_t(__popc(m)));
+    base = __shfl_sync(m, base, leader);
+    return base + uint32_t(__popc(m & ((1u << laneId()) - 1u)));
+}
+
 // adds a per-thread count into a 64-bit device counter with one atomic per warp
 SVCM_D void warpCount(unsigned long long *counter, uint32_t mine)
 {
@@ -65,6 +77,22 @@ SVCM_D void addPixel(float *accum, uint32_t pixel, f3 c)
 
 SVCM_D float4 mk4(f3 a, float w) { return make_float4(a.x, a.y, a.z, w); }
 SVCM_D f3 xyz(float4 a) { return mk3(a.x, a.y, a.z); }
+
+// Queue one visibility test: "add `contrib` to `pixel` unless point -> point + dir*tMax is
+// blocked" (Scene::Occluded, reference src/scene.hxx:72-85). If the queue is full the ray is
+// traced on the spot — slower, never wrong.
+SVCM_D void emitShadowRay(const DevScene &sc, const ShadowQueue &q, uint32_t bounce, float *accum,
+                          f3 point, f3 dir, float tMax, uint32_t pixel, f3 contrib)
+{
+    const uint32_t slot = activeAppend(q.counts + bounce);
+    if(slot < q.capacity)
+    {
+        q.r0[slot] = mk4(point, tMax);
+        q.r1[slot] = mk4(dir, __uint_as_float(pixel));
+        q.r2[slot] = mk4(contrib, 0.f);
+    }
+    else if(!sceneOccluded(sc, point, dir, tMax)) addPixel(accum, pixel, contrib);
+}
 
 // local (per-rank) path index <-> global path index: rows are dealt round-robin to ranks
 SVCM_D uint32_t localToGlobalPath(const IterConst &ic, uint32_t l)
@@ -198,7 +226,7 @@ SVCM_D void generateLightSample(const DevScene &sc, const IterConst &ic, SubPath
 // ConnectToCamera, reference src/vertexcm.hxx:862-933: splat the light vertex onto the
 // image through the pinhole; float atomics because the target pixel is arbitrary.
 SVCM_D void connectToCamera(const DevScene &sc, const IterConst &ic, const SubPath &s, f3 hitPoint,
-                            const Bsdf &bsdf, float *accum, uint32_t &shadowRays)
+                            const Bsdf &bsdf, const TraceArgs &a, uint32_t bounce)
 {
     const f3 camPos = ld3(sc.camPos), camFwd = ld3(sc.camFwd);
     f3 dirToCamera = camPos - hitPoint;
@@ -231,11 +259,9 @@ SVCM_D void connectToCamera(const DevScene &sc, const IterConst &ic, const SubPa
         (ic.lightSubPathCount * surfaceToImageFactor);
     if(iszero(contrib)) return;
 
-    shadowRays++;
-    if(sceneOccluded(sc, hitPoint, dirToCamera, distance)) return;
-    // Framebuffer::AddColor, reference src/framebuffer.hxx:43-57
+    // Framebuffer::AddColor target, reference src/framebuffer.hxx:43-57; visibility deferred
     const uint32_t pixel = uint32_t(int(raster.x)) + uint32_t(int(raster.y)) * uint32_t(ic.resX);
-    addPixel(accum, pixel, contrib);
+    emitShadowRay(sc, a.shadow, bounce, a.accum, hitPoint, dirToCamera, distance, pixel, contrib);
 }
 
 // One bounce of every live light sub-path: reference src/vertexcm.hxx:328-393 (loop body)
@@ -244,7 +270,7 @@ k_lightBounce(const __grid_constant__ DevScene sc, const __grid_constant__ IterC
               const __grid_constant__ TraceArgs a, const uint32_t bounce)
 {
     const uint32_t count = (bounce == 1u) ? ic.localPaths : a.queueCounts[bounce];
-    uint32_t nRays = 0u, nShadow = 0u;
+    uint32_t nRays = 0u;
 
     for(uint32_t i0 = blockIdx.x * blockDim.x; i0 < count; i0 += gridDim.x * blockDim.x)
     {
@@ -312,7 +338,7 @@ k_lightBounce(const __grid_constant__ DevScene sc, const __grid_constant__ IterC
         if(alive)
         {
             if(!bsdf.isDelta() && (ic.useVC || ic.lightTraceOnly) && (s.length + 1u >= ic.minLen))
-                connectToCamera(sc, ic, s, hitPoint, bsdf, a.accum, nShadow);
+                connectToCamera(sc, ic, s, hitPoint, bsdf, a, bounce);
 
             // terminate if the path would become too long after scattering
             if(s.length + 2u > ic.maxLen) alive = false;
@@ -325,7 +351,6 @@ k_lightBounce(const __grid_constant__ DevScene sc, const __grid_constant__ IterC
     }
 
     warpCount(a.counters + CNT_LIGHT_RAYS, nRays);
-    warpCount(a.counters + CNT_SHADOW_RAYS, nShadow);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -376,8 +401,9 @@ SVCM_D f3 getLightRadiance(const DevScene &sc, const IterConst &ic, const DevLig
 }
 
 // DirectIllumination, reference src/vertexcm.hxx:663-738
+// (the shadow test of :734 is deferred: the caller queues oDirToLight / oDistance)
 SVCM_D f3 directIllumination(const DevScene &sc, const IterConst &ic, SubPath &s, f3 hitPoint,
-                             const Bsdf &bsdf, uint32_t &shadowRays)
+                             const Bsdf &bsdf, f3 &oDirToLight, float &oDistance)
 {
     const int   lightCount = sc.numLights;
     const float lightPickProb = 1.f / float(lightCount);
@@ -386,10 +412,11 @@ SVCM_D f3 directIllumination(const DevScene &sc, const IterConst &ic, SubPath &s
     lightID = min(lightID, lightCount - 1);
     const DevLight &light = sc.lights[lightID];
 
-    f3 dirToLight;
-    float distance, directPdfW, emissionPdfW, cosAtLight;
+    f3 dirToLight = mk3(0.f);
+    float distance = 0.f, directPdfW, emissionPdfW, cosAtLight;
     const f3 radiance = lightIlluminate(sc, light, hitPoint, rx, ry, dirToLight, distance,
                                         directPdfW, emissionPdfW, cosAtLight);
+    oDirToLight = dirToLight; oDistance = distance;
     if(iszero(radiance)) return mk3(0.f);
 
     float bsdfDirPdfW, bsdfRevPdfW, cosToLight;
@@ -405,23 +432,21 @@ SVCM_D f3 directIllumination(const DevScene &sc, const IterConst &ic, SubPath &s
         (ic.misVmWeightFactor + s.dVCM + s.dVC * bsdfRevPdfW);                         // (45)
     const float misWeight = 1.f / (wLight + 1.f + wCamera);
 
-    const f3 contrib = (misWeight * cosToLight / (lightPickProb * directPdfW)) * (radiance * bsdfFactor);
-    if(iszero(contrib)) return mk3(0.f);
-    shadowRays++;
-    if(sceneOccluded(sc, hitPoint, dirToLight, distance)) return mk3(0.f);
-    return contrib;
+    return (misWeight * cosToLight / (lightPickProb * directPdfW)) * (radiance * bsdfFactor);
 }
 
 // ConnectVertices, reference src/vertexcm.hxx:743-809; the light vertex's BSDF is rebuilt
 // from its stored normal / local direction / material (what BSDF<true>::Setup computed).
+// (the shadow test of :805 is deferred: the caller queues oDirection / oDistance)
 SVCM_D f3 connectVertices(const DevScene &sc, const IterConst &ic, f3 lvPos, const Bsdf &lvBsdf,
                           float lvdVCM, float lvdVC, const Bsdf &camBsdf, f3 camHit,
-                          const SubPath &s, uint32_t &shadowRays)
+                          const SubPath &s, f3 &oDirection, float &oDistance)
 {
     f3 direction = lvPos - camHit;
     const float dist2 = lensqr(direction);
     const float distance = sqrtf(dist2);
     direction = direction / distance;
+    oDirection = direction; oDistance = distance;
 
     float cosCamera, camDirPdfW, camRevPdfW;
     const f3 camFactor = bsdfEvaluate(sc, camBsdf, direction, cosCamera, camDirPdfW, camRevPdfW);
@@ -445,11 +470,7 @@ SVCM_D f3 connectVertices(const DevScene &sc, const IterConst &ic, f3 lvPos, con
     const float wCamera = lightDirPdfA * (ic.misVmWeightFactor + s.dVCM + s.dVC * camRevPdfW);    // (41)
     const float misWeight = 1.f / (wLight + 1.f + wCamera);
 
-    const f3 contrib = ((misWeight * geometryTerm) * camFactor) * lightFactor;
-    if(iszero(contrib)) return mk3(0.f);
-    shadowRays++;
-    if(sceneOccluded(sc, camHit, direction, distance)) return mk3(0.f);
-    return contrib;
+    return ((misWeight * geometryTerm) * camFactor) * lightFactor;
 }
 
 // One bounce of every live camera sub-path: reference src/vertexcm.hxx:423-542 (loop body).
@@ -461,7 +482,7 @@ k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ Iter
                const __grid_constant__ TraceArgs a, const uint32_t bounce)
 {
     const uint32_t count = (bounce == 1u) ? ic.localPaths : a.queueCounts[bounce];
-    uint32_t nRays = 0u, nShadow = 0u;
+    uint32_t nRays = 0u;
 
     f3 bbMin = mk3(0.f), bbMax = mk3(0.f);
     if(ic.useVM)
@@ -537,7 +558,11 @@ k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ Iter
             {
                 // vertex connection: to a light source ...
                 if(s.length + 1u >= ic.minLen)
-                    color = color + s.throughput * directIllumination(sc, ic, s, hitPoint, bsdf, nShadow);
+                {
+                    f3 dir; float dist;
+                    const f3 c = s.throughput * directIllumination(sc, ic, s, hitPoint, bsdf, dir, dist);
+                    if(!iszero(c)) emitShadowRay(sc, a.shadow, bounce, a.accum, hitPoint, dir, dist, s.extra, c);
+                }
 
                 // ... and to the vertices of this pixel's own light sub-path (:498-526)
                 const uint32_t l = globalToLocalPath(ic, s.path);
@@ -557,8 +582,10 @@ k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ Iter
                     lvBsdf.localDirFix = xyz(lm);
                     lvBsdf.diffProb = lvBsdf.phongProb = lvBsdf.reflProb = lvBsdf.refrProb = 0.f;
                     bsdfFromLocal(sc, __float_as_int(lm.w), lvBsdf);
-                    const f3 c = connectVertices(sc, ic, xyz(pl), lvBsdf, tv.w, nv4.w, bsdf, hitPoint, s, nShadow);
-                    color = color + (s.throughput * xyz(tv)) * c;
+                    f3 dir; float dist;
+                    const f3 c = (s.throughput * xyz(tv)) *
+                        connectVertices(sc, ic, xyz(pl), lvBsdf, tv.w, nv4.w, bsdf, hitPoint, s, dir, dist);
+                    if(!iszero(c)) emitShadowRay(sc, a.shadow, bounce, a.accum, hitPoint, dir, dist, s.extra, c);
                 }
             }
             if(ic.useVM)
@@ -599,7 +626,23 @@ k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ Iter
     }
 
     warpCount(a.counters + CNT_CAMERA_RAYS, nRays);
-    warpCount(a.counters + CNT_SHADOW_RAYS, nShadow);
+}
+
+// The deferred Scene::Occluded tests of one bounce (reference src/scene.hxx:72-85), one lane per
+// queued segment, then Framebuffer::AddColor for the unoccluded ones. Every lane runs the same
+// primitive loop: this is where the bounce kernels' divergent any-hit loops went.
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ TraceArgs a, const uint32_t bounce)
+{
+    const uint32_t queued = a.shadow.counts[bounce];
+    const uint32_t count = min(queued, a.shadow.capacity);
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    {
+        const float4 r0 = a.shadow.r0[i], r1 = a.shadow.r1[i];
+        if(!sceneOccluded(sc, xyz(r0), xyz(r1), r0.w))
+            addPixel(a.accum, __float_as_uint(r1.w), xyz(a.shadow.r2[i]));
+    }
+    if(blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.counters + CNT_SHADOW_RAYS, (unsigned long long)queued);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -946,6 +989,210 @@ k_merge(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst i
 }
 
 // ------------------------------------------------------------------------------------------
+// merge, lane-per-query variant (the default): every lane owns one range query and walks its 8
+// cell ranges one candidate at a time; the accepted (query, particle) pairs — about one in
+// eight — are compacted through a per-warp shared-memory queue with ballots, and each time 32
+// pairs are waiting the whole warp evaluates RangeQuery::Process for them, one pair per lane.
+// The distance test thus runs with whatever lanes still have candidates, and the expensive
+// BSDF + MIS body always runs with a full warp, whatever the acceptance rate.
+// ------------------------------------------------------------------------------------------
+#define MERGE_WARPS (SVCM_BLOCK / 32)
+#define MERGE_QWORDS 20     // per-query words parked in shared memory for the pair evaluation
+#define MERGE_IDX_BITS 27   // queue entry = owner lane << 27 | sorted particle index
+
+struct MergeWarpSmem
+{
+    uint32_t queue[64];                 // ring of accepted pairs
+    float    q[MERGE_QWORDS][32];       // [word][owner lane]: conflict-free for distinct owners
+    float    acc[3][32];                // per-owner radiance sums
+    uint32_t rangeStart[8][32];
+    uint32_t rangeEnd[8][32];
+};
+
+SVCM_D void mergeEvaluatePairs(const DevScene &sc, const IterConst &ic, const GridBuffers &g,
+                               MergeWarpSmem &w, uint32_t head, uint32_t tail)
+{
+    const uint32_t lane = laneId();
+    if(head + lane < tail)
+    {
+        const uint32_t e = w.queue[(head + lane) & 63u];
+        const uint32_t owner = e >> MERGE_IDX_BITS, idx = e & ((1u << MERGE_IDX_BITS) - 1u);
+        const uint32_t lvLen = __float_as_uint(g.sPosLen[idx].w);
+        const uint32_t lenMat = __float_as_uint(w.q[12][owner]);
+        const uint32_t camLen = lenMat & 0xFFFFu;
+        // RangeQuery::Process, reference src/vertexcm.hxx:130-169
+        if(!((lvLen + camLen > ic.maxLen) || (lvLen + camLen < ic.minLen)))
+        {
+            const float4 dv = g.sDirVm[idx];
+            Bsdf b;
+            b.frame.x = mk3(w.q[0][owner], w.q[1][owner], w.q[2][owner]);
+            b.frame.y = mk3(w.q[3][owner], w.q[4][owner], w.q[5][owner]);
+            b.frame.z = mk3(w.q[6][owner], w.q[7][owner], w.q[8][owner]);
+            b.localDirFix = mk3(w.q[9][owner], w.q[10][owner], w.q[11][owner]);
+            const f3 localDirGen = b.frame.toLocal(xyz(dv));
+            if(!(localDirGen.z * b.localDirFix.z < 0.f))
+            {
+                b.diffProb = w.q[13][owner]; b.phongProb = w.q[14][owner]; b.contProb = w.q[15][owner];
+                float camDirPdfW, camRevPdfW;
+                const f3 f = bsdfEvaluateLocal(sc.mats[lenMat >> 16], b, localDirGen, camDirPdfW, camRevPdfW);
+                if(!iszero(f))
+                {
+                    const float4 tv = g.sThrVcm[idx];
+                    camDirPdfW *= b.contProb;
+                    camRevPdfW *= g.sContProb[idx];                    // the LIGHT vertex's RR probability
+                    const float wLight  = tv.w * ic.misVcWeightFactor + dv.w * camDirPdfW;                     // (38)
+                    const float wCamera = w.q[16][owner] * ic.misVcWeightFactor + w.q[17][owner] * camRevPdfW; // (39)
+                    const float misWeight = ic.ppm ? 1.f : 1.f / (wLight + 1.f + wCamera);
+                    const f3 c = (misWeight * f) * xyz(tv);
+                    atomicAdd(&w.acc[0][owner], c.x);
+                    atomicAdd(&w.acc[1][owner], c.y);
+                    atomicAdd(&w.acc[2][owner], c.z);
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_mergeLane(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
+            const __grid_constant__ QueryStore qs, const unsigned long long *queryCountPtr,
+            const uint32_t hostQueryCount, const __grid_constant__ GridBuffers g, float *accum,
+            float *contribOut, int32_t *countsOut, unsigned long long *counters)
+{
+    __shared__ MergeWarpSmem smem[MERGE_WARPS];
+    MergeWarpSmem &w = smem[threadIdx.x >> 5];
+    uint32_t nq = hostQueryCount;
+    if(queryCountPtr) nq = uint32_t(min(*queryCountPtr, (unsigned long long)qs.capacity));
+    const uint32_t lane = laneId();
+    const uint32_t ltMask = (1u << lane) - 1u;
+
+    const f3 bbMin = mk3(orderedToFloat(g.bboxBits[0]), orderedToFloat(g.bboxBits[1]), orderedToFloat(g.bboxBits[2]));
+    const f3 bbMax = mk3(orderedToFloat(g.bboxBits[3]), orderedToFloat(g.bboxBits[4]), orderedToFloat(g.bboxBits[5]));
+    uint32_t nCand = 0u, nAcc = 0u;
+
+    for(uint32_t q0i = (blockIdx.x * MERGE_WARPS + (threadIdx.x >> 5)) * 32u; q0i < nq;
+        q0i += gridDim.x * MERGE_WARPS * 32u)
+    {
+        const uint32_t q = q0i + lane;
+        const bool valid = q < nq;
+        f3 qpos = mk3(0.f), scale = mk3(0.f);
+        uint32_t pixel = 0u;
+        uint32_t cand = 0u, accepted = 0u;
+        w.acc[0][lane] = 0.f; w.acc[1][lane] = 0.f; w.acc[2][lane] = 0.f;
+#pragma unroll
+        for(int j = 0; j < 8; j++) { w.rangeStart[j][lane] = 0u; w.rangeEnd[j][lane] = 0u; }
+
+        if(valid)
+        {
+            const float4 q0 = qs.q0[q], q1 = qs.q1[q], q2 = qs.q2[q], q3 = qs.q3[q];
+            qpos = xyz(q0); scale = xyz(q3); pixel = __float_as_uint(q0.w);
+            const uint32_t lenMat = __float_as_uint(q1.w);
+            // camera BSDF: BSDF<false>::Setup from the stored normal / local direction / material
+            Bsdf bsdf;
+            bsdf.frame.setFromZ(xyz(q1));
+            bsdf.localDirFix = xyz(q2);
+            bsdf.diffProb = bsdf.phongProb = bsdf.reflProb = bsdf.refrProb = 0.f;
+            bsdfFromLocal(sc, int32_t(lenMat >> 16), bsdf);
+            w.q[0][lane] = bsdf.frame.x.x; w.q[1][lane] = bsdf.frame.x.y; w.q[2][lane] = bsdf.frame.x.z;
+            w.q[3][lane] = bsdf.frame.y.x; w.q[4][lane] = bsdf.frame.y.y; w.q[5][lane] = bsdf.frame.y.z;
+            w.q[6][lane] = bsdf.frame.z.x; w.q[7][lane] = bsdf.frame.z.y; w.q[8][lane] = bsdf.frame.z.z;
+            w.q[9][lane] = bsdf.localDirFix.x; w.q[10][lane] = bsdf.localDirFix.y; w.q[11][lane] = bsdf.localDirFix.z;
+            w.q[12][lane] = q1.w;
+            w.q[13][lane] = bsdf.diffProb; w.q[14][lane] = bsdf.phongProb; w.q[15][lane] = bsdf.contProb;
+            w.q[16][lane] = q2.w; w.q[17][lane] = q3.w;
+
+            // HashGrid::Process: bbox early-out, then the 8 cells (src/hashgrid.hxx:116-155)
+            const bool inside = !(qpos.x - bbMin.x < 0.f || bbMax.x - qpos.x < 0.f ||
+                                  qpos.y - bbMin.y < 0.f || bbMax.y - qpos.y < 0.f ||
+                                  qpos.z - bbMin.z < 0.f || bbMax.z - qpos.z < 0.f);
+            if(inside)
+            {
+                const f3 cellPt = mk3(ic.invCellSize * (qpos.x - bbMin.x), ic.invCellSize * (qpos.y - bbMin.y),
+                                      ic.invCellSize * (qpos.z - bbMin.z));
+                const f3 coordF = mk3(floorf(cellPt.x), floorf(cellPt.y), floorf(cellPt.z));
+                const int px = int(coordF.x), py = int(coordF.y), pz = int(coordF.z);
+                const int pxo = px + ((cellPt.x - coordF.x) < 0.5f ? -1 : +1);
+                const int pyo = py + ((cellPt.y - coordF.y) < 0.5f ? -1 : +1);
+                const int pzo = pz + ((cellPt.z - coordF.z) < 0.5f ? -1 : +1);
+#pragma unroll
+                for(int j = 0; j < 8; j++)
+                {
+                    const uint32_t h = cellHash((j & 4) ? pxo : px, (j & 2) ? pyo : py, (j & 1) ? pzo : pz, ic.numCells);
+                    const uint32_t start = (h == 0u) ? 0u : g.cellCount[h - 1u];   // GetCellRange
+                    const uint32_t end = g.cellCount[h];
+                    w.rangeStart[j][lane] = start; w.rangeEnd[j][lane] = end;
+                    cand += end - start;
+                }
+            }
+        }
+        __syncwarp();
+
+        // walk the ranges; compact accepted pairs through the warp queue
+        uint32_t j = 0u, cur = w.rangeStart[0][lane], end = w.rangeEnd[0][lane];
+        uint32_t head = 0u, tail = 0u;
+        for(;;)
+        {
+            while(cur == end && j < 7u) { j++; cur = w.rangeStart[j][lane]; end = w.rangeEnd[j][lane]; }
+            const bool has = cur < end;
+            if(!__any_sync(FULL_MASK, has)) break;
+            bool hitIt = false;
+            uint32_t idx = 0u;
+            if(has)
+            {
+                idx = cur++;
+                const float4 pl = g.sPosLen[idx];
+                // |q - p|^2 <= r^2 in the reference's exact (unfused) evaluation order
+                // (src/hashgrid.hxx:162-165): identical accept decisions for identical inputs
+                const float dx = qpos.x - pl.x, dy = qpos.y - pl.y, dz = qpos.z - pl.z;
+                const float distSqr = __fadd_rn(__fadd_rn(__fadd_rn(0.f, __fmul_rn(dx, dx)), __fmul_rn(dy, dy)),
+                                                __fmul_rn(dz, dz));
+                hitIt = distSqr <= ic.radiusSqr;
+            }
+            const uint32_t m = __ballot_sync(FULL_MASK, hitIt);
+            if(m)
+            {
+                if(hitIt)
+                {
+                    w.queue[(tail + uint32_t(__popc(m & ltMask))) & 63u] = (lane << MERGE_IDX_BITS) | idx;
+                    accepted++;
+                }
+                tail += uint32_t(__popc(m));
+                __syncwarp();
+                if(tail - head >= 32u)
+                {
+                    mergeEvaluatePairs(sc, ic, g, w, head, head + 32u);
+                    head += 32u;
+                }
+            }
+        }
+        if(tail != head) mergeEvaluatePairs(sc, ic, g, w, head, tail);
+        __syncwarp();
+
+        if(valid)
+        {
+            const f3 contrib = mk3(w.acc[0][lane], w.acc[1][lane], w.acc[2][lane]);
+            nCand += cand; nAcc += accepted;
+            if(contribOut)
+            {
+                contribOut[3ull * q + 0] = contrib.x; contribOut[3ull * q + 1] = contrib.y;
+                contribOut[3ull * q + 2] = contrib.z;
+            }
+            if(countsOut) { countsOut[2ull * q] = int32_t(cand); countsOut[2ull * q + 1] = int32_t(accepted); }
+            // color += cameraState.mThroughput * mVmNormalization * query.GetContrib()  (:534)
+            if(accum) addPixel(accum, pixel, scale * contrib);
+        }
+        __syncwarp();
+    }
+
+    if(counters)
+    {
+        warpCount(counters + CNT_CANDIDATES, nCand);
+        warpCount(counters + CNT_ACCEPTED, nAcc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // kernel-level batch kernels (parity tests call the same device functions as the path)
 // ------------------------------------------------------------------------------------------
 __global__ void k_intersectBatch(const __grid_constant__ DevScene sc, const float *rays, int64_t count,
@@ -1083,6 +1330,13 @@ void launchCameraBounce(const DevScene &sc, const IterConst &ic, const TraceArgs
     k_cameraBounce<<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
 }
 
+void launchShadow(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t bounce,
+                  uint32_t maxItems, cudaStream_t stream)
+{
+    (void)ic;
+    k_shadow<<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, args, bounce);
+}
+
 int launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers &grid, cudaStream_t stream)
 {
     const uint32_t n = ic.numCells + 1u;
@@ -1115,10 +1369,18 @@ int launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers 
 void launchMerge(const DevScene &sc, const IterConst &ic, const QueryStore &queries,
                  const unsigned long long *queryCount, uint32_t hostQueryCount, const GridBuffers &grid,
                  float *accum, float *contribOut, int32_t *countsOut, unsigned long long *counters,
-                 int groupSize, cudaStream_t stream)
+                 int groupSize, uint32_t particleCapacity, cudaStream_t stream)
 {
     const uint64_t maxQueries = queryCount ? queries.capacity : hostQueryCount;
     if(maxQueries == 0) return;
+    // the lane-per-query kernel packs (owner lane, particle index) into 32 bits
+    if(groupSize == 1 && particleCapacity >= (1u << MERGE_IDX_BITS)) groupSize = 8;
+    if(groupSize == 1)
+    {
+        k_mergeLane<<<gridFor(maxQueries, SVCM_BLOCK, 4), SVCM_BLOCK, 0, stream>>>(
+            sc, ic, queries, queryCount, hostQueryCount, grid, accum, contribOut, countsOut, counters);
+        return;
+    }
     const uint32_t gridN = gridFor(maxQueries * uint64_t(groupSize), SVCM_BLOCK, 8);
     if(groupSize == 32)
         k_merge<32><<<gridN, SVCM_BLOCK, 0, stream>>>(sc, ic, queries, queryCount, hostQueryCount, grid, accum,

@@ -175,6 +175,12 @@ class VertexCM:
         _check(self._lib.svcm_get_stats(self._h, C.byref(s)), self._h)
         return {name: getattr(s, name) for name, _ in abi.Stats._fields_}
 
+    def profile(self):
+        """Sums over the iterations run since the previous call (svcm_get_profile)."""
+        p = abi.Profile()
+        _check(self._lib.svcm_get_profile(self._h, C.byref(p)), self._h)
+        return {name: getattr(p, name) for name, _ in abi.Profile._fields_}
+
     def event_record(self, slot):
         _check(self._lib.svcm_event_record(self._h, slot), self._h)
 

@@ -176,12 +176,15 @@ def test_hashgrid_edge_cases():
     assert close(gc, oc).all()
 
 
+@pytest.mark.parametrize("merge_kernel", ["1", "8", "32"])
 @pytest.mark.parametrize("scene_id,alg,w,ppm", [(1, "vcm", 128, False), (3, "bpm", 128, False), (1, "ppm", 96, True),
                                                 (0, "vcm", 96, False)])
-def test_hashgrid_query_against_oracle(scene_id, alg, w, ppm):
+def test_hashgrid_query_against_oracle(scene_id, alg, w, ppm, merge_kernel, monkeypatch):
     """HashGrid::Process + RangeQuery::Process on the oracle's light vertices: visited and
     accepted counts exact, merged radiance within 1e-5 relative."""
     from test_oracle import synthetic_queries
+    # both merge kernels (lane-per-query with compaction, cooperative groups) are product code
+    monkeypatch.setenv("SVCM_MERGE_GROUP", merge_kernel)
     scene, orc = oracle_iteration(scene_id, alg, w)
     verts, _, mats, normals, _ = orc.light_vertices()
     radius, _, _, mis_vc = orc.iteration_constants(0)

@@ -132,13 +132,13 @@ def test_accumulate_clear_and_linearity():
 def test_merge_group_sizes_agree():
     scene = sv.Scene.cornell_box(3, 128, 128)
     imgs = []
-    for group in (8, 16, 32):
+    for group in (1, 8, 16, 32):
         r = sv.VertexCM(scene, "bpm"); r.max_path_length = 10
         r.set_option(abi.OPT_MERGE_GROUP, group)
         r.run_iterations(0, 2)
         imgs.append(r.accum()[0])
         r.close()
-    assert rel_l2(imgs[1], imgs[0]) < 1e-5 and rel_l2(imgs[2], imgs[0]) < 1e-5
+    assert max(rel_l2(imgs[k], imgs[0]) for k in (1, 2, 3)) < 1e-5
 
 
 @pytest.mark.parametrize("scene_id,alg", [(1, "vcm"), (3, "bpm"), (0, "bpt")])
