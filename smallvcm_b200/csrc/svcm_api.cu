@@ -97,8 +97,9 @@ struct svcm_renderer
     VertexStore verts;
     uint32_t  vertSlots;            // rows of verts.pathVerts
     uint8_t  *pathVertCount;
-    QueryStore queries;
-    ShadowQueue shadow;             // counts: [2 * countsAlloc] (light bounces, then camera bounces)
+    QueryStore queries;             // camera vertices (connection + merge consumers)
+    PairStore pairs;
+    ShadowQueue shadow;             // counts: [0] light pass, [1] camera pass
     unsigned long long *counters;   // CNT_WORDS
     unsigned long long *hostCounters; // pinned ring [SVCM_PROFILE_RING][CNT_WORDS]
     int       ringLaunches[SVCM_PROFILE_RING];
@@ -242,7 +243,8 @@ void freeVerts(svcm_renderer *r)
 void freeQueries(svcm_renderer *r)
 {
     devFree(r->queries.q0); devFree(r->queries.q1); devFree(r->queries.q2); devFree(r->queries.q3);
-    r->queries.capacity = 0;
+    devFree(r->queries.q4); devFree(r->pairs.pairs);
+    r->queries.capacity = 0; r->pairs.capacity = 0;
 }
 void freeGridSorted(svcm_renderer *r)
 {
@@ -295,23 +297,12 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
     const uint32_t needCounts = camBounces + 3u;
     if(needCounts > r->countsAlloc)
     {
-        devFree(r->queueCountsLight); devFree(r->queueCountsCamera); devFree(r->shadow.counts);
+        devFree(r->queueCountsLight); devFree(r->queueCountsCamera);
         if((rc = devAlloc(r, &r->queueCountsLight, needCounts))) return rc;
         if((rc = devAlloc(r, &r->queueCountsCamera, needCounts))) return rc;
-        if((rc = devAlloc(r, &r->shadow.counts, size_t(needCounts) * 2))) return rc;
         r->countsAlloc = needCounts;
     }
-    if(r->shadow.capacity == 0 && (r->useVC || r->lightTraceOnly))
-    {
-        // one bounce queues at most (1 + stored vertices of the path) segments per camera path
-        // and one per light path; 4 per path covers the measured mix (scene 1 vcm: 3.0 on the
-        // first bounce), anything beyond is traced inline by the producer
-        const uint64_t cap = std::min<uint64_t>(uint64_t(r->localPaths) * 4u, 0xFFFFFF00u);
-        if((rc = devAlloc(r, &r->shadow.r0, cap))) return rc;
-        if((rc = devAlloc(r, &r->shadow.r1, cap))) return rc;
-        if((rc = devAlloc(r, &r->shadow.r2, cap))) return rc;
-        r->shadow.capacity = uint32_t(cap);
-    }
+    if(!r->shadow.counts) if((rc = devAlloc(r, &r->shadow.counts, 2))) return rc;
 
     size_t freeB = 0, totalB = 0;
     cudaMemGetInfo(&freeB, &totalB);
@@ -342,26 +333,61 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
             if((rc = ensureGridSorted(r, r->verts.capacity))) return rc;
     }
 
-    if(r->useVM)
+    // camera vertices: at most one per camera bounce that can still connect or merge
+    if(!r->lightTraceOnly)
     {
-        const uint64_t worst = uint64_t(r->localPaths) * (r->ppm ? 1u : camBounces);
-        if(r->queries.capacity < worst)
+        const uint64_t worst = uint64_t(r->localPaths) * (r->ppm ? 1u : std::max(1u, camBounces - 1u));
+        if(r->queries.capacity < worst && r->queries.capacity < 0xFFFFFF00u)
         {
             const uint32_t old = r->queries.capacity;
             freeQueries(r);
             cudaMemGetInfo(&freeB, &totalB);
-            const uint64_t budget = uint64_t(double(freeB) * 0.5);
-            uint64_t cap = std::min<uint64_t>(worst, budget / 64u);
+            const uint64_t perVertex = 80u + (r->useVC ? 8u * 12u : 0u);
+            uint64_t cap = std::min<uint64_t>(worst, uint64_t(double(freeB) * 0.4) / perVertex);
             cap = std::min<uint64_t>(cap, 0xFFFFFF00u);
             cap = std::max<uint64_t>(cap, old);
             if((rc = devAlloc(r, &r->queries.q0, cap))) return rc;
             if((rc = devAlloc(r, &r->queries.q1, cap))) return rc;
             if((rc = devAlloc(r, &r->queries.q2, cap))) return rc;
             if((rc = devAlloc(r, &r->queries.q3, cap))) return rc;
+            if(r->useVC) if((rc = devAlloc(r, &r->queries.q4, cap))) return rc;
             r->queries.capacity = uint32_t(cap);
         }
-        if((rc = ensureGridCells(r, r->paths))) return rc;
     }
+    // (camera vertex, light vertex) pairs: a camera vertex of length c pairs with at most
+    // maxLen-1-c light vertices (see k_cameraBounce), i.e. sum_{c=1}^{maxLen-2} (maxLen-1-c) per path
+    if(r->useVC)
+    {
+        uint64_t perPath = 0;
+        for(uint32_t c = 1; c + 1u < maxLen; c++) perPath += std::min<uint64_t>(lightBounces, maxLen - 1u - c);
+        const uint64_t worst = std::max<uint64_t>(1, uint64_t(r->localPaths) * perPath);
+        if(r->pairs.capacity < worst && r->pairs.capacity < 0xFFFFFF00u)
+        {
+            const uint32_t old = r->pairs.capacity;
+            devFree(r->pairs.pairs);
+            cudaMemGetInfo(&freeB, &totalB);
+            uint64_t cap = std::min<uint64_t>(worst, uint64_t(double(freeB) * 0.25) / 8u);
+            cap = std::min<uint64_t>(cap, 0xFFFFFF00u);
+            cap = std::max<uint64_t>(cap, old);
+            if((rc = devAlloc(r, &r->pairs.pairs, cap))) return rc;
+            r->pairs.capacity = uint32_t(cap);
+        }
+    }
+    // visibility segments: one per light vertex splat, one per direct-illumination sample and
+    // one per pair at most; sized for the measured mix (scene 1 vcm: 7.9 per path), a full
+    // queue makes producers trace inline
+    if((r->useVC || r->lightTraceOnly) && r->shadow.capacity == 0)
+    {
+        cudaMemGetInfo(&freeB, &totalB);
+        uint64_t cap = uint64_t(r->localPaths) * (r->lightTraceOnly ? std::min(lightBounces, 4u) : 12u);
+        cap = std::min<uint64_t>(cap, uint64_t(double(freeB) * 0.3) / 48u);
+        cap = std::min<uint64_t>(std::max<uint64_t>(cap, 1024u), 0xFFFFFF00u);
+        if((rc = devAlloc(r, &r->shadow.r0, cap))) return rc;
+        if((rc = devAlloc(r, &r->shadow.r1, cap))) return rc;
+        if((rc = devAlloc(r, &r->shadow.r2, cap))) return rc;
+        r->shadow.capacity = uint32_t(cap);
+    }
+    if(r->useVM) if((rc = ensureGridCells(r, r->paths))) return rc;
     return SVCM_OK;
 }
 
@@ -482,7 +508,7 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     SVCM_CUDA(r, cudaMemsetAsync(r->counters, 0, sizeof(unsigned long long) * CNT_WORDS, st));
     SVCM_CUDA(r, cudaMemsetAsync(r->queueCountsLight, 0, sizeof(uint32_t) * r->countsAlloc, st));
     SVCM_CUDA(r, cudaMemsetAsync(r->queueCountsCamera, 0, sizeof(uint32_t) * r->countsAlloc, st));
-    SVCM_CUDA(r, cudaMemsetAsync(r->shadow.counts, 0, sizeof(uint32_t) * 2 * r->countsAlloc, st));
+    SVCM_CUDA(r, cudaMemsetAsync(r->shadow.counts, 0, sizeof(uint32_t) * 2, st));
     if(r->useVC) SVCM_CUDA(r, cudaMemsetAsync(r->pathVertCount, 0, r->localPaths, st));
     if(timed) cudaEventRecord(ev[0], st);
     th[1] = hostNowMs();
@@ -492,6 +518,7 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     a.verts = r->verts;
     a.pathVertCount = r->pathVertCount;
     a.queries = r->queries;
+    a.pairs = r->pairs;
     a.shadow = r->shadow;
     a.counters = r->counters;
     a.accum = r->accum;
@@ -505,11 +532,11 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
         a.in = r->queue[(b + 1) & 1]; a.out = r->queue[b & 1];
         launchLightBounce(r->scene, ic, a, b, r->localPaths, st);
         launches++;
-        if(r->useVC || r->lightTraceOnly)
-        {
-            launchShadow(r->scene, ic, a, b, r->localPaths, st);
-            launches++;
-        }
+    }
+    if(r->useVC || r->lightTraceOnly)
+    {
+        launchShadow(r->scene, ic, a, 0, st);     // visibility of all camera connections, then splat
+        launches++;
     }
     if(timed) cudaEventRecord(ev[1], st);
     th[2] = hostNowMs();
@@ -544,17 +571,17 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     {
         const uint32_t camBounces = std::max(1u, maxLen);
         a.queueCounts = r->queueCountsCamera;
-        a.shadow.counts = r->shadow.counts + r->countsAlloc;
         for(uint32_t b = 1; b <= camBounces; b++)
         {
             a.in = r->queue[(b + 1) & 1]; a.out = r->queue[b & 1];
             launchCameraBounce(r->scene, ic, a, b, r->localPaths, st);
             launches++;
-            if(r->useVC && b < camBounces)     // the last camera bounce cannot connect (length == maxLen)
-            {
-                launchShadow(r->scene, ic, a, b, r->shadow.capacity, st);
-                launches++;
-            }
+        }
+        if(r->useVC)
+        {
+            launchConnect(r->scene, ic, a, st);       // every (camera vertex, light vertex) pair
+            launchShadow(r->scene, ic, a, 1, st);     // direct-illumination + connection visibility
+            launches += 2;
         }
     }
     if(timed) cudaEventRecord(ev[4], st);
@@ -563,7 +590,7 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     // ---- deferred merging of all queued camera vertices ------------------------------------
     if(r->useVM && !r->lightTraceOnly)
     {
-        launchMerge(r->scene, ic, r->queries, r->counters + CNT_QUERIES, 0, r->grid, r->accum, NULL, NULL,
+        launchMerge(r->scene, ic, r->queries, r->counters + CNT_CAM_VERTS, 0, r->grid, r->accum, NULL, NULL,
                     r->counters, r->mergeGroup, r->gridCapacity, st);
         launches++;
     }
@@ -661,6 +688,7 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     memset(&r->verts, 0, sizeof(r->verts)); r->vertSlots = 0; r->pathVertCount = NULL;
     memset(&r->queries, 0, sizeof(r->queries));
     memset(&r->shadow, 0, sizeof(r->shadow));
+    memset(&r->pairs, 0, sizeof(r->pairs));
     r->counters = NULL; r->hostCounters = NULL; r->accum = NULL;
     memset(&r->grid, 0, sizeof(r->grid)); r->gridCells = 0; r->gridCapacity = 0; r->bboxInit = NULL;
     r->comm = NULL; r->gPosLen = r->gThrVcm = r->gDirVm = NULL; r->gContProb = NULL; r->gatherCapacity = 0;
@@ -1135,6 +1163,7 @@ int svcm_hashgrid_query(svcm_hashgrid *g, const SvcmSceneDesc *scene, const Svcm
     QueryStore qs;
     qs.q0 = s.alloc<float4>(size_t(count), e); qs.q1 = s.alloc<float4>(size_t(count), e);
     qs.q2 = s.alloc<float4>(size_t(count), e); qs.q3 = s.alloc<float4>(size_t(count), e);
+    qs.q4 = NULL;
     qs.capacity = uint32_t(count);
     float *dContrib = s.alloc<float>(size_t(count) * 3, e);
     int32_t *dCounts = s.alloc<int32_t>(size_t(count) * 2, e);
@@ -1145,6 +1174,7 @@ int svcm_hashgrid_query(svcm_hashgrid *g, const SvcmSceneDesc *scene, const Svcm
         ic.radius = g->radius; ic.radiusSqr = g->radius * g->radius; ic.invCellSize = 1.f / (g->radius * 2.f);
         ic.numCells = g->numCells; ic.minLen = minPathLength; ic.maxLen = maxPathLength;
         ic.misVcWeightFactor = misVcWeightFactor; ic.ppm = ppm != 0; ic.useVM = 1;
+        ic.vmNormalization = 1.f;             // the entry point returns the un-normalised mContrib
         launchPackMergeQueries(sc, dq, count, qs, 0);
         // the parity tests exercise both merge kernels: the environment picks the variant
         const char *variant = getenv("SVCM_MERGE_GROUP");

@@ -85,12 +85,24 @@ struct GridBuffers
     int32_t  *sIndex;     // original (virtual) index at each sorted position  (mIndices)
 };
 
-// Merge queries emitted by the camera pass (RangeQuery, src/vertexcm.hxx:109-178):
-//   q0 = position.xyz | pixel (bits)      q1 = normal.xyz | pathLength | matID << 16 (bits)
-//   q2 = local fixed dir.xyz | dVCM       q3 = throughput * vmNormalization .xyz | dVM
+// Camera vertices: every non-delta vertex of a camera sub-path that can still be connected or
+// merged is appended here once by its bounce kernel and consumed twice afterwards — by
+// k_connect (vertex connection, src/vertexcm.hxx:498-526) through the pair list and by the
+// merge kernels as a RangeQuery (src/vertexcm.hxx:109-178, 530-538).
+//   q0 = position.xyz | pixel (bits)      q1 = normal.xyz | pathLength | matID << 16 | flags << 24
+//   q2 = local fixed dir.xyz | dVCM       q3 = throughput.xyz | dVM
+//   q4 = dVC | local path index (bits) | - | -          (vertex connection only)
 struct QueryStore
 {
-    float4 *q0, *q1, *q2, *q3;
+    float4 *q0, *q1, *q2, *q3, *q4;
+    uint32_t capacity;
+};
+enum { CAMV_MERGEABLE = 1u << 24 };   // inside the light-vertex bbox and merging is on
+
+// (camera vertex index, k): connect camera vertex to the k-th stored vertex of its light path
+struct PairStore
+{
+    uint2   *pairs;
     uint32_t capacity;
 };
 
@@ -102,14 +114,14 @@ struct QueryStore
 struct ShadowQueue
 {
     float4 *r0, *r1, *r2;
-    uint32_t *counts;       // [bounce index] rays queued by that bounce
+    uint32_t *counts;       // [0] rays queued by the light pass, [1] by the camera pass
     uint32_t capacity;      // a full queue makes the producer trace its ray inline instead
 };
 
 // device-side counters (one block of 64-bit words, zeroed per iteration)
 enum {
     CNT_LIGHT_VERTS = 0, CNT_QUERIES, CNT_CANDIDATES, CNT_ACCEPTED, CNT_LIGHT_RAYS,
-    CNT_CAMERA_RAYS, CNT_SHADOW_RAYS, CNT_OVERFLOW, CNT_WORDS
+    CNT_CAMERA_RAYS, CNT_SHADOW_RAYS, CNT_OVERFLOW, CNT_CAM_VERTS, CNT_PAIRS, CNT_WORDS
 };
 
 struct TraceArgs
@@ -119,6 +131,7 @@ struct TraceArgs
     VertexStore verts;
     uint8_t    *pathVertCount;   // [local path] number of stored vertices
     QueryStore  queries;
+    PairStore   pairs;
     ShadowQueue shadow;
     unsigned long long *counters; // CNT_*
     float      *accum;           // W*H*3 accumulated image
@@ -151,15 +164,19 @@ void launchLightBounce(const DevScene &sc, const IterConst &ic, const TraceArgs 
                        uint32_t bounce, uint32_t maxItems, cudaStream_t stream);
 void launchCameraBounce(const DevScene &sc, const IterConst &ic, const TraceArgs &args,
                         uint32_t bounce, uint32_t maxItems, cudaStream_t stream);
-// any-hit tests + splats for the rays queued by `bounce` (count read on the device)
-void launchShadow(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t bounce,
-                  uint32_t maxItems, cudaStream_t stream);
+// vertex connection of every queued (camera vertex, light vertex) pair
+void launchConnect(const DevScene &sc, const IterConst &ic, const TraceArgs &args, cudaStream_t stream);
+// any-hit tests + splats for the rays queued by pass `which` (0 light, 1 camera; count read on
+// the device)
+void launchShadow(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t which,
+                  cudaStream_t stream);
 // HashGrid::Build: bbox -> keys + histogram -> exclusive scan -> scatter. Returns the
 // number of kernels launched.
 int  launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers &grid,
                      cudaStream_t stream);
-// HashGrid::Process + RangeQuery::Process over `numQueries` (read from *queryCount on the
-// device when queryCount != NULL, else the host value) queued queries.
+// HashGrid::Process + RangeQuery::Process over the queued camera vertices flagged
+// CAMV_MERGEABLE (their number is read from *queryCount on the device when queryCount != NULL,
+// else the host value).
 void launchMerge(const DevScene &sc, const IterConst &ic, const QueryStore &queries,
                  const unsigned long long *queryCount, uint32_t hostQueryCount,
                  const GridBuffers &grid, float *accum, float *contribOut, int32_t *countsOut,

@@ -81,10 +81,10 @@ SVCM_D f3 xyz(float4 a) { return mk3(a.x, a.y, a.z); }
 // Queue one visibility test: "add `contrib` to `pixel` unless point -> point + dir*tMax is
 // blocked" (Scene::Occluded, reference src/scene.hxx:72-85). If the queue is full the ray is
 // traced on the spot — slower, never wrong.
-SVCM_D void emitShadowRay(const DevScene &sc, const ShadowQueue &q, uint32_t bounce, float *accum,
+SVCM_D void emitShadowRay(const DevScene &sc, const ShadowQueue &q, uint32_t which, float *accum,
                           f3 point, f3 dir, float tMax, uint32_t pixel, f3 contrib)
 {
-    const uint32_t slot = activeAppend(q.counts + bounce);
+    const uint32_t slot = activeAppend(q.counts + which);
     if(slot < q.capacity)
     {
         q.r0[slot] = mk4(point, tMax);
@@ -226,7 +226,7 @@ SVCM_D void generateLightSample(const DevScene &sc, const IterConst &ic, SubPath
 // ConnectToCamera, reference src/vertexcm.hxx:862-933: splat the light vertex onto the
 // image through the pinhole; float atomics because the target pixel is arbitrary.
 SVCM_D void connectToCamera(const DevScene &sc, const IterConst &ic, const SubPath &s, f3 hitPoint,
-                            const Bsdf &bsdf, const TraceArgs &a, uint32_t bounce)
+                            const Bsdf &bsdf, const TraceArgs &a)
 {
     const f3 camPos = ld3(sc.camPos), camFwd = ld3(sc.camFwd);
     f3 dirToCamera = camPos - hitPoint;
@@ -261,7 +261,7 @@ SVCM_D void connectToCamera(const DevScene &sc, const IterConst &ic, const SubPa
 
     // Framebuffer::AddColor target, reference src/framebuffer.hxx:43-57; visibility deferred
     const uint32_t pixel = uint32_t(int(raster.x)) + uint32_t(int(raster.y)) * uint32_t(ic.resX);
-    emitShadowRay(sc, a.shadow, bounce, a.accum, hitPoint, dirToCamera, distance, pixel, contrib);
+    emitShadowRay(sc, a.shadow, 0u, a.accum, hitPoint, dirToCamera, distance, pixel, contrib);
 }
 
 // One bounce of every live light sub-path: reference src/vertexcm.hxx:328-393 (loop body)
@@ -338,7 +338,7 @@ k_lightBounce(const __grid_constant__ DevScene sc, const __grid_constant__ IterC
         if(alive)
         {
             if(!bsdf.isDelta() && (ic.useVC || ic.lightTraceOnly) && (s.length + 1u >= ic.minLen))
-                connectToCamera(sc, ic, s, hitPoint, bsdf, a, bounce);
+                connectToCamera(sc, ic, s, hitPoint, bsdf, a);
 
             // terminate if the path would become too long after scattering
             if(s.length + 2u > ic.maxLen) alive = false;
@@ -511,7 +511,6 @@ k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ Iter
         Hit hit;
         Bsdf bsdf;
         f3 hitPoint = mk3(0.f);
-        bool emitQuery = false;
 
         if(alive)
         {
@@ -552,64 +551,75 @@ k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ Iter
             else if(s.length >= ic.maxLen) alive = false;
         }
 
+        // a non-delta vertex is recorded once; vertex connection (:498-526) and merging (:530-538)
+        // consume the record later (k_connect, k_merge*) — neither draws random numbers nor
+        // steers the walk, so deferring them changes nothing but the order of summation
+        bool record = false, mergeable = false;
+        uint32_t nv = 0u, lpath = 0u;
         if(alive && !bsdf.isDelta())
         {
             if(ic.useVC)
             {
-                // vertex connection: to a light source ...
+                // vertex connection to a light source: evaluate here, visibility deferred
                 if(s.length + 1u >= ic.minLen)
                 {
                     f3 dir; float dist;
                     const f3 c = s.throughput * directIllumination(sc, ic, s, hitPoint, bsdf, dir, dist);
-                    if(!iszero(c)) emitShadowRay(sc, a.shadow, bounce, a.accum, hitPoint, dir, dist, s.extra, c);
+                    if(!iszero(c)) emitShadowRay(sc, a.shadow, 1u, a.accum, hitPoint, dir, dist, s.extra, c);
                 }
-
-                // ... and to the vertices of this pixel's own light sub-path (:498-526)
-                const uint32_t l = globalToLocalPath(ic, s.path);
-                const uint32_t nv = a.pathVertCount[l];
-                for(uint32_t k = 0; k < nv; k++)
-                {
-                    const int32_t vi = a.verts.pathVerts[size_t(k) * ic.localPaths + l];
-                    const float4 pl = a.verts.posLen[vi];
-                    const uint32_t lvLen = __float_as_uint(pl.w);
-                    if(lvLen + 1u + s.length < ic.minLen) continue;
-                    if(lvLen + 1u + s.length > ic.maxLen) break;      // stored in increasing length
-                    const float4 tv = a.verts.thrVcm[vi];
-                    const float4 nv4 = a.verts.nrmVc[vi];
-                    const float4 lm = a.verts.ldfMat[vi];
-                    Bsdf lvBsdf;
-                    lvBsdf.frame.setFromZ(xyz(nv4));
-                    lvBsdf.localDirFix = xyz(lm);
-                    lvBsdf.diffProb = lvBsdf.phongProb = lvBsdf.reflProb = lvBsdf.refrProb = 0.f;
-                    bsdfFromLocal(sc, __float_as_int(lm.w), lvBsdf);
-                    f3 dir; float dist;
-                    const f3 c = (s.throughput * xyz(tv)) *
-                        connectVertices(sc, ic, xyz(pl), lvBsdf, tv.w, nv4.w, bsdf, hitPoint, s, dir, dist);
-                    if(!iszero(c)) emitShadowRay(sc, a.shadow, bounce, a.accum, hitPoint, dir, dist, s.extra, c);
-                }
+                lpath = globalToLocalPath(ic, s.path);
+                // the k-th stored light vertex has path length >= k+1, so only the first
+                // maxLen-1-length of them can pass the window of src/vertexcm.hxx:519-521
+                nv = a.pathVertCount[lpath];
+                nv = min(nv, ic.maxLen - 1u - s.length);
             }
             if(ic.useVM)
             {
                 // HashGrid::Process early-out: query outside the particle bbox
                 // (reference src/hashgrid.hxx:116-122)
                 const f3 dMin = hitPoint - bbMin, dMax = bbMax - hitPoint;
-                emitQuery = !(dMin.x < 0.f || dMax.x < 0.f || dMin.y < 0.f || dMax.y < 0.f ||
+                mergeable = !(dMin.x < 0.f || dMax.x < 0.f || dMin.y < 0.f || dMax.y < 0.f ||
                               dMin.z < 0.f || dMax.z < 0.f);
             }
+            record = mergeable || nv > 0u;
         }
 
-        const uint32_t qidx = warpAppend64(a.counters + CNT_QUERIES, emitQuery);
-        if(emitQuery)
+        const uint32_t qidx = warpAppend64(a.counters + CNT_CAM_VERTS, record);
+        // pairs (this vertex, k-th vertex of its own light sub-path): contiguous block per lane
+        uint32_t pairBase = 0u;
+        {
+            uint32_t inc = record ? nv : 0u;
+#pragma unroll
+            for(int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o);
+                if(laneId() >= uint32_t(o)) inc += t;
+            }
+            const uint32_t total = __shfl_sync(FULL_MASK, inc, 31);
+            unsigned long long base = 0ull;
+            if(total && laneId() == 31u) base = atomicAdd(a.counters + CNT_PAIRS, (unsigned long long)total);
+            base = __shfl_sync(FULL_MASK, base, 31);
+            pairBase = uint32_t(base) + inc - (record ? nv : 0u);
+        }
+        if(record)
         {
             if(qidx < a.queries.capacity)
             {
                 a.queries.q0[qidx] = mk4(hitPoint, __uint_as_float(s.extra));
-                a.queries.q1[qidx] = mk4(hit.normal, __uint_as_float(s.length | (uint32_t(hit.matID) << 16)));
+                a.queries.q1[qidx] = mk4(hit.normal, __uint_as_float(s.length | (uint32_t(hit.matID) << 16) |
+                                                                     (mergeable ? CAMV_MERGEABLE : 0u)));
                 a.queries.q2[qidx] = mk4(bsdf.localDirFix, s.dVCM);
-                a.queries.q3[qidx] = mk4(s.throughput * ic.vmNormalization, s.dVM);
+                a.queries.q3[qidx] = mk4(s.throughput, s.dVM);
+                if(ic.useVC) a.queries.q4[qidx] = make_float4(s.dVC, __uint_as_float(lpath), 0.f, 0.f);
+                for(uint32_t k = 0; k < nv; k++)
+                {
+                    if(pairBase + k < a.pairs.capacity) a.pairs.pairs[pairBase + k] = make_uint2(qidx, k);
+                    else atomicAdd(a.counters + CNT_OVERFLOW, 1ull);
+                }
             }
             else atomicAdd(a.counters + CNT_OVERFLOW, 1ull);
         }
+        warpCount(a.counters + CNT_QUERIES, mergeable ? 1u : 0u);
 
         if(alive)
         {
@@ -628,7 +638,54 @@ k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ Iter
     warpCount(a.counters + CNT_CAMERA_RAYS, nRays);
 }
 
-// The deferred Scene::Occluded tests of one bounce (reference src/scene.hxx:72-85), one lane per
+// Vertex connection (reference src/vertexcm.hxx:498-526 + ConnectVertices :743-809), one lane
+// per (camera vertex, light vertex) pair: both BSDFs are rebuilt from the stored records, the
+// connection is evaluated with its MIS weight and, if it carries energy, its visibility
+// segment is queued for k_shadow.
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_connect(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
+          const __grid_constant__ TraceArgs a)
+{
+    const uint32_t count = uint32_t(min(a.counters[CNT_PAIRS], (unsigned long long)a.pairs.capacity));
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    {
+        const uint2 pr = a.pairs.pairs[i];
+        const float4 q0 = a.queries.q0[pr.x], q1 = a.queries.q1[pr.x], q2 = a.queries.q2[pr.x],
+                     q3 = a.queries.q3[pr.x], q4 = a.queries.q4[pr.x];
+        const uint32_t bits = __float_as_uint(q1.w);
+        const uint32_t camLen = bits & 0xFFFFu;
+        const uint32_t lpath = __float_as_uint(q4.y);
+
+        const int32_t vi = a.verts.pathVerts[size_t(pr.y) * ic.localPaths + lpath];
+        const float4 pl = a.verts.posLen[vi];
+        const uint32_t lvLen = __float_as_uint(pl.w);
+        // path-length window, src/vertexcm.hxx:512-521
+        if(lvLen + 1u + camLen < ic.minLen || lvLen + 1u + camLen > ic.maxLen) continue;
+        const float4 tv = a.verts.thrVcm[vi];
+        const float4 nv4 = a.verts.nrmVc[vi];
+        const float4 lm = a.verts.ldfMat[vi];
+
+        Bsdf camBsdf;                      // BSDF<false>::Setup at the camera vertex
+        camBsdf.frame.setFromZ(xyz(q1));
+        camBsdf.localDirFix = xyz(q2);
+        camBsdf.diffProb = camBsdf.phongProb = camBsdf.reflProb = camBsdf.refrProb = 0.f;
+        bsdfFromLocal(sc, int32_t((bits >> 16) & 0xFFu), camBsdf);
+        Bsdf lvBsdf;                       // BSDF<true>::Setup at the light vertex
+        lvBsdf.frame.setFromZ(xyz(nv4));
+        lvBsdf.localDirFix = xyz(lm);
+        lvBsdf.diffProb = lvBsdf.phongProb = lvBsdf.reflProb = lvBsdf.refrProb = 0.f;
+        bsdfFromLocal(sc, __float_as_int(lm.w), lvBsdf);
+
+        SubPath s;                         // the camera state ConnectVertices reads
+        s.dVCM = q2.w; s.dVC = q4.x;
+        f3 dir; float dist;
+        const f3 c = (xyz(q3) * xyz(tv)) *
+            connectVertices(sc, ic, xyz(pl), lvBsdf, tv.w, nv4.w, camBsdf, xyz(q0), s, dir, dist);
+        if(!iszero(c)) emitShadowRay(sc, a.shadow, 1u, a.accum, xyz(q0), dir, dist, __float_as_uint(q0.w), c);
+    }
+}
+
+// The deferred Scene::Occluded tests of one pass (reference src/scene.hxx:72-85), one lane per
 // queued segment, then Framebuffer::AddColor for the unoccluded ones. Every lane runs the same
 // primitive loop: this is where the bounce kernels' divergent any-hit loops went.
 __global__ void __launch_bounds__(SVCM_BLOCK)
@@ -859,7 +916,9 @@ k_merge(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst i
         const float4 q0 = qs.q0[q], q1 = qs.q1[q], q2 = qs.q2[q], q3 = qs.q3[q];
         const f3 qpos = xyz(q0);
         const uint32_t lenMat = __float_as_uint(q1.w);
+        if(!(lenMat & CAMV_MERGEABLE)) continue;          // recorded for vertex connection only
         const uint32_t camLen = lenMat & 0xFFFFu;
+        const int32_t camMat = int32_t((lenMat >> 16) & 0xFFu);
         const float camdVCM = q2.w, camdVM = q3.w;
 
         // camera BSDF: BSDF<false>::Setup from the stored normal / local direction / material
@@ -867,8 +926,8 @@ k_merge(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst i
         bsdf.frame.setFromZ(xyz(q1));
         bsdf.localDirFix = xyz(q2);
         bsdf.diffProb = bsdf.phongProb = bsdf.reflProb = bsdf.refrProb = 0.f;
-        bsdfFromLocal(sc, int32_t(lenMat >> 16), bsdf);
-        const SvcmMaterial &mat = sc.mats[lenMat >> 16];
+        bsdfFromLocal(sc, camMat, bsdf);
+        const SvcmMaterial &mat = sc.mats[camMat];
 
         // the 8 cells: the query's cell and its neighbours on the near side of each axis
         const f3 cellPt = mk3(ic.invCellSize * (qpos.x - bbMin.x), ic.invCellSize * (qpos.y - bbMin.y),
@@ -977,7 +1036,7 @@ k_merge(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst i
             }
             if(countsOut) { countsOut[2ull * q] = int32_t(total); countsOut[2ull * q + 1] = int32_t(accepted); }
             // color += cameraState.mThroughput * mVmNormalization * query.GetContrib()  (:534)
-            if(accum) addPixel(accum, __float_as_uint(q0.w), xyz(q3) * contrib);
+            if(accum) addPixel(accum, __float_as_uint(q0.w), (xyz(q3) * ic.vmNormalization) * contrib);
         }
     }
 
@@ -1020,6 +1079,7 @@ SVCM_D void mergeEvaluatePairs(const DevScene &sc, const IterConst &ic, const Gr
         const uint32_t lvLen = __float_as_uint(g.sPosLen[idx].w);
         const uint32_t lenMat = __float_as_uint(w.q[12][owner]);
         const uint32_t camLen = lenMat & 0xFFFFu;
+        const uint32_t camMat = (lenMat >> 16) & 0xFFu;
         // RangeQuery::Process, reference src/vertexcm.hxx:130-169
         if(!((lvLen + camLen > ic.maxLen) || (lvLen + camLen < ic.minLen)))
         {
@@ -1034,7 +1094,7 @@ SVCM_D void mergeEvaluatePairs(const DevScene &sc, const IterConst &ic, const Gr
             {
                 b.diffProb = w.q[13][owner]; b.phongProb = w.q[14][owner]; b.contProb = w.q[15][owner];
                 float camDirPdfW, camRevPdfW;
-                const f3 f = bsdfEvaluateLocal(sc.mats[lenMat >> 16], b, localDirGen, camDirPdfW, camRevPdfW);
+                const f3 f = bsdfEvaluateLocal(sc.mats[camMat], b, localDirGen, camDirPdfW, camRevPdfW);
                 if(!iszero(f))
                 {
                     const float4 tv = g.sThrVcm[idx];
@@ -1075,7 +1135,7 @@ k_mergeLane(const __grid_constant__ DevScene sc, const __grid_constant__ IterCon
         q0i += gridDim.x * MERGE_WARPS * 32u)
     {
         const uint32_t q = q0i + lane;
-        const bool valid = q < nq;
+        bool valid = q < nq;
         f3 qpos = mk3(0.f), scale = mk3(0.f);
         uint32_t pixel = 0u;
         uint32_t cand = 0u, accepted = 0u;
@@ -1083,17 +1143,23 @@ k_mergeLane(const __grid_constant__ DevScene sc, const __grid_constant__ IterCon
 #pragma unroll
         for(int j = 0; j < 8; j++) { w.rangeStart[j][lane] = 0u; w.rangeEnd[j][lane] = 0u; }
 
+        float4 q1 = make_float4(0.f, 0.f, 0.f, 0.f);
         if(valid)
         {
-            const float4 q0 = qs.q0[q], q1 = qs.q1[q], q2 = qs.q2[q], q3 = qs.q3[q];
-            qpos = xyz(q0); scale = xyz(q3); pixel = __float_as_uint(q0.w);
+            q1 = qs.q1[q];
+            valid = (__float_as_uint(q1.w) & CAMV_MERGEABLE) != 0u;   // else: vertex connection only
+        }
+        if(valid)
+        {
+            const float4 q0 = qs.q0[q], q2 = qs.q2[q], q3 = qs.q3[q];
+            qpos = xyz(q0); scale = xyz(q3) * ic.vmNormalization; pixel = __float_as_uint(q0.w);
             const uint32_t lenMat = __float_as_uint(q1.w);
             // camera BSDF: BSDF<false>::Setup from the stored normal / local direction / material
             Bsdf bsdf;
             bsdf.frame.setFromZ(xyz(q1));
             bsdf.localDirFix = xyz(q2);
             bsdf.diffProb = bsdf.phongProb = bsdf.reflProb = bsdf.refrProb = 0.f;
-            bsdfFromLocal(sc, int32_t(lenMat >> 16), bsdf);
+            bsdfFromLocal(sc, int32_t((lenMat >> 16) & 0xFFu), bsdf);
             w.q[0][lane] = bsdf.frame.x.x; w.q[1][lane] = bsdf.frame.x.y; w.q[2][lane] = bsdf.frame.x.z;
             w.q[3][lane] = bsdf.frame.y.x; w.q[4][lane] = bsdf.frame.y.y; w.q[5][lane] = bsdf.frame.y.z;
             w.q[6][lane] = bsdf.frame.z.x; w.q[7][lane] = bsdf.frame.z.y; w.q[8][lane] = bsdf.frame.z.z;
@@ -1290,7 +1356,8 @@ __global__ void k_packMergeQueries(const __grid_constant__ DevScene sc, const Sv
         // park it outside any bbox
         const f3 pos = usable ? ld3(q[i].position) : mk3(3e37f);
         store.q0[i] = mk4(pos, __uint_as_float(uint32_t(i)));
-        store.q1[i] = mk4(ld3(q[i].normal), __uint_as_float(q[i].pathLength | (uint32_t(q[i].matID) << 16)));
+        store.q1[i] = mk4(ld3(q[i].normal), __uint_as_float(q[i].pathLength | (uint32_t(q[i].matID) << 16) |
+                                                             CAMV_MERGEABLE));
         store.q2[i] = mk4(b.localDirFix, q[i].dVCM);
         store.q3[i] = mk4(mk3(1.f), q[i].dVM);
     }
@@ -1330,11 +1397,16 @@ void launchCameraBounce(const DevScene &sc, const IterConst &ic, const TraceArgs
     k_cameraBounce<<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
 }
 
-void launchShadow(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t bounce,
-                  uint32_t maxItems, cudaStream_t stream)
+void launchConnect(const DevScene &sc, const IterConst &ic, const TraceArgs &args, cudaStream_t stream)
+{
+    k_connect<<<gridFor(args.pairs.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args);
+}
+
+void launchShadow(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t which,
+                  cudaStream_t stream)
 {
     (void)ic;
-    k_shadow<<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, args, bounce);
+    k_shadow<<<gridFor(args.shadow.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, args, which);
 }
 
 int launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers &grid, cudaStream_t stream)
