@@ -99,6 +99,8 @@ struct svcm_renderer
     uint8_t  *pathVertCount;
     QueryStore queries;             // camera vertices (connection + merge consumers)
     PairStore pairs;
+    QuerySortBuffers qsort;
+    bool sortQueries;
     ShadowQueue shadow;             // counts: [0] light pass, [1] camera pass
     unsigned long long *counters;   // CNT_WORDS
     unsigned long long *hostCounters; // pinned ring [SVCM_PROFILE_RING][CNT_WORDS]
@@ -244,6 +246,7 @@ void freeQueries(svcm_renderer *r)
 {
     devFree(r->queries.q0); devFree(r->queries.q1); devFree(r->queries.q2); devFree(r->queries.q3);
     devFree(r->queries.q4); devFree(r->pairs.pairs);
+    devFree(r->qsort.key); devFree(r->qsort.order);
     r->queries.capacity = 0; r->pairs.capacity = 0;
 }
 void freeGridSorted(svcm_renderer *r)
@@ -351,6 +354,11 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
             if((rc = devAlloc(r, &r->queries.q2, cap))) return rc;
             if((rc = devAlloc(r, &r->queries.q3, cap))) return rc;
             if(r->useVC) if((rc = devAlloc(r, &r->queries.q4, cap))) return rc;
+            if(r->useVM)
+            {
+                if((rc = devAlloc(r, &r->qsort.key, cap))) return rc;
+                if((rc = devAlloc(r, &r->qsort.order, cap))) return rc;
+            }
             r->queries.capacity = uint32_t(cap);
         }
     }
@@ -387,7 +395,15 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
         if((rc = devAlloc(r, &r->shadow.r2, cap))) return rc;
         r->shadow.capacity = uint32_t(cap);
     }
-    if(r->useVM) if((rc = ensureGridCells(r, r->paths))) return rc;
+    if(r->useVM)
+    {
+        if((rc = ensureGridCells(r, r->paths))) return rc;
+        if(!r->qsort.cellCount)
+        {
+            if((rc = devAlloc(r, &r->qsort.cellCount, size_t(r->paths) + 1))) return rc;
+            if((rc = devAlloc(r, &r->qsort.blockSums, (size_t(r->paths) + 1) / 2048 + 2))) return rc;
+        }
+    }
     return SVCM_OK;
 }
 
@@ -590,7 +606,15 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     // ---- deferred merging of all queued camera vertices ------------------------------------
     if(r->useVM && !r->lightTraceOnly)
     {
-        launchMerge(r->scene, ic, r->queries, r->counters + CNT_CAM_VERTS, 0, r->grid, r->accum, NULL, NULL,
+        QueryStore qs = r->queries;
+        const unsigned long long *count = r->counters + CNT_CAM_VERTS;
+        if(r->sortQueries)
+        {
+            launches += launchQuerySort(ic, r->queries, r->counters + CNT_CAM_VERTS, r->grid.bboxBits, r->qsort, st);
+            qs.order = r->qsort.order;
+            count = r->counters + CNT_QUERIES;           // only the mergeable vertices are in the order
+        }
+        launchMerge(r->scene, ic, qs, count, 0, r->grid, r->accum, NULL, NULL,
                     r->counters, r->mergeGroup, r->gridCapacity, st);
         launches++;
     }
@@ -689,6 +713,7 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     memset(&r->queries, 0, sizeof(r->queries));
     memset(&r->shadow, 0, sizeof(r->shadow));
     memset(&r->pairs, 0, sizeof(r->pairs));
+    memset(&r->qsort, 0, sizeof(r->qsort)); r->sortQueries = getenv("SVCM_NO_QUERY_SORT") == NULL;
     r->counters = NULL; r->hostCounters = NULL; r->accum = NULL;
     memset(&r->grid, 0, sizeof(r->grid)); r->gridCells = 0; r->gridCapacity = 0; r->bboxInit = NULL;
     r->comm = NULL; r->gPosLen = r->gThrVcm = r->gDirVm = NULL; r->gContProb = NULL; r->gatherCapacity = 0;
@@ -778,6 +803,7 @@ void svcm_destroy(svcm_renderer *r)
     freeVerts(r); freeQueries(r); freeGridSorted(r); freeGather(r);
     devFree(r->pathVertCount); devFree(r->counters); devFree(r->accum);
     devFree(r->grid.cellCount); devFree(r->grid.blockSums); devFree(r->grid.bboxBits);
+    devFree(r->qsort.cellCount); devFree(r->qsort.blockSums);
     devFree(r->bboxInit); devFree(r->devCounts);
     if(r->hostCounters) cudaFreeHost(r->hostCounters);
     if(r->hostCounts) cudaFreeHost(r->hostCounts);
@@ -1163,7 +1189,7 @@ int svcm_hashgrid_query(svcm_hashgrid *g, const SvcmSceneDesc *scene, const Svcm
     QueryStore qs;
     qs.q0 = s.alloc<float4>(size_t(count), e); qs.q1 = s.alloc<float4>(size_t(count), e);
     qs.q2 = s.alloc<float4>(size_t(count), e); qs.q3 = s.alloc<float4>(size_t(count), e);
-    qs.q4 = NULL;
+    qs.q4 = NULL; qs.order = NULL;
     qs.capacity = uint32_t(count);
     float *dContrib = s.alloc<float>(size_t(count) * 3, e);
     int32_t *dCounts = s.alloc<int32_t>(size_t(count) * 2, e);

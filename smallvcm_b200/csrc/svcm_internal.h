@@ -96,6 +96,18 @@ struct QueryStore
 {
     float4 *q0, *q1, *q2, *q3, *q4;
     uint32_t capacity;
+    // optional processing order for the merge: indices of the CAMV_MERGEABLE vertices grouped by
+    // the hash bucket of their own cell (NULL: process 0..count-1 and skip the others)
+    const uint32_t *order;
+};
+
+// scratch of the query sort (a second counting sort over the same bucket space as the grid)
+struct QuerySortBuffers
+{
+    uint32_t *cellCount;   // [numCells + 1]
+    uint32_t *key;         // [query capacity]
+    uint32_t *order;       // [query capacity]
+    uint32_t *blockSums;
 };
 enum { CAMV_MERGEABLE = 1u << 24 };   // inside the light-vertex bbox and merging is on
 
@@ -164,6 +176,10 @@ void launchLightBounce(const DevScene &sc, const IterConst &ic, const TraceArgs 
                        uint32_t bounce, uint32_t maxItems, cudaStream_t stream);
 void launchCameraBounce(const DevScene &sc, const IterConst &ic, const TraceArgs &args,
                         uint32_t bounce, uint32_t maxItems, cudaStream_t stream);
+// groups the mergeable camera vertices by cell (counting sort of indices): neighbouring lanes of
+// the merge kernel then walk the same cell ranges. Returns the number of kernels launched.
+int launchQuerySort(const IterConst &ic, const QueryStore &queries, const unsigned long long *vertexCount,
+                    const int32_t *bboxBits, const QuerySortBuffers &qs, cudaStream_t stream);
 // vertex connection of every queued (camera vertex, light vertex) pair
 void launchConnect(const DevScene &sc, const IterConst &ic, const TraceArgs &args, cudaStream_t stream);
 // any-hit tests + splats for the rays queued by pass `which` (0 light, 1 camera; count read on

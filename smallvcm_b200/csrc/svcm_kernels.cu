@@ -868,17 +868,69 @@ k_scanAdd(uint32_t *data, uint32_t n, const uint32_t *tileSums)
 __global__ void __launch_bounds__(SVCM_BLOCK)
 k_gridScatter(const __grid_constant__ MergeSet set, const __grid_constant__ GridBuffers g)
 {
+    // four records per thread per trip: the cursor atomics return values (300+ cycles each),
+    // so they are issued back to back before any dependent store
     const uint32_t total = mergeSetTotal(set);
-    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    for(uint32_t i0 = blockIdx.x * blockDim.x * 4u + threadIdx.x; i0 < total; i0 += gridDim.x * blockDim.x * 4u)
     {
-        const uint32_t key = g.cellKey[i];
-        if(key == 0xFFFFFFFFu) continue;
-        const uint32_t dst = atomicAdd(g.cellCount + key, 1u);
-        g.sPosLen[dst]   = set.posLen[i];
-        g.sThrVcm[dst]   = set.thrVcm[i];
-        g.sDirVm[dst]    = set.dirVm[i];
-        g.sContProb[dst] = set.contProb[i];
-        g.sIndex[dst]    = int32_t(i);
+        uint32_t key[4], dst[4];
+#pragma unroll
+        for(int k = 0; k < 4; k++)
+        {
+            const uint32_t i = i0 + uint32_t(k) * blockDim.x;
+            key[k] = (i < total) ? g.cellKey[i] : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for(int k = 0; k < 4; k++) dst[k] = (key[k] != 0xFFFFFFFFu) ? atomicAdd(g.cellCount + key[k], 1u) : 0u;
+#pragma unroll
+        for(int k = 0; k < 4; k++)
+        {
+            if(key[k] == 0xFFFFFFFFu) continue;
+            const uint32_t i = i0 + uint32_t(k) * blockDim.x;
+            g.sPosLen[dst[k]]   = set.posLen[i];
+            g.sThrVcm[dst[k]]   = set.thrVcm[i];
+            g.sDirVm[dst[k]]    = set.dirVm[i];
+            g.sContProb[dst[k]] = set.contProb[i];
+            g.sIndex[dst[k]]    = int32_t(i);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// query grouping: the merge is a join between cell-sorted particles and range queries; sorting
+// the QUERIES by the bucket of their own cell as well makes neighbouring lanes of the merge
+// kernel walk identical ranges (their loads coalesce to broadcasts and their trip counts match).
+// Pure scheduling: which particles a query visits and accepts is unchanged.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_queryKeys(const __grid_constant__ QueryStore qs, const unsigned long long *vertexCount, const int32_t *bboxBits,
+            float invCellSize, uint32_t numCells, uint32_t *key, uint32_t *cellCount)
+{
+    const uint32_t n = uint32_t(min(*vertexCount, (unsigned long long)qs.capacity));
+    const f3 bbMin = mk3(orderedToFloat(bboxBits[0]), orderedToFloat(bboxBits[1]), orderedToFloat(bboxBits[2]));
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        uint32_t k = 0xFFFFFFFFu;
+        if(__float_as_uint(qs.q1[i].w) & CAMV_MERGEABLE)
+        {
+            const float4 p = qs.q0[i];
+            k = cellHash(int32_t(floorf(invCellSize * (p.x - bbMin.x))), int32_t(floorf(invCellSize * (p.y - bbMin.y))),
+                         int32_t(floorf(invCellSize * (p.z - bbMin.z))), numCells);
+            atomicAdd(cellCount + k, 1u);
+        }
+        key[i] = k;
+    }
+}
+
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_queryScatter(const unsigned long long *vertexCount, uint32_t capacity, const uint32_t *key, uint32_t *cellCount,
+               uint32_t *order)
+{
+    const uint32_t n = uint32_t(min(*vertexCount, (unsigned long long)capacity));
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t k = key[i];
+        if(k != 0xFFFFFFFFu) order[atomicAdd(cellCount + k, 1u)] = i;
     }
 }
 
@@ -911,8 +963,9 @@ k_merge(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst i
     const f3 bbMax = mk3(orderedToFloat(g.bboxBits[3]), orderedToFloat(g.bboxBits[4]), orderedToFloat(g.bboxBits[5]));
     uint32_t nCand = 0u, nAcc = 0u;
 
-    for(uint32_t q = blockIdx.x * groupsPerBlock + groupInBlock; q < nq; q += gridDim.x * groupsPerBlock)
+    for(uint32_t qi = blockIdx.x * groupsPerBlock + groupInBlock; qi < nq; qi += gridDim.x * groupsPerBlock)
     {
+        const uint32_t q = qs.order ? qs.order[qi] : qi;
         const float4 q0 = qs.q0[q], q1 = qs.q1[q], q2 = qs.q2[q], q3 = qs.q3[q];
         const f3 qpos = xyz(q0);
         const uint32_t lenMat = __float_as_uint(q1.w);
@@ -1134,8 +1187,8 @@ k_mergeLane(const __grid_constant__ DevScene sc, const __grid_constant__ IterCon
     for(uint32_t q0i = (blockIdx.x * MERGE_WARPS + (threadIdx.x >> 5)) * 32u; q0i < nq;
         q0i += gridDim.x * MERGE_WARPS * 32u)
     {
-        const uint32_t q = q0i + lane;
-        bool valid = q < nq;
+        bool valid = q0i + lane < nq;
+        const uint32_t q = valid ? (qs.order ? qs.order[q0i + lane] : q0i + lane) : 0u;
         f3 qpos = mk3(0.f), scale = mk3(0.f);
         uint32_t pixel = 0u;
         uint32_t cand = 0u, accepted = 0u;
@@ -1397,6 +1450,22 @@ void launchCameraBounce(const DevScene &sc, const IterConst &ic, const TraceArgs
     k_cameraBounce<<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
 }
 
+int launchQuerySort(const IterConst &ic, const QueryStore &queries, const unsigned long long *vertexCount,
+                    const int32_t *bboxBits, const QuerySortBuffers &qs, cudaStream_t stream)
+{
+    const uint32_t n = ic.numCells + 1u;
+    cudaMemsetAsync(qs.cellCount, 0, sizeof(uint32_t) * n, stream);
+    const uint32_t gridN = gridFor(queries.capacity, SVCM_BLOCK, 8);
+    k_queryKeys<<<gridN, SVCM_BLOCK, 0, stream>>>(queries, vertexCount, bboxBits, ic.invCellSize, ic.numCells,
+                                                  qs.key, qs.cellCount);
+    const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scanTiles<<<tiles, SVCM_BLOCK, 0, stream>>>(qs.cellCount, n, qs.blockSums);
+    k_scanSums<<<1, SVCM_BLOCK, 0, stream>>>(qs.blockSums, tiles);
+    k_scanAdd<<<tiles, SVCM_BLOCK, 0, stream>>>(qs.cellCount, n, qs.blockSums);
+    k_queryScatter<<<gridN, SVCM_BLOCK, 0, stream>>>(vertexCount, queries.capacity, qs.key, qs.cellCount, qs.order);
+    return 5;
+}
+
 void launchConnect(const DevScene &sc, const IterConst &ic, const TraceArgs &args, cudaStream_t stream)
 {
     k_connect<<<gridFor(args.pairs.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args);
@@ -1432,7 +1501,7 @@ int launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers 
     launches += 3;
     if(maxTotal > 0)
     {
-        k_gridScatter<<<gridFor(maxTotal, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(set, grid);
+        k_gridScatter<<<gridFor((maxTotal + 3u) / 4u, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(set, grid);
         launches++;
     }
     return launches;
