@@ -66,16 +66,22 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Median SM clock / throttle reasons of the samples that arrived in [t_begin, t_end]
+        (perf_counter times; the sampler itself is started well before, nvidia-smi needs
+        ~0.3 s to deliver its first row)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
+        rows = [r for (t, r) in self.rows if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.12)]
+        if not rows:
+            rows = [r for (_, r) in self.rows[-3:]]
+        for row in rows:
             f = [x.strip() for x in row.split(",")]
             if len(f) < 9:
                 continue
@@ -212,21 +218,30 @@ def run_gpu_arm(args):
             D.barrier(tdev)
 
     # ---- warm-up -------------------------------------------------------------------------------
-    run_steps(args.warmup)
-    sync_all()
-    r.profile()                        # drop warm-up from the accumulated profile
-
-    # ---- timed: K steps, device time on the launching stream, max over ranks -------------------
     clocks = ClockSampler(device)
     if rank == 0:
         clocks.start()
+    run_steps(args.warmup)
     sync_all()
+    r.profile()                        # drop warm-up from the accumulated profile
+    # keep the GPU busy until the clock sampler has delivered its first rows (~0.3 s)
+    t_wait = time.perf_counter()
+    while rank == 0 and clocks.proc is not None and not clocks.rows and time.perf_counter() - t_wait < 2.0:
+        run_steps(1)
+        r.synchronize()
+    sync_all()
+    r.profile()
+
+    # ---- timed: K steps, device time on the launching stream, max over ranks -------------------
+    sync_all()
+    t_begin = time.perf_counter()
     r.event_record(0)
     run_steps(args.steps)
     r.event_record(1)
     ms = r.event_elapsed_ms(0, 1)
     sync_all()
-    clk = clocks.stop() if rank == 0 else None
+    t_end = time.perf_counter()
+    clk = clocks.stop(t_begin, t_end) if rank == 0 else None
     prof = r.profile()
     if world > 1:
         ms = D.max_over_ranks(ms, tdev)
@@ -306,7 +321,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs)")

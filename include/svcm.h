@@ -151,7 +151,12 @@ enum {
     SVCM_ALG_PPM         = 1,
     SVCM_ALG_BPM         = 2,
     SVCM_ALG_BPT         = 3,
-    SVCM_ALG_VCM         = 4
+    SVCM_ALG_VCM         = 4,
+    /* SURVEY §8(f) rank 1 — the reference's two other integrators on the same device functions:
+     * PathTracer (src/pathtracer.hxx:45-215) and EyeLight (src/eyelight.hxx:47-78). They are
+     * separate classes in the reference; here they are two more algorithm ids of one handle. */
+    SVCM_ALG_PATH_TRACE  = 5,
+    SVCM_ALG_EYE_LIGHT   = 6
 };
 
 typedef struct SvcmParams {

@@ -1425,9 +1425,183 @@ struct Oracle
         AddColor(sampleX, sampleY, color);
     }
 
+    // ---------------------------------------------------------------------------------
+    // PathTracer::RunIteration, src/pathtracer.hxx:45-215 (next-event estimation + BSDF
+    // sampling combined with the balance heuristic) — SURVEY §8(f) rank 1
+    // ---------------------------------------------------------------------------------
+    static float Mis2(float samplePdf, float otherPdf) { return samplePdf / (samplePdf + otherPdf); }  // :228-233
+
+    void TracePathTracerPixel(int aIteration, int pixID)
+    {
+        rng.SetPath(aIteration, 1, pixID);
+        const int   lightCount    = int(scene.lights.size());
+        const float lightPickProb = 1.f / lightCount;
+        const SvcmCamera &cam = scene.camera;
+
+        const int x = pixID % resX;
+        const int y = pixID / resX;
+        const float jx = rng.GetFloat(), jy = rng.GetFloat();
+        const float sampleX = float(x) + jx, sampleY = float(y) + jy;
+
+        // Camera::GenerateRay, src/camera.hxx:108-117 (no origin offset on the first segment)
+        const V3 camPos = Load3(cam.position);
+        Ray ray;
+        ray.org = camPos;
+        ray.dir = Normalize(TransformPoint(cam.rasterToWorld, V3(sampleX, sampleY, 0)) - camPos);
+        ray.tmin = 0;
+        Isect isect; isect.dist = 1e36f;
+
+        V3 pathWeight(1.f);
+        V3 color(0.f);
+        uint  pathLength   = 1;
+        bool  lastSpecular = true;
+        float lastPdfW     = 1;
+
+        for(;; ++pathLength)
+        {
+            cnt.cameraRays++;
+            if(!SceneIntersect(scene, ray, isect))
+            {
+                if(pathLength < minPathLength) break;
+                if(scene.background < 0) break;
+                float directPdfW = 0, emissionPdfW = 0;
+                const V3 contrib = LightGetRadiance(scene.lights[scene.background], scene.sphere, ray.dir,
+                                                    directPdfW, emissionPdfW);
+                if(IsZero(contrib)) break;
+                float misWeight = 1.f;
+                if(pathLength > 1 && !lastSpecular)
+                    misWeight = Mis2(lastPdfW, directPdfW * lightPickProb);
+                color = color + pathWeight * misWeight * contrib;
+                break;
+            }
+
+            const V3 hitPoint = ray.org + ray.dir * isect.dist;
+            isect.dist += kEpsRay;
+
+            Bsdf bsdf;
+            BsdfSetup(scene, ray.dir, isect, false, bsdf);
+            if(bsdf.matID < 0) break;
+
+            if(isect.lightID >= 0)
+            {
+                if(pathLength < minPathLength) break;
+                const SvcmLight &light = LightPtr(isect.lightID);
+                float directPdfA = 0, emissionPdfW = 0;
+                const V3 contrib = LightGetRadiance(light, scene.sphere, ray.dir, directPdfA, emissionPdfW);
+                if(IsZero(contrib)) break;
+                float misWeight = 1.f;
+                if(pathLength > 1 && !lastSpecular)
+                {
+                    // PdfAtoW, src/utils.hxx:253-259
+                    const float directPdfW = directPdfA * Sqr(isect.dist) / std::abs(bsdf.CosThetaFix());
+                    misWeight = Mis2(lastPdfW, directPdfW * lightPickProb);
+                }
+                color = color + pathWeight * misWeight * contrib;
+                break;
+            }
+
+            if(pathLength >= maxPathLength) break;
+            if(bsdf.contProb == 0) break;
+
+            // next event estimation
+            if(!bsdf.isDelta && pathLength + 1 >= minPathLength)
+            {
+                const int lightID = int(rng.GetFloat() * lightCount);
+                const SvcmLight &light = LightPtr(lightID);
+                const float rx = rng.GetFloat(), ry = rng.GetFloat();
+                V3 directionToLight(0);
+                float distance, directPdfW, emissionPdfW, cosAtLight;
+                const V3 radiance = LightIlluminate(light, scene.sphere, hitPoint, rx, ry, directionToLight,
+                                                    distance, directPdfW, emissionPdfW, cosAtLight);
+                if(!IsZero(radiance))
+                {
+                    float bsdfPdfW, cosThetaOut;
+                    const V3 factor = BsdfEvaluate(scene, bsdf, directionToLight, cosThetaOut, &bsdfPdfW, NULL);
+                    if(!IsZero(factor))
+                    {
+                        float weight = 1.f;
+                        if(!LightIsDelta(light))
+                        {
+                            const float contProb = bsdf.contProb;
+                            bsdfPdfW *= contProb;
+                            weight = Mis2(directPdfW * lightPickProb, bsdfPdfW);
+                        }
+                        const V3 contrib = (weight * cosThetaOut / (lightPickProb * directPdfW)) * (radiance * factor);
+                        cnt.shadowRays++;
+                        if(!SceneOccluded(scene, hitPoint, directionToLight, distance))
+                            color = color + pathWeight * contrib;
+                    }
+                }
+            }
+
+            // continue random walk
+            {
+                const float r0 = rng.GetFloat(), r1 = rng.GetFloat(), r2 = rng.GetFloat();
+                float pdf, cosThetaOut;
+                uint  sampledEvent;
+                const V3 factor = BsdfSample(scene, bsdf, V3(r0, r1, r2), ray.dir, pdf, cosThetaOut, &sampledEvent);
+                if(IsZero(factor)) break;
+
+                const float contProb = bsdf.contProb;
+                lastSpecular = (sampledEvent & kSpecular) != 0;
+                lastPdfW     = pdf * contProb;
+                if(contProb < 1.f)
+                {
+                    if(rng.GetFloat() > contProb) break;
+                    pdf *= contProb;
+                }
+                pathWeight = pathWeight * (factor * (cosThetaOut / pdf));
+                ray.org    = hitPoint + kEpsRay * ray.dir;
+                ray.tmin   = 0.f;
+                isect.dist = 1e36f;
+            }
+        }
+        AddColor(sampleX, sampleY, color);
+    }
+
+    // EyeLight::RunIteration, src/eyelight.hxx:47-78 (N.L preview; iteration 1 is unjittered)
+    void TraceEyeLightPixel(int aIteration, int pixID)
+    {
+        rng.SetPath(aIteration, 1, pixID);
+        const SvcmCamera &cam = scene.camera;
+        const int x = pixID % resX;
+        const int y = pixID / resX;
+        float jx = 0.5f, jy = 0.5f;
+        if(aIteration != 1) { jx = rng.GetFloat(); jy = rng.GetFloat(); }
+        const float sampleX = float(x) + jx, sampleY = float(y) + jy;
+        const V3 camPos = Load3(cam.position);
+        Ray ray;
+        ray.org = camPos;
+        ray.dir = Normalize(TransformPoint(cam.rasterToWorld, V3(sampleX, sampleY, 0)) - camPos);
+        ray.tmin = 0;
+        Isect isect; isect.dist = 1e36f;
+        cnt.cameraRays++;
+        if(SceneIntersect(scene, ray, isect))
+        {
+            const float dotLN = Dot(isect.normal, -ray.dir);
+            if(dotLN > 0) AddColor(sampleX, sampleY, V3(dotLN));
+            else          AddColor(sampleX, sampleY, V3(-dotLN, 0, 0));
+        }
+    }
+
+    int algorithm;   // SVCM_ALG_*
+
     // VertexCM::RunIteration, src/vertexcm.hxx:284-548
     void RunIteration(int aIteration)
     {
+        if(algorithm == SVCM_ALG_PATH_TRACE || algorithm == SVCM_ALG_EYE_LIGHT)
+        {
+            memset(&cnt, 0, sizeof(cnt));
+            lightVertices.clear();
+            for(int pixID = 0; pixID < resX * resY; pixID++)
+            {
+                if(algorithm == SVCM_ALG_PATH_TRACE) TracePathTracerPixel(aIteration, pixID);
+                else                                 TraceEyeLightPixel(aIteration, pixID);
+            }
+            iterations++;
+            return;
+        }
+
         const int pathCount = resX * resY;
         const float radius = SetupIteration(aIteration);
         memset(&cnt, 0, sizeof(cnt));
@@ -1490,8 +1664,11 @@ ORACLE_API void *oracle_create(const SvcmSceneDesc *scene, int algorithm, float 
     case SVCM_ALG_BPM:         o->useVM = true; break;
     case SVCM_ALG_BPT:         o->useVC = true; break;
     case SVCM_ALG_VCM:         o->useVC = true; o->useVM = true; break;
+    case SVCM_ALG_PATH_TRACE:  break;
+    case SVCM_ALG_EYE_LIGHT:   break;
     default: delete o; return NULL;
     }
+    o->algorithm = algorithm;
     if(o->ppm)
     {
         // src/vertexcm.hxx:246-278: mixed specular / non-specular materials => BPM

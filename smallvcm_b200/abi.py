@@ -12,8 +12,9 @@ MAX_PRIMITIVES, MAX_MATERIALS, MAX_LIGHTS = 64, 16, 8
 PRIM_TRIANGLE, PRIM_SPHERE = 0, 1
 LIGHT_AREA, LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_BACKGROUND = 0, 1, 2, 3
 # VertexCM::AlgorithmType numbering (reference src/vertexcm.hxx:182-204)
-ALG_LIGHT_TRACE, ALG_PPM, ALG_BPM, ALG_BPT, ALG_VCM = 0, 1, 2, 3, 4
-ALGORITHMS = {"lt": ALG_LIGHT_TRACE, "ppm": ALG_PPM, "bpm": ALG_BPM, "bpt": ALG_BPT, "vcm": ALG_VCM}
+ALG_LIGHT_TRACE, ALG_PPM, ALG_BPM, ALG_BPT, ALG_VCM, ALG_PATH_TRACE, ALG_EYE_LIGHT = 0, 1, 2, 3, 4, 5, 6
+ALGORITHMS = {"lt": ALG_LIGHT_TRACE, "ppm": ALG_PPM, "bpm": ALG_BPM, "bpt": ALG_BPT, "vcm": ALG_VCM,
+              "pt": ALG_PATH_TRACE, "el": ALG_EYE_LIGHT}
 OPT_PROFILE, OPT_MERGE_GROUP, OPT_COUNTERS = 1, 2, 3
 COMM_ID_BYTES = 128
 

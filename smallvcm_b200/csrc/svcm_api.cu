@@ -116,8 +116,9 @@ struct svcm_renderer
     ncclComm_t comm;
     float4 *gPosLen, *gThrVcm, *gDirVm; float *gContProb;   // gathered records
     uint32_t gatherCapacity;        // records per gathered stream
-    uint32_t *devCounts;            // [worldSize] per-rank vertex counts (device)
-    uint32_t *hostCounts;           // pinned
+    unsigned long long *devCounts64;   // [worldSize] per-rank vertex counts (device)
+    unsigned long long *hostCounts64;  // pinned
+    uint32_t *hostCounts;           // clamped copy
 
     int  iterationsDone;
     int  mergeGroup;
@@ -449,20 +450,16 @@ int gatherLightVertices(svcm_renderer *r, MergeSet &set)
     const int ws = r->params.worldSize;
     if(!r->comm) return fail(r, SVCM_E_STATE, "worldSize %d but svcm_comm_init was not called", ws);
 
-    // own count -> device slot -> all ranks
-    SVCM_CUDA(r, cudaMemcpyAsync(r->hostCounts + 8, r->counters + CNT_LIGHT_VERTS, sizeof(unsigned long long),
+    // per-rank counts: the 64-bit device counters are all-gathered as they are (no host round
+    // trip before the collective), then ONE stream synchronisation brings them to the host
+    int rc;
+    if((rc = ncclCheck(r, n->AllGather(r->counters + CNT_LIGHT_VERTS, r->devCounts64, 2, NCCL_UINT32, r->comm, r->stream),
+                       "ncclAllGather(counts)"))) return rc;
+    SVCM_CUDA(r, cudaMemcpyAsync(r->hostCounts64, r->devCounts64, sizeof(unsigned long long) * ws,
                                  cudaMemcpyDeviceToHost, r->stream));
     SVCM_CUDA(r, cudaStreamSynchronize(r->stream));
-    unsigned long long mine64; memcpy(&mine64, r->hostCounts + 8, 8);
-    const uint32_t mine = uint32_t(std::min<unsigned long long>(mine64, r->verts.capacity));
-    r->hostCounts[r->params.rank] = mine;
-    SVCM_CUDA(r, cudaMemcpyAsync(r->devCounts + r->params.rank, r->hostCounts + r->params.rank, 4,
-                                 cudaMemcpyHostToDevice, r->stream));
-    int rc;
-    if((rc = ncclCheck(r, n->AllGather(r->devCounts + r->params.rank, r->devCounts, 1, NCCL_UINT32, r->comm, r->stream),
-                       "ncclAllGather(counts)"))) return rc;
-    SVCM_CUDA(r, cudaMemcpyAsync(r->hostCounts, r->devCounts, sizeof(uint32_t) * ws, cudaMemcpyDeviceToHost, r->stream));
-    SVCM_CUDA(r, cudaStreamSynchronize(r->stream));
+    for(int i = 0; i < ws; i++)
+        r->hostCounts[i] = uint32_t(std::min<unsigned long long>(r->hostCounts64[i], r->verts.capacity));
 
     uint32_t maxCount = 0;
     for(int i = 0; i < ws; i++) maxCount = std::max(maxCount, r->hostCounts[i]);
@@ -717,7 +714,7 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     r->counters = NULL; r->hostCounters = NULL; r->accum = NULL;
     memset(&r->grid, 0, sizeof(r->grid)); r->gridCells = 0; r->gridCapacity = 0; r->bboxInit = NULL;
     r->comm = NULL; r->gPosLen = r->gThrVcm = r->gDirVm = NULL; r->gContProb = NULL; r->gatherCapacity = 0;
-    r->devCounts = NULL; r->hostCounts = NULL;
+    r->devCounts64 = NULL; r->hostCounts64 = NULL; r->hostCounts = NULL;
     r->iterationsDone = 0; r->mergeGroup = 1; r->profile = false;
     r->ev = NULL; r->ringHead = r->ringTail = 0;
     memset(r->ringLaunches, 0, sizeof(r->ringLaunches)); memset(r->ringTimed, 0, sizeof(r->ringTimed));
@@ -773,18 +770,19 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     if((rc = devAlloc(r, &r->accum, size_t(r->paths) * 3))) SVCM_CREATE_FAIL(rc);
     if((rc = devAlloc(r, &r->grid.bboxBits, 6))) SVCM_CREATE_FAIL(rc);
     if((rc = devAlloc(r, &r->bboxInit, 6))) SVCM_CREATE_FAIL(rc);
-    if((rc = devAlloc(r, &r->devCounts, 8))) SVCM_CREATE_FAIL(rc);
+    if((rc = devAlloc(r, &r->devCounts64, 8))) SVCM_CREATE_FAIL(rc);
     SVCM_TRY(cudaMallocHost((void**)&r->hostCounters, sizeof(unsigned long long) * CNT_WORDS * SVCM_PROFILE_RING));
-    SVCM_TRY(cudaMallocHost((void**)&r->hostCounts, sizeof(uint32_t) * 16));
+    SVCM_TRY(cudaMallocHost((void**)&r->hostCounts64, sizeof(unsigned long long) * 8));
+    r->hostCounts = new uint32_t[8];
     memset(r->hostCounters, 0, sizeof(unsigned long long) * CNT_WORDS * SVCM_PROFILE_RING);
-    memset(r->hostCounts, 0, sizeof(uint32_t) * 16);
+    memset(r->hostCounts64, 0, sizeof(unsigned long long) * 8); memset(r->hostCounts, 0, sizeof(uint32_t) * 8);
     const int32_t init[6] = { floatToOrdered(1e36f), floatToOrdered(1e36f), floatToOrdered(1e36f),
                               floatToOrdered(-1e36f), floatToOrdered(-1e36f), floatToOrdered(-1e36f) };
     SVCM_TRY(cudaMemcpy(r->bboxInit, init, sizeof(init), cudaMemcpyHostToDevice));
     SVCM_TRY(cudaMemcpy(r->grid.bboxBits, init, sizeof(init), cudaMemcpyHostToDevice));
     r->grid.bboxInit = r->bboxInit;
     SVCM_TRY(cudaMemset(r->accum, 0, sizeof(float) * 3 * size_t(r->paths)));
-    SVCM_TRY(cudaMemset(r->devCounts, 0, sizeof(uint32_t) * 8));
+    SVCM_TRY(cudaMemset(r->devCounts64, 0, sizeof(unsigned long long) * 8));
 #undef SVCM_TRY
 #undef SVCM_CREATE_FAIL
     *out = r;
@@ -804,9 +802,10 @@ void svcm_destroy(svcm_renderer *r)
     devFree(r->pathVertCount); devFree(r->counters); devFree(r->accum);
     devFree(r->grid.cellCount); devFree(r->grid.blockSums); devFree(r->grid.bboxBits);
     devFree(r->qsort.cellCount); devFree(r->qsort.blockSums);
-    devFree(r->bboxInit); devFree(r->devCounts);
+    devFree(r->bboxInit); devFree(r->devCounts64);
     if(r->hostCounters) cudaFreeHost(r->hostCounters);
-    if(r->hostCounts) cudaFreeHost(r->hostCounts);
+    if(r->hostCounts64) cudaFreeHost(r->hostCounts64);
+    delete[] r->hostCounts;
     if(r->ev)
     {
         for(int k = 0; k < SVCM_PROFILE_RING; k++) for(int i = 0; i < 6; i++) if(r->ev[k][i]) cudaEventDestroy(r->ev[k][i]);
