@@ -84,10 +84,10 @@ private:
 #include "camera.hxx"
 #include "framebuffer.hxx"
 #include "scene.hxx"
-#include "eyelight.hxx"
-#include "pathtracer.hxx"
+#include <eyelight.hxx>   // the patched copies: first -I directory, angle brackets skip "."
+#include <pathtracer.hxx>
 #include "bsdf.hxx"
-#include <vertexcm.hxx>   // the patched copy: first -I directory, angle brackets skip "."
+#include <vertexcm.hxx>
 
 #define main smallvcm_reference_main
 #include "smallvcm.cxx"
@@ -101,9 +101,10 @@ namespace {
 
 struct Handle
 {
-    Scene    *scene;
-    VertexCM *renderer;
-    int       width, height;
+    Scene            *scene;
+    VertexCM         *renderer;   // NULL for the two unidirectional integrators
+    AbstractRenderer *any;        // whatever CreateRenderer would have built
+    int               width, height;
 };
 
 Scene *MakeScene(int sceneId, int width, int height)
@@ -132,10 +133,17 @@ REF_API void *refctr_create(int sceneId, int algorithm, int width, int height, i
     h->scene    = scene;
     h->width    = width;
     h->height   = height;
-    h->renderer = new VertexCM(*scene, VertexCM::AlgorithmType(algorithm),
-                               radiusFactor, radiusAlpha, seed);
-    h->renderer->mMaxPathLength = maxPathLength;   // after construction, like src/smallvcm.cxx:70-71
-    h->renderer->mMinPathLength = minPathLength;
+    h->renderer = NULL;
+    if(algorithm == SVCM_ALG_PATH_TRACE)     h->any = new PathTracer(*scene, seed);   // src/config.hxx:121-122
+    else if(algorithm == SVCM_ALG_EYE_LIGHT) h->any = new EyeLight(*scene, seed);     // src/config.hxx:119-120
+    else
+    {
+        h->renderer = new VertexCM(*scene, VertexCM::AlgorithmType(algorithm),
+                                   radiusFactor, radiusAlpha, seed);
+        h->any = h->renderer;
+    }
+    h->any->mMaxPathLength = maxPathLength;   // after construction, like src/smallvcm.cxx:70-71
+    h->any->mMinPathLength = minPathLength;
     return h;
 }
 
@@ -143,28 +151,29 @@ REF_API void refctr_destroy(void *handle)
 {
     Handle *h = (Handle*)handle;
     if(!h) return;
-    delete h->renderer;
+    delete h->any;
     delete h->scene;
     delete h;
 }
 
 REF_API void refctr_run_iteration(void *handle, int iteration)
 {
-    ((Handle*)handle)->renderer->RunIteration(iteration);
+    ((Handle*)handle)->any->RunIteration(iteration);
 }
 
 // The ACCUMULATED framebuffer (mFramebuffer, not divided by mIterations)
 REF_API int refctr_accum(void *handle, float *outRgb)
 {
     Handle *h = (Handle*)handle;
-    memcpy(outRgb, &h->renderer->mFramebuffer.mColor[0],
+    memcpy(outRgb, &h->any->mFramebuffer.mColor[0],
            sizeof(float) * 3 * size_t(h->width) * size_t(h->height));
-    return h->renderer->mIterations;
+    return h->any->mIterations;
 }
 
 REF_API long long refctr_num_light_vertices(void *handle)
 {
-    return (long long)((Handle*)handle)->renderer->mLightVertices.size();
+    Handle *h = (Handle*)handle;
+    return h->renderer ? (long long)h->renderer->mLightVertices.size() : 0;
 }
 
 // mLightVertices of the last iteration in the 52-byte merge form + dVC, the shading

@@ -85,7 +85,7 @@ struct svcm_renderer
     DevScene   scene;
     int        device;
     cudaStream_t stream;
-    bool useVC, useVM, ppm, lightTraceOnly;
+    bool useVC, useVM, ppm, lightTraceOnly, pathTrace, eyeLight;
     int  resX, resY;
     uint32_t paths, localPaths, localRows;
     float baseRadius;
@@ -338,7 +338,7 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
     }
 
     // camera vertices: at most one per camera bounce that can still connect or merge
-    if(!r->lightTraceOnly)
+    if(!r->lightTraceOnly && !r->pathTrace && !r->eyeLight)
     {
         const uint64_t worst = uint64_t(r->localPaths) * (r->ppm ? 1u : std::max(1u, camBounces - 1u));
         if(r->queries.capacity < worst && r->queries.capacity < 0xFFFFFF00u)
@@ -385,10 +385,10 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
     // visibility segments: one per light vertex splat, one per direct-illumination sample and
     // one per pair at most; sized for the measured mix (scene 1 vcm: 7.9 per path), a full
     // queue makes producers trace inline
-    if((r->useVC || r->lightTraceOnly) && r->shadow.capacity == 0)
+    if((r->useVC || r->lightTraceOnly || r->pathTrace) && r->shadow.capacity == 0)
     {
         cudaMemGetInfo(&freeB, &totalB);
-        uint64_t cap = uint64_t(r->localPaths) * (r->lightTraceOnly ? std::min(lightBounces, 4u) : 12u);
+        uint64_t cap = uint64_t(r->localPaths) * ((r->lightTraceOnly || r->pathTrace) ? std::min(camBounces, 4u) : 12u);
         cap = std::min<uint64_t>(cap, uint64_t(double(freeB) * 0.3) / 48u);
         cap = std::min<uint64_t>(std::max<uint64_t>(cap, 1024u), 0xFFFFFF00u);
         if((rc = devAlloc(r, &r->shadow.r0, cap))) return rc;
@@ -536,6 +536,43 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     a.counters = r->counters;
     a.accum = r->accum;
     a.bboxBits = r->grid.bboxBits;
+
+    // ---- the unidirectional integrators ---------------------------------
+    if(r->pathTrace || r->eyeLight)
+    {
+        if(timed) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); cudaEventRecord(ev[3], st); }
+        a.queueCounts = r->queueCountsCamera;
+        if(r->eyeLight)
+        {
+            launchEyeLight(r->scene, ic, a, uint32_t(iteration), st);
+            launches++;
+        }
+        else
+        {
+            const uint32_t bounces = std::max(1u, maxLen);
+            for(uint32_t b = 1; b <= bounces; b++)
+            {
+                a.in = r->queue[(b + 1) & 1]; a.out = r->queue[b & 1];
+                launchPathTraceBounce(r->scene, ic, a, b, r->localPaths, st);
+                launches++;
+            }
+            launchShadow(r->scene, ic, a, 1, st);      // next-event visibility, then splat
+            launches++;
+        }
+        if(timed) { cudaEventRecord(ev[4], st); cudaEventRecord(ev[5], st); }
+        SVCM_CUDA(r, cudaMemcpyAsync(r->hostCounters + size_t(slot) * CNT_WORDS, r->counters,
+                                     sizeof(unsigned long long) * CNT_WORDS, cudaMemcpyDeviceToHost, st));
+        SVCM_CUDA(r, cudaGetLastError());
+        r->ringLaunches[slot] = launches;
+        r->ringTimed[slot] = timed;
+        r->ringHead++;
+        if(r->ringHead - r->ringTail > SVCM_PROFILE_RING) r->ringTail = r->ringHead - SVCM_PROFILE_RING;
+        r->stats.radius = 0.f;
+        r->statsPending = true;
+        r->lastLaunches = launches;
+        r->iterationsDone++;
+        return SVCM_OK;
+    }
 
     // ---- light sub-paths (reference src/vertexcm.hxx:321-396) -----------------------------
     const uint32_t lightBounces = std::max(1u, maxLen > 0 ? maxLen - 1u : 0u);
@@ -694,7 +731,7 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     if(!out) return fail(NULL, SVCM_E_INVALID, "out is NULL");
     *out = NULL;
     if(!params) return fail(NULL, SVCM_E_INVALID, "params is NULL");
-    if(params->algorithm < SVCM_ALG_LIGHT_TRACE || params->algorithm > SVCM_ALG_VCM)
+    if(params->algorithm < SVCM_ALG_LIGHT_TRACE || params->algorithm > SVCM_ALG_EYE_LIGHT)
         return fail(NULL, SVCM_E_INVALID, "unknown algorithm %d", params->algorithm);
     if(params->worldSize < 1 || params->worldSize > 8 || params->rank < 0 || params->rank >= params->worldSize)
         return fail(NULL, SVCM_E_INVALID, "bad rank/worldSize %d/%d (1..8 ranks)", params->rank, params->worldSize);
@@ -726,9 +763,11 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     if((rc = buildDevScene(r, scene, r->scene))) SVCM_CREATE_FAIL(rc);
 
     // algorithm flags, reference src/vertexcm.hxx:222-244
-    r->useVC = r->useVM = r->ppm = r->lightTraceOnly = false;
+    r->useVC = r->useVM = r->ppm = r->lightTraceOnly = r->pathTrace = r->eyeLight = false;
     switch(params->algorithm)
     {
+    case SVCM_ALG_PATH_TRACE: r->pathTrace = true; break;
+    case SVCM_ALG_EYE_LIGHT: r->eyeLight = true; break;
     case SVCM_ALG_LIGHT_TRACE: r->lightTraceOnly = true; break;
     case SVCM_ALG_PPM: r->ppm = true; r->useVM = true; break;
     case SVCM_ALG_BPM: r->useVM = true; break;

@@ -186,6 +186,11 @@ void launchConnect(const DevScene &sc, const IterConst &ic, const TraceArgs &arg
 // the device)
 void launchShadow(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t which,
                   cudaStream_t stream);
+// PathTracer (src/pathtracer.hxx:45-215) bounce and EyeLight (src/eyelight.hxx:47-78) pass
+void launchPathTraceBounce(const DevScene &sc, const IterConst &ic, const TraceArgs &args,
+                           uint32_t bounce, uint32_t maxItems, cudaStream_t stream);
+void launchEyeLight(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t iteration,
+                    cudaStream_t stream);
 // HashGrid::Build: bbox -> keys + histogram -> exclusive scan -> scatter. Returns the
 // number of kernels launched.
 int  launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers &grid,

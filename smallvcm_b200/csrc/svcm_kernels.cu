@@ -703,6 +703,207 @@ k_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ TraceArgs 
 }
 
 // ------------------------------------------------------------------------------------------
+// the reference's unidirectional integrators on the same device functions
+// ------------------------------------------------------------------------------------------
+
+// One bounce of PathTracer::RunIteration's walk (reference src/pathtracer.hxx:68-208): emission
+// (environment / area light) with the balance heuristic against next-event estimation, the
+// next-event sample itself (visibility deferred to k_shadow) and BSDF sampling with Russian
+// roulette. Sub-path slots: s0 = ray origin (already offset) | lastPdfW, s1 = direction | -,
+// s2 = pathWeight | -, s3 = pixel index | length + flags (PATH_FLAG_SPECULAR = lastSpecular) |
+// rng draw | target pixel.
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_pathTraceBounce(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
+                  const __grid_constant__ TraceArgs a, const uint32_t bounce)
+{
+    const uint32_t count = (bounce == 1u) ? ic.localPaths : a.queueCounts[bounce];
+    const float lightPickProb = 1.f / float(sc.numLights);
+    uint32_t nRays = 0u;
+
+    for(uint32_t i0 = blockIdx.x * blockDim.x; i0 < count; i0 += gridDim.x * blockDim.x)
+    {
+        const uint32_t i = i0 + threadIdx.x;
+        bool alive = i < count;
+        SubPath s;                       // dVCM doubles as lastPdfW, specular as lastSpecular
+        if(alive)
+        {
+            if(bounce == 1u)
+            {
+                s.path = localToGlobalPath(ic, i);
+                s.rng.key = ic.keyCamera; s.rng.path = s.path; s.rng.draw = 0u;
+                // jittered pixel sample + Camera::GenerateRay (:52-57, src/camera.hxx:108-117);
+                // the first segment starts AT the camera (no epsilon offset, unlike VertexCM)
+                const uint32_t x = s.path % uint32_t(ic.resX), y = s.path / uint32_t(ic.resX);
+                const float jx = s.rng.next(), jy = s.rng.next();
+                const float sx = float(x) + jx, sy = float(y) + jy;
+                const f3 camPos = ld3(sc.camPos);
+                s.origin = camPos;
+                s.direction = normalize(transformPoint(sc.rasterToWorld, mk3(sx, sy, 0.f)) - camPos);
+                s.throughput = mk3(1.f);
+                s.length = 1u; s.specular = true; s.finiteLight = false;
+                s.dVCM = 1.f; s.dVC = 0.f; s.dVM = 0.f;
+                // Framebuffer::AddColor drops samples that round outside the image
+                alive = !(sx < 0.f || sx >= sc.resX || sy < 0.f || sy >= sc.resY);
+                s.extra = alive ? uint32_t(int(sx)) + uint32_t(int(sy)) * uint32_t(ic.resX) : 0u;
+            }
+            else loadSubPath(a.in, i, ic.keyCamera, s);
+        }
+
+        f3 color = mk3(0.f);
+        if(alive)
+        {
+            Hit hit;
+            nRays++;
+            if(!sceneIntersect(sc, s.origin, s.direction, hit))
+            {
+                // environment (:72-93)
+                alive = false;
+                if(s.length >= ic.minLen && sc.background >= 0)
+                {
+                    float directPdfW, emissionPdfW;
+                    const f3 contrib = lightRadiance(sc, sc.lights[sc.background], s.direction, directPdfW, emissionPdfW);
+                    if(!iszero(contrib))
+                    {
+                        float misWeight = 1.f;
+                        if(s.length > 1u && !s.specular)
+                            misWeight = s.dVCM / (s.dVCM + directPdfW * lightPickProb);      // Mis2 (:228-233)
+                        color = (s.throughput * misWeight) * contrib;
+                    }
+                }
+            }
+            else
+            {
+                const f3 hitPoint = mulAddUnfused(s.origin, s.direction, hit.dist);
+                hit.dist += SVCM_EPS_RAY;
+                Bsdf bsdf;
+                bsdfSetup(sc, s.direction, hit.normal, hit.matID, bsdf);
+                alive = bsdf.isValid();
+                const int lightID = alive ? sc.matToLight[hit.matID] : -1;
+                if(alive && lightID >= 0)
+                {
+                    // directly hit an emitter; lights do not reflect (:103-125)
+                    alive = false;
+                    if(s.length >= ic.minLen)
+                    {
+                        float directPdfA, emissionPdfW;
+                        const f3 contrib = lightRadiance(sc, sc.lights[min(lightID, sc.numLights - 1)], s.direction,
+                                                         directPdfA, emissionPdfW);
+                        if(!iszero(contrib))
+                        {
+                            float misWeight = 1.f;
+                            if(s.length > 1u && !s.specular)
+                            {
+                                // PdfAtoW, src/utils.hxx:253-259
+                                const float directPdfW = directPdfA * sqr(hit.dist) / fabsf(bsdf.cosThetaFix());
+                                misWeight = s.dVCM / (s.dVCM + directPdfW * lightPickProb);
+                            }
+                            color = (s.throughput * misWeight) * contrib;
+                        }
+                    }
+                }
+                if(alive && (s.length >= ic.maxLen || bsdf.contProb == 0.f)) alive = false;   // :127-131
+
+                if(alive && !bsdf.isDelta() && s.length + 1u >= ic.minLen)
+                {
+                    // next event estimation (:134-169); Scene::Occluded deferred to k_shadow
+                    int lid = int(s.rng.next() * float(sc.numLights));
+                    lid = min(lid, sc.numLights - 1);
+                    const DevLight &light = sc.lights[lid];
+                    const float rx = s.rng.next(), ry = s.rng.next();
+                    f3 dirToLight = mk3(0.f);
+                    float distance = 0.f, directPdfW, emissionPdfW, cosAtLight;
+                    const f3 radiance = lightIlluminate(sc, light, hitPoint, rx, ry, dirToLight, distance,
+                                                        directPdfW, emissionPdfW, cosAtLight);
+                    if(!iszero(radiance))
+                    {
+                        float bsdfPdfW, bsdfRevPdfW, cosThetaOut;
+                        const f3 factor = bsdfEvaluate(sc, bsdf, dirToLight, cosThetaOut, bsdfPdfW, bsdfRevPdfW);
+                        if(!iszero(factor))
+                        {
+                            float weight = 1.f;
+                            if(!lightIsDelta(light.type))
+                            {
+                                bsdfPdfW *= bsdf.contProb;
+                                const float lp = directPdfW * lightPickProb;
+                                weight = lp / (lp + bsdfPdfW);
+                            }
+                            const f3 contrib = s.throughput *
+                                ((weight * cosThetaOut / (lightPickProb * directPdfW)) * (radiance * factor));
+                            if(!iszero(contrib))
+                                emitShadowRay(sc, a.shadow, 1u, a.accum, hitPoint, dirToLight, distance, s.extra, contrib);
+                        }
+                    }
+                }
+
+                if(alive)
+                {
+                    // continue the random walk (:172-206)
+                    const float r0 = s.rng.next(), r1 = s.rng.next(), r2 = s.rng.next();
+                    float pdf, cosThetaOut;
+                    uint32_t ev;
+                    f3 dirOut = s.direction;
+                    const f3 factor = bsdfSample<false>(sc, bsdf, r0, r1, r2, dirOut, pdf, cosThetaOut, ev);
+                    if(iszero(factor)) alive = false;
+                    else
+                    {
+                        const float contProb = bsdf.contProb;
+                        s.specular = (ev & EV_SPECULAR) != 0u;
+                        s.dVCM = pdf * contProb;                          // lastPdfW
+                        if(contProb < 1.f)
+                        {
+                            if(s.rng.next() > contProb) alive = false;
+                            pdf *= contProb;
+                        }
+                        if(alive)
+                        {
+                            s.throughput = s.throughput * (factor * (cosThetaOut / pdf));
+                            s.direction = dirOut;
+                            s.origin = mulAddUnfused(hitPoint, dirOut, SVCM_EPS_RAY);
+                            s.length++;
+                        }
+                    }
+                }
+            }
+        }
+
+        if(!iszero(color)) addPixel(a.accum, s.extra, color);
+        const uint32_t slot = warpAppend(a.queueCounts + bounce + 1u, alive);
+        if(alive) storeSubPath(a.out, slot, s);
+    }
+    warpCount(a.counters + CNT_CAMERA_RAYS, nRays);
+}
+
+// EyeLight::RunIteration, reference src/eyelight.hxx:47-78: N.L preview, back faces in red; the
+// iteration with index 1 samples pixel centres
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_eyeLight(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
+           const __grid_constant__ TraceArgs a, const uint32_t iteration)
+{
+    uint32_t nRays = 0u;
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ic.localPaths; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t path = localToGlobalPath(ic, i);
+        PathRng rng; rng.key = ic.keyCamera; rng.path = path; rng.draw = 0u;
+        const uint32_t x = path % uint32_t(ic.resX), y = path / uint32_t(ic.resX);
+        float jx = 0.5f, jy = 0.5f;
+        if(iteration != 1u) { jx = rng.next(); jy = rng.next(); }
+        const float sx = float(x) + jx, sy = float(y) + jy;
+        if(sx < 0.f || sx >= sc.resX || sy < 0.f || sy >= sc.resY) continue;
+        const f3 camPos = ld3(sc.camPos);
+        const f3 dir = normalize(transformPoint(sc.rasterToWorld, mk3(sx, sy, 0.f)) - camPos);
+        Hit hit;
+        nRays++;
+        if(sceneIntersect(sc, camPos, dir, hit))
+        {
+            const float dotLN = dot(hit.normal, -dir);
+            const uint32_t pixel = uint32_t(int(sx)) + uint32_t(int(sy)) * uint32_t(ic.resX);
+            addPixel(a.accum, pixel, dotLN > 0.f ? mk3(dotLN) : mk3(-dotLN, 0.f, 0.f));
+        }
+    }
+    warpCount(a.counters + CNT_CAMERA_RAYS, nRays);
+}
+
+// ------------------------------------------------------------------------------------------
 // hash grid build (HashGrid::Build, reference src/hashgrid.hxx:41-107)
 // ------------------------------------------------------------------------------------------
 
@@ -1442,6 +1643,18 @@ void launchLightBounce(const DevScene &sc, const IterConst &ic, const TraceArgs 
                        uint32_t maxItems, cudaStream_t stream)
 {
     k_lightBounce<<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
+}
+
+void launchPathTraceBounce(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t bounce,
+                           uint32_t maxItems, cudaStream_t stream)
+{
+    k_pathTraceBounce<<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
+}
+
+void launchEyeLight(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t iteration,
+                    cudaStream_t stream)
+{
+    k_eyeLight<<<gridFor(ic.localPaths, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, iteration);
 }
 
 void launchCameraBounce(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t bounce,

@@ -9,8 +9,8 @@
 //   4. smallvcm.cxx itself is included verbatim; all its header includes are now no-ops
 //      through the include guards.
 //
-// el / pt still run the reference's CPU classes (EyeLight, PathTracer), so BASELINE config #1
-// (`-a pt`, no GPU needed) works from the same binary.
+// el / pt run the reference's CPU classes (EyeLight, PathTracer) unless SVCM_GPU_PT=1 is set, so
+// BASELINE config #1 (`-a pt`, no GPU needed) works from the same binary.
 //
 // Build (see Makefile next to this file):
 //   g++ -O3 -std=c++0x -fopenmp -fno-access-control -I<SmallVCM>/src -I<repo>/include \
@@ -40,7 +40,11 @@
 #include "vertexcm_gpu.hxx"
 
 #define VertexCM VertexCMGpu
+#define PathTracer PathTracerGpu     // GPU only with SVCM_GPU_PT=1, else the reference's CPU class
+#define EyeLight EyeLightGpu
 #include "config.hxx"
 #undef VertexCM
+#undef PathTracer
+#undef EyeLight
 
 #include "smallvcm.cxx"

@@ -26,14 +26,17 @@ class VertexCMGpu : public AbstractRenderer
 {
 public:
 
-    // same names and values as VertexCM::AlgorithmType (src/vertexcm.hxx:182-204)
+    // same names and values as VertexCM::AlgorithmType (src/vertexcm.hxx:182-204); the two
+    // extra ids select the unidirectional integrators of the library (PathTracerGpu below)
     enum AlgorithmType
     {
         kLightTrace = 0,
         kPpm,
         kBpm,
         kBpt,
-        kVcm
+        kVcm,
+        kPathTrace,
+        kEyeLight
     };
 
     VertexCMGpu(
@@ -140,5 +143,55 @@ private:
     svcm_renderer       *mHandle;
     bool                 mRegistered;
 };
+
+// ---------------------------------------------------------------------------------------
+// the reference's PathTracer / EyeLight on the GPU, opt-in.
+//
+// `-a pt` must keep working on a machine without a GPU (BASELINE config #1), so these two
+// plugs choose at construction: with SVCM_GPU_PT=1 in the environment they run on the device
+// (algorithm ids 5 / 6 of the same library), otherwise they delegate to the reference's own CPU
+// class and mirror its framebuffer (GetFramebuffer is non-virtual and reads OUR members).
+// Constructor signatures are the reference's: (const Scene&, int aSeed), src/pathtracer.hxx:37-42,
+// src/eyelight.hxx:39-44.
+// ---------------------------------------------------------------------------------------
+template<class tCpuRenderer, int tAlgorithm>
+class SvcmUnidirectionalGpu : public AbstractRenderer
+{
+public:
+
+    SvcmUnidirectionalGpu(const Scene& aScene, int aSeed = 1234) :
+        AbstractRenderer(aScene), mCpu(NULL), mGpu(NULL)
+    {
+        const char *useGpu = getenv("SVCM_GPU_PT");
+        if(useGpu && useGpu[0] && useGpu[0] != '0')
+            mGpu = new VertexCMGpu(aScene, VertexCMGpu::AlgorithmType(tAlgorithm), 0.003f, 0.75f, aSeed);
+        else
+            mCpu = new tCpuRenderer(aScene, aSeed);
+    }
+
+    virtual ~SvcmUnidirectionalGpu()
+    {
+        delete mCpu;
+        delete mGpu;
+    }
+
+    virtual void RunIteration(int aIteration)
+    {
+        AbstractRenderer *inner = mGpu ? static_cast<AbstractRenderer*>(mGpu) : static_cast<AbstractRenderer*>(mCpu);
+        inner->mMaxPathLength = mMaxPathLength;     // assigned by the driver after construction
+        inner->mMinPathLength = mMinPathLength;
+        inner->RunIteration(aIteration);
+        mFramebuffer = inner->mFramebuffer;         // accumulated sum, as GetFramebuffer expects
+        mIterations  = inner->mIterations;
+    }
+
+private:
+
+    tCpuRenderer *mCpu;
+    VertexCMGpu  *mGpu;
+};
+
+typedef SvcmUnidirectionalGpu<PathTracer, SVCM_ALG_PATH_TRACE> PathTracerGpu;
+typedef SvcmUnidirectionalGpu<EyeLight,   SVCM_ALG_EYE_LIGHT>  EyeLightGpu;
 
 #endif // SVCM_HOST_VERTEXCM_GPU_HXX_

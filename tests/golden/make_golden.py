@@ -8,7 +8,7 @@ builder on machines without the reference (the GPU box, CI).
 
 Files
   ref_kat.json        known-answer scalars of the unmodified reference (BASELINE.md §3 recipe)
-  ref_images.npz      unmodified reference, 64x64, 2 iterations, 8 (scene, algorithm) pairs
+  ref_images.npz      unmodified reference, 64x64, 2 iterations, 12 (scene, algorithm) pairs
   refctr_images.npz   reference arithmetic + per-path counter RNG, same 8 pairs, + vertex counts
   ref_noise.npz       unmodified reference 128x128 x16 iterations, two seeds (noise floor for
                       the statistical GPU-vs-reference test)
@@ -29,7 +29,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_api as oa  # noqa: E402
 from smallvcm_b200 import abi  # noqa: E402
 
-PAIRS = [(1, "vcm"), (0, "bpt"), (3, "bpm"), (2, "vcm"), (1, "lt"), (1, "ppm"), (0, "vcm"), (3, "vcm")]
+PAIRS = [(1, "vcm"), (0, "bpt"), (3, "bpm"), (2, "vcm"), (1, "lt"), (1, "ppm"), (0, "vcm"), (3, "vcm"),
+         (0, "pt"), (1, "pt"), (3, "pt"), (2, "el")]
 
 
 def raw(x):
@@ -43,7 +44,8 @@ def main():
     # --- known answers of the unmodified reference (1 renderer, seed 1234, minLen 0) ---------
     kat = []
     for sid, alg, w, iters in [(1, "vcm", 512, 1), (1, "vcm", 512, 2), (0, "bpt", 512, 1), (3, "bpm", 512, 1),
-                               (2, "vcm", 256, 1), (1, "lt", 256, 1), (1, "ppm", 256, 1)]:
+                               (2, "vcm", 256, 1), (1, "lt", 256, 1), (1, "ppm", 256, 1), (0, "pt", 512, 1),
+                               (0, "el", 256, 1)]:
         _, img = oa.ref_render(sid, alg, w, w, iters, threads=1)
         kat.append(dict(scene=sid, alg=alg, width=w, height=w, iterations=iters, seed=1234, maxPathLength=10,
                         totalLuminance=float(oa.ref_lib().ref_total_luminance(img.ctypes.data, w, w)),
@@ -56,7 +58,7 @@ def main():
     ref, ctr = {}, {}
     for sid, alg in PAIRS:
         key = "s%d_%s" % (sid, alg)
-        _, img = oa.ref_render(sid, alg, w, w, 2, threads=1)
+        _, img = oa.ref_render(sid, alg, w, w, 2, threads=1)   # el: iteration 1 is the unjittered one
         ref[key] = img
         r = oa.RefCtr(sid, abi.ALGORITHMS[alg], w, w, seed=1234)
         r.run_iteration(0); r.run_iteration(1)
@@ -69,7 +71,7 @@ def main():
 
     # --- noise floor for the statistical test ---------------------------------------------------
     noise = {}
-    for sid, alg in [(1, "vcm"), (3, "bpm"), (0, "bpt")]:
+    for sid, alg in [(1, "vcm"), (3, "bpm"), (0, "bpt"), (1, "pt")]:
         for seed in (1234, 1235):
             _, img = oa.ref_render(sid, alg, 128, 128, 16, threads=1, base_seed=seed)
             noise["s%d_%s_seed%d" % (sid, alg, seed)] = img.astype(np.float16)

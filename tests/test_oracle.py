@@ -17,7 +17,8 @@ import smallvcm_b200 as sv
 from smallvcm_b200 import abi
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-PAIRS = [(1, "vcm"), (0, "bpt"), (3, "bpm"), (2, "vcm"), (1, "lt"), (1, "ppm"), (0, "vcm"), (3, "vcm")]
+PAIRS = [(1, "vcm"), (0, "bpt"), (3, "bpm"), (2, "vcm"), (1, "lt"), (1, "ppm"), (0, "vcm"), (3, "vcm"),
+         (0, "pt"), (1, "pt"), (3, "pt"), (2, "el")]      # pt / el: SURVEY §8(f) rank 1
 
 
 def same_bits(a, b):
@@ -66,6 +67,17 @@ def test_known_answer_scene1_vcm_512():
     img = get_framebuffer(orc)
     assert oa.oracle_total_luminance(img) == kat["totalLuminance"]   # same float accumulation
     assert np.allclose(img.reshape(-1, 3).astype(np.float64).mean(0), kat["meanRGB"], rtol=0, atol=1e-12)
+
+
+def test_known_answer_scene0_pt_512():
+    """BASELINE config #1 / BASELINE.md §3: scene 0 pt 512x512 1 iteration -> 31074.3."""
+    kat = [k for k in json.load(open(os.path.join(GOLD, "ref_kat.json")))
+           if (k["scene"], k["alg"], k["width"]) == (0, "pt", 512)][0]
+    assert abs(kat["totalLuminance"] - 31074.3) < 0.05
+    scene = sv.Scene.cornell_box(0, 512, 512)
+    orc = oa.Oracle(scene, abi.ALG_PATH_TRACE, seed=1234, rng_mode=0)
+    orc.run_iteration(0)
+    assert oa.oracle_total_luminance(get_framebuffer(orc)) == kat["totalLuminance"]
 
 
 def test_known_answers_256():
@@ -129,7 +141,8 @@ def synthetic_queries(verts, normals, mats, n, seed, jitter):
 
 @pytest.mark.ref
 @pytest.mark.skipif(not oa.have_ref_ctr(), reason="oracle/_ref not built (no reference checkout)")
-@pytest.mark.parametrize("scene_id,alg", [(1, "vcm"), (3, "bpm"), (2, "vcm"), (1, "ppm"), (0, "bpt")])
+@pytest.mark.parametrize("scene_id,alg", [(1, "vcm"), (3, "bpm"), (2, "vcm"), (1, "ppm"), (0, "bpt"), (1, "pt"),
+                                          (3, "pt"), (0, "el")])
 def test_internals_against_reference_classes(scene_id, alg):
     w = 80
     scene = sv.Scene.cornell_box(scene_id, w, w)
@@ -139,6 +152,8 @@ def test_internals_against_reference_classes(scene_id, alg):
         ref.run_iteration(it)
         orc.run_iteration(it)
     assert same_bits(ref.accum()[0], orc.accum()[0])
+    if alg in ("pt", "el"):
+        return
     va, vb = ref.light_vertices(), orc.light_vertices()
     for x, y in zip(va, vb):
         assert same_bits(x, y)
