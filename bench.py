@@ -17,9 +17,11 @@ Our arm (default):
             N_q*140 + N_cand*12 + N_acc*40 per launch over its CUDA-event time.
   cpu_baseline  the reference's own OpenMP path (oracle/_ref/libsvcm_ref.so -> render(),
             src/smallvcm.cxx:52) timed on this host's cores on a bounded sample; rank 0, N=1.
-N > 1 (torchrun): every iteration is pixel-sharded over the ranks (rows round-robin) with one
-  NCCL all-gather of the light vertices before the grid build; a step is N iterations, so each
-  GPU still traces W*H paths per step ("weak": per-GPU work fixed).
+N > 1 (torchrun): headline = iteration-parallel replicas, one private renderer per GPU with
+  seed + rank (the reference's own parallel model, src/smallvcm.cxx:61-142; no data-path
+  collective; "weak": every GPU renders one full iteration per step). The same line also
+  carries "sharded": every iteration pixel-sharded over the ranks (rows round-robin) with one
+  NCCL all-gather of the light vertices before the grid build, N iterations per step.
 
 --impl reference: times the UNMODIFIED reference's CPU implementation of the same path on the
   same workload with all host threads (one private renderer per thread, one iteration each per
@@ -149,15 +151,27 @@ def run_reference_arm(args):
         return 0
     threads = host_threads()
     # the reference parallelises over ITERATIONS (src/smallvcm.cxx:99-108): one step = one
-    # render() call with one iteration per thread
+    # render() call with one iteration per thread — the smallest sample of this workload that
+    # uses every host thread (one 1024^2 iteration is 15-20 s on an idle core, ~2 minutes when all
+    # 128 threads share the memory system). The arm must end within a few minutes whatever
+    # --steps / --warmup say, so steps beyond the time budget are not run and "steps" reports
+    # what was timed; a CPU has no clocks to warm, warm-up is skipped when it does not fit.
     iters = threads
-    for _ in range(args.warmup):
-        cpu_reference_step(threads, iters)
-    t0 = time.perf_counter()
-    kind = "reference"
-    for _ in range(args.steps):
+    budget = float(os.environ.get("SVCM_REF_BUDGET_S", "240"))
+    t_start = time.perf_counter()
+    step_s = None
+    warm = 0
+    while warm < args.warmup and step_s is not None and (time.perf_counter() - t_start) + 2 * step_s <= budget:
+        cpu_reference_step(threads, iters); warm += 1
+    kind, done, secs = "reference", 0, 0.0
+    while done < args.steps:
+        t0 = time.perf_counter()
         _, _, kind = cpu_reference_step(threads, iters)
-    secs = time.perf_counter() - t0
+        step_s = time.perf_counter() - t0
+        secs += step_s; done += 1
+        if (time.perf_counter() - t_start) + step_s > budget:
+            break
+    args.steps, args.warmup = done, warm
     value = WIDTH * HEIGHT * iters * args.steps / secs / 1e6
     sample = "%d iterations of the full %dx%d workload per step, one private renderer per thread (%s)" % (
         iters, WIDTH, HEIGHT, "reference render(), src/smallvcm.cxx:52" if kind == "reference" else "oracle port")
@@ -176,10 +190,107 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_gpu_arm(args):
+def measure(sv, D, args, rank, world, device, tdev, sharded, want_e2e, clocks=None):
+    """Times `args.steps` steps in one of the two multi-GPU modes and returns the numbers.
+
+    replicas (sharded=False): every GPU owns a private renderer (seed + rank) and renders one
+        full iteration per step — the reference's own iteration-parallel model
+        (src/smallvcm.cxx:61-142), no data-path collective. At N = 1 this is simply "the renderer".
+    sharded  (sharded=True) : every iteration is split over the GPUs by image rows; the light
+        vertices are all-gathered (NCCL) before each grid build. A step is N iterations, so each
+        GPU still traces W*H paths per step.
+    """
     import numpy as np
+    from smallvcm_b200 import abi
+    scene = sv.Scene.cornell_box(SCENE, WIDTH, HEIGHT)
+    if sharded:
+        r = sv.VertexCM(scene, ALG, radius_factor=RADIUS_FACTOR, radius_alpha=RADIUS_ALPHA, seed=SEED, device=device,
+                        rank=rank, world_size=world)
+        uid = sv.comm_unique_id() if rank == 0 else None
+        r.comm_init(D.broadcast_bytes(uid, abi.COMM_ID_BYTES, 0, tdev))
+        iters_per_step, first = world, 0
+    else:
+        r = sv.VertexCM(scene, ALG, radius_factor=RADIUS_FACTOR, radius_alpha=RADIUS_ALPHA, seed=SEED + rank,
+                        device=device, rank=0, world_size=1)
+        # replica g renders the global iterations g, g + N, g + 2N, ... (radius schedule, :295-298)
+        iters_per_step, first = 1, rank
+    r.max_path_length, r.min_path_length = MAXLEN, MINLEN
+    r.set_option(abi.OPT_PROFILE, 1)
+    stride = 1 if sharded else world
+    state = {"next": first}
+
+    def run_steps(n):
+        if sharded:
+            r.run_iterations(state["next"], n * iters_per_step)
+            state["next"] += n * iters_per_step
+        else:
+            for _ in range(n):
+                r.run_iterations(state["next"], 1)
+                state["next"] += stride
+
+    def sync_all():
+        r.synchronize()
+        if world > 1:
+            D.barrier(tdev)
+
+    run_steps(args.warmup)
+    sync_all()
+    r.profile()
+    if clocks is not None:
+        # keep the GPU busy until the clock sampler has delivered its first rows (~0.3 s)
+        t_wait = time.perf_counter()
+        while clocks.proc is not None and not clocks.rows and time.perf_counter() - t_wait < 2.0:
+            run_steps(1)
+            r.synchronize()
+    sync_all()
+    r.profile()
+
+    # timed: K steps, device time on the launching stream, max over ranks
+    t_begin = time.perf_counter()
+    r.event_record(0)
+    run_steps(args.steps)
+    r.event_record(1)
+    ms = r.event_elapsed_ms(0, 1)
+    sync_all()
+    t_end = time.perf_counter()
+    prof = r.profile()
+    if world > 1:
+        ms = D.max_over_ranks(ms, tdev)
+    paths_per_step = WIDTH * HEIGHT * world          # both modes: W*H paths per GPU per step
+    out = {"value": paths_per_step * args.steps / (ms * 1e-3) / 1e6, "ms_per_step": ms / args.steps,
+           "paths_per_step": paths_per_step, "prof": prof, "window": (t_begin, t_end),
+           "iterations_per_step": world}
+
+    if want_e2e:
+        # the plugin's call sequence with a HOST framebuffer every iteration
+        host_fb = np.empty((HEIGHT, WIDTH, 3), np.float32)
+        lib = sv.load_library()
+        lib.svcm_host_register(host_fb.ctypes.data, host_fb.nbytes)     # what VertexCMGpu does once
+        st = r.stats()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            for _ in range(iters_per_step):
+                r.run_iterations(state["next"], 1)
+                state["next"] += stride
+                r.accum(host_fb)                                      # D2H of the accumulated image
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            e2e_s = D.max_over_ranks(e2e_s, tdev)
+        lib.svcm_host_unregister(host_fb.ctypes.data)
+        out["e2e"] = {"value": paths_per_step * args.steps / e2e_s / 1e6, "unit": UNIT,
+                      "h2d_bytes_per_step": int(st["kernelLaunches"] * st["paramBytesPerLaunch"] * world),
+                      "d2h_bytes_per_step": int((host_fb.nbytes + 64) * world),
+                      "note": "svcm_run_iterations(1) + svcm_download_accum per iteration, as "
+                              "VertexCMGpu::RunIteration does (the non-virtual GetFramebuffer forces the copy); the "
+                              "inputs of a step are the iteration index and the kernel parameter blocks"}
+    r.close()
+    return out
+
+
+def run_gpu_arm(args):
     import smallvcm_b200 as sv
-    from smallvcm_b200 import abi, dist as D
+    from smallvcm_b200 import dist as D
 
     rank, local_rank, world = D.env_rank()
     if world != args.gpus and world > 1:
@@ -194,60 +305,18 @@ def run_gpu_arm(args):
         tdev = "cuda:%d" % device
         D.init_process_group("nccl")
 
-    scene = sv.Scene.cornell_box(SCENE, WIDTH, HEIGHT)
-    r = sv.VertexCM(scene, ALG, radius_factor=RADIUS_FACTOR, radius_alpha=RADIUS_ALPHA, seed=SEED, device=device,
-                    rank=rank, world_size=world)
-    r.max_path_length, r.min_path_length = MAXLEN, MINLEN
-    r.set_option(abi.OPT_PROFILE, 1)
-    if world > 1:
-        uid = sv.comm_unique_id() if rank == 0 else None
-        r.comm_init(D.broadcast_bytes(uid, abi.COMM_ID_BYTES, 0, tdev))
-
-    iters_per_step = world            # weak scaling: every GPU traces W*H paths per step
-    paths_per_step = WIDTH * HEIGHT * iters_per_step
-    next_iter = 0
-
-    def run_steps(n):
-        nonlocal next_iter
-        r.run_iterations(next_iter, n * iters_per_step)
-        next_iter += n * iters_per_step
-
-    def sync_all():
-        r.synchronize()
-        if world > 1:
-            D.barrier(tdev)
-
-    # ---- warm-up -------------------------------------------------------------------------------
-    clocks = ClockSampler(device)
-    if rank == 0:
+    clocks = ClockSampler(device) if rank == 0 else None
+    if clocks is not None:
         clocks.start()
-    run_steps(args.warmup)
-    sync_all()
-    r.profile()                        # drop warm-up from the accumulated profile
-    # keep the GPU busy until the clock sampler has delivered its first rows (~0.3 s)
-    t_wait = time.perf_counter()
-    while rank == 0 and clocks.proc is not None and not clocks.rows and time.perf_counter() - t_wait < 2.0:
-        run_steps(1)
-        r.synchronize()
-    sync_all()
-    r.profile()
 
-    # ---- timed: K steps, device time on the launching stream, max over ranks -------------------
-    sync_all()
-    t_begin = time.perf_counter()
-    r.event_record(0)
-    run_steps(args.steps)
-    r.event_record(1)
-    ms = r.event_elapsed_ms(0, 1)
-    sync_all()
-    t_end = time.perf_counter()
-    clk = clocks.stop(t_begin, t_end) if rank == 0 else None
-    prof = r.profile()
-    if world > 1:
-        ms = D.max_over_ranks(ms, tdev)
-    value = paths_per_step * args.steps / (ms * 1e-3) / 1e6
+    # headline: one renderer per GPU (at N > 1: iteration-parallel replicas, no collective)
+    head = measure(sv, D, args, rank, world, device, tdev, sharded=False, want_e2e=True, clocks=clocks)
+    clk = clocks.stop(*head["window"]) if clocks is not None else None
+    # N > 1: also the pixel-sharded mode with the NCCL all-gather of light vertices
+    shard = measure(sv, D, args, rank, world, device, tdev, sharded=True, want_e2e=False) if world > 1 else None
 
-    # ---- roofline of the merge kernel (per launch = per iteration) ------------------------------
+    # roofline of the merge kernel (one launch per iteration)
+    prof = head["prof"]
     n = max(1, prof["timedIterations"])
     nq, ncand, nacc = prof["mergeQueries"] / n, prof["mergeCandidates"] / n, prof["mergeAccepted"] / n
     merge_ms = prof["msMerge"] / n
@@ -258,37 +327,15 @@ def run_gpu_arm(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "merge_traffic.json")))["dram_bytes_per_launch"]
     except Exception:
         pass
-    roofline = {"kernel": "k_merge (HashGrid::Process + RangeQuery::Process)", "bound": "hbm", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
-                "ms_per_launch": merge_ms, "queries": nq, "candidates": ncand, "accepted": nacc,
-                "algorithmic_bytes_per_launch": merge_algorithmic_bytes(nq, ncand, nacc),
-                "stage_ms_per_iteration": {k: prof[k] / n for k in ("msLightTrace", "msGather", "msGridBuild",
-                                                                     "msCameraTrace", "msMerge", "msTotal")}}
-    launches = prof["kernelLaunches"]
+    stage = lambda p: {k: p[k] / max(1, p["timedIterations"]) for k in
+                       ("msLightTrace", "msGather", "msGridBuild", "msCameraTrace", "msMerge", "msTotal")}
+    roofline = {"kernel": "k_querySort + k_mergeLane (HashGrid::Process + RangeQuery::Process)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_kind, "ms_per_launch": merge_ms, "queries": nq, "candidates": ncand,
+                "accepted": nacc, "algorithmic_bytes_per_launch": merge_algorithmic_bytes(nq, ncand, nacc),
+                "stage_ms_per_iteration": stage(prof)}
 
-    # ---- e2e: the plugin's call sequence with a HOST framebuffer every step ---------------------
-    host_fb = np.empty((HEIGHT, WIDTH, 3), np.float32)
-    lib = sv.load_library()
-    lib.svcm_host_register(host_fb.ctypes.data, host_fb.nbytes)     # what VertexCMGpu does once
-    st = r.stats()
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        for _ in range(iters_per_step):
-            r.run_iterations(next_iter, 1)
-            next_iter += 1
-            r.accum(host_fb)                                          # D2H of the accumulated image
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        e2e_s = D.max_over_ranks(e2e_s, tdev)
-    lib.svcm_host_unregister(host_fb.ctypes.data)
-    e2e = {"value": paths_per_step * args.steps / e2e_s / 1e6, "unit": UNIT,
-           "h2d_bytes_per_step": int(st["kernelLaunches"] * st["paramBytesPerLaunch"] * iters_per_step),
-           "d2h_bytes_per_step": int((host_fb.nbytes + 64) * iters_per_step),
-           "note": "svcm_run_iterations(1) + svcm_download_accum per iteration, as VertexCMGpu::RunIteration; "
-                   "inputs of a step are the iteration index and the kernel parameter blocks (scene + constants)"}
-
-    # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------
+    # CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
@@ -299,19 +346,31 @@ def run_gpu_arm(args):
                          % (threads, WIDTH, HEIGHT, secs)}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "paths_per_step": paths_per_step,
-                           "iterations_per_step": iters_per_step, "seed": SEED, "radiusFactor": RADIUS_FACTOR,
-                           "radiusAlpha": RADIUS_ALPHA,
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "paths_per_step": head["paths_per_step"],
+                           "iterations_per_step": head["iterations_per_step"], "seed": SEED,
+                           "radiusFactor": RADIUS_FACTOR, "radiusAlpha": RADIUS_ALPHA,
                            "parallelism": "1 GPU" if world == 1 else
-                           "pixel rows sharded over %d GPUs, NCCL all-gather of light vertices per iteration" % world,
-                           "l2": "per-iteration working set (path state, light vertices, queries, grid: ~0.6 GB) exceeds the 126 MB L2; no flush needed"},
-                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                           "%d iteration-parallel replicas (one renderer per GPU, seed + rank, global iteration "
+                           "indices interleaved: the reference's own model, src/smallvcm.cxx:61-142); no data-path "
+                           "collective. The pixel-sharded mode with the NCCL all-gather is under \"sharded\"" % world,
+                           "l2": "per-iteration working set (path state, light vertices, camera vertices, pair and "
+                                 "shadow queues, grid: ~0.8 GB) exceeds the 126 MB L2; no flush needed"},
+                "clocks": clk, "e2e": head["e2e"], "gpu_launches": int(prof["kernelLaunches"]), "roofline": roofline,
                 "cpu_baseline": cpu}
+        if shard is not None:
+            line["sharded"] = {"value": shard["value"], "unit": UNIT, "ms_per_step": shard["ms_per_step"],
+                               "iterations_per_step": world, "stage_ms_per_iteration": stage(shard["prof"]),
+                               "gpu_launches": int(shard["prof"]["kernelLaunches"]),
+                               "note": "every iteration split over the GPUs by image rows (round robin); per "
+                                       "iteration one NCCL all-gather of the 52-byte light-vertex merge records "
+                                       "(counts first, then one group of four ncclAllGather) before the grid build; "
+                                       "a step is N such iterations. Fixed per-iteration costs (replicated grid "
+                                       "build, gather, launch floors of 1/N-sized kernels) bound this mode at 1024^2; "
+                                       "it exists for iterations too large for one GPU (BASELINE config #5)"}
         print(json.dumps(line))
-    r.close()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -308,8 +308,7 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
     }
     if(!r->shadow.counts) if((rc = devAlloc(r, &r->shadow.counts, 2))) return rc;
 
-    size_t freeB = 0, totalB = 0;
-    cudaMemGetInfo(&freeB, &totalB);
+    size_t freeB = 0, totalB = 0;      // queried only where something is (re)allocated
 
     const bool needVerts = r->useVC || r->useVM;
     if(needVerts && (r->vertSlots < lightBounces || r->verts.capacity == 0))
