@@ -477,7 +477,10 @@ int gatherLightVertices(svcm_renderer *r, MergeSet &set)
         if((rc = devAlloc(r, &r->gContProb, cap))) return rc;
         r->gatherCapacity = uint32_t(std::min<uint64_t>(cap, 0xFFFFFFFFu));
     }
-    if((rc = ensureGridSorted(r, uint32_t(need)))) return rc;
+    // (slack: the per-iteration counts wobble by a fraction of a percent and a reallocation is a
+    // device-wide synchronisation worth tens of milliseconds at config #5 sizes)
+    if(need > r->gridCapacity)
+        if((rc = ensureGridSorted(r, uint32_t(std::min<uint64_t>(need + need / 8, 0xFFFFFF00u))))) return rc;
 
     if(stride > 0)
     {
