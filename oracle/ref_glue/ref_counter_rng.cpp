@@ -27,7 +27,7 @@
 // replacement for src/rng.hxx (same five-method interface, src/rng.hxx:48-78)
 // Generator: Philox2x32-7 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"),
 // counter = (draw index, path index), key = seed + 0x85EBCA6B * (2*iteration + phase);
-// float = top 24 bits / 2^24 in [0,1).  The same definition is restated in
+// float = (top 24 bits | 1) / 2^24: strictly inside (0,1).  The same definition is restated in
 // oracle/vcm_oracle.cpp and in the product (smallvcm_b200/csrc/svcm_rng.cuh).
 // ---------------------------------------------------------------------------------------
 #define __RNG_HXX__
@@ -58,7 +58,7 @@ public:
     }
 
     int   GetInt()   { return int(GetUint() >> 1); }
-    float GetFloat() { return float(GetUint() >> 8) * (1.0f / 16777216.0f); }
+    float GetFloat() { return float((GetUint() >> 8) | 1u) * (1.0f / 16777216.0f); }
 
     Vec2f GetVec2f()
     {

@@ -158,7 +158,7 @@ struct Rng
     float GetFloat()
     {
         if(mMode == 0) return mDistFloat(mEngine);
-        return float(Philox(mDraw++, mPath, mKey) >> 8) * (1.0f / 16777216.0f);
+        return float((Philox(mDraw++, mPath, mKey) >> 8) | 1u) * (1.0f / 16777216.0f);
     }
 };
 

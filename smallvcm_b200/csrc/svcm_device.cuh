@@ -84,7 +84,7 @@ struct Frame3
 
 // ---------------------------------------------------------------------------------------
 // per-path random stream (DESIGN.md "random numbers"): Philox2x32-7, counter = (draw index,
-// path index), key = seed + 0x85EBCA6B * (2*iteration + phase); float = top 24 bits / 2^24.
+// path index), key = seed + 0x85EBCA6B * (2*iteration + phase); float = (top 24 bits | 1) / 2^24, i.e. 2^23 equally spaced values strictly inside (0, 1).
 // Replaces the reference's single sequential mt19937_64 stream (src/rng.hxx:41-86), which a
 // parallel renderer cannot reproduce; the draw ORDER inside a path is the reference's.
 // ---------------------------------------------------------------------------------------
@@ -116,7 +116,8 @@ struct PathRng
     uint32_t key, path, draw;
     SVCM_HD float next()
     {
-        return float(philox2x32_7(draw++, path, key) >> 8) * (1.0f / 16777216.0f);
+        // odd multiples of 2^-24: strictly inside (0, 1), every value exact in float32
+        return float((philox2x32_7(draw++, path, key) >> 8) | 1u) * (1.0f / 16777216.0f);
     }
 };
 

@@ -182,7 +182,7 @@ def test_full_size_properties_scene1_vcm_1024():
     assert abs(st["mergeAccepted"] - 25559886) < 0.01 * 25559886
     total_lum = float((img.astype(np.float64) @ LUM).sum())
     assert abs(total_lum - 277959) < 0.005 * 277959
-    assert np.isfinite(img).all() and img.min() >= 0       # (iteration 0 has no zero-pdf light sample)
+    assert np.isfinite(img).all() and img.min() >= 0
     img2, _, st2 = render(scene, "vcm", 1)
     for key in ("lightVertices", "mergeQueries", "mergeCandidates", "mergeAccepted", "lightRays", "cameraRays",
                 "shadowRays"):
@@ -214,17 +214,11 @@ def test_full_size_properties_scene1_vcm_4096_maxlen20():
     assert abs(st["lightVertices"] - 37817883) < 0.005 * 37817883
     assert abs(st["mergeQueries"] - 45.6e6) < 0.01 * 45.6e6
     assert st["mergeAccepted"] > 5e9 and st["mergeCandidates"] > 3e10
-    # Non-finite pixels are inherited, reference-identical behaviour: a light sample whose
-    # direction draw is exactly 0 has zero emission pdf and infinite throughput (AreaLight::Emit,
-    # src/lights.hxx:179-188; probability 2^-24 per path), and everything its vertices touch
-    # becomes inf/NaN — the oracle reproduces the same pixels. Bounded, not absent.
-    finite = np.isfinite(img).all(2)
-    assert (~finite).sum() <= 256
-    assert img[finite].min() >= 0
+    assert np.isfinite(img).all() and img.min() >= 0
     # same scene, same estimator: the mean radiance agrees with the 1024^2 image to its noise
     small, _, _ = render(sv.Scene.cornell_box(1, 1024, 1024), "vcm", 4, max_len=20)
-    sf = np.isfinite(small).all(2)
-    assert abs(img[finite].mean() - small[sf].mean() / 4) < 0.02 * img[finite].mean()
+    assert np.isfinite(small).all()
+    assert abs(img.mean() - small.mean() / 4) < 0.02 * img.mean()
 
 
 def test_full_size_properties_scene0_bpt_1024():
