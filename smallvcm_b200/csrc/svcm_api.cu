@@ -377,6 +377,8 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
             uint64_t cap = std::min<uint64_t>(worst, uint64_t(double(freeB) * 0.25) / 8u);
             cap = std::min<uint64_t>(cap, 0xFFFFFF00u);
             cap = std::max<uint64_t>(cap, old);
+            // test hook: a deliberately small pair list must surface as an error, not as a dim image
+            if(getenv("SVCM_DEBUG_PAIR_CAP")) cap = std::max<uint64_t>(32u, strtoull(getenv("SVCM_DEBUG_PAIR_CAP"), NULL, 10));
             if((rc = devAlloc(r, &r->pairs.pairs, cap))) return rc;
             r->pairs.capacity = uint32_t(cap);
         }
@@ -390,6 +392,8 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
         uint64_t cap = uint64_t(r->localPaths) * ((r->lightTraceOnly || r->pathTrace) ? std::min(camBounces, 4u) : 12u);
         cap = std::min<uint64_t>(cap, uint64_t(double(freeB) * 0.3) / 48u);
         cap = std::min<uint64_t>(std::max<uint64_t>(cap, 1024u), 0xFFFFFF00u);
+        // test hook: a deliberately small queue exercises the producers' inline fallback
+        if(getenv("SVCM_DEBUG_SHADOW_CAP")) cap = std::max<uint64_t>(32u, strtoull(getenv("SVCM_DEBUG_SHADOW_CAP"), NULL, 10));
         if((rc = devAlloc(r, &r->shadow.r0, cap))) return rc;
         if((rc = devAlloc(r, &r->shadow.r1, cap))) return rc;
         if((rc = devAlloc(r, &r->shadow.r2, cap))) return rc;

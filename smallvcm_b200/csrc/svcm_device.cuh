@@ -95,7 +95,9 @@ SVCM_HD uint32_t rngKey(int32_t seed, int32_t iteration, int32_t phase)
 
 SVCM_HD uint32_t philox2x32_7(uint32_t c0, uint32_t c1, uint32_t key)
 {
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
     for(int round = 0; round < 7; round++)
     {
 #ifdef __CUDA_ARCH__

@@ -268,6 +268,51 @@ def test_multi_handle_isolation():
     assert rel_l2(ib, render(s3, "bpm", 2)[0]) < 1e-5
 
 
+def test_full_shadow_queue_falls_back_to_inline_tracing(monkeypatch):
+    """A visibility queue that is far too small (64 segments for ~80 000) makes the producers trace
+    inline; the image must not change beyond float-atomic order."""
+    scene = sv.Scene.cornell_box(1, 96, 96)
+    ref, _, st = render(scene, "vcm", 2)
+    monkeypatch.setenv("SVCM_DEBUG_SHADOW_CAP", "64")
+    img, _, st2 = render(scene, "vcm", 2)
+    assert st2["shadowRays"] == st["shadowRays"] > 10000
+    assert rel_l2(img, ref) < 1e-5
+
+
+def test_pair_list_overflow_is_an_error_not_a_dim_image(monkeypatch):
+    """Records that do not fit are never dropped silently: the next synchronisation fails."""
+    scene = sv.Scene.cornell_box(1, 96, 96)
+    monkeypatch.setenv("SVCM_DEBUG_PAIR_CAP", "1000")
+    r = sv.VertexCM(scene, "vcm"); r.max_path_length = 10
+    r.run_iterations(0, 1)
+    with pytest.raises(sv.SvcmError) as e:
+        r.synchronize()
+    assert e.value.code == abi.E_NOMEM and "overflow" in str(e.value)
+    r.close()
+
+
+def test_handles_driven_from_concurrent_threads():
+    """render() calls RunIteration concurrently on DIFFERENT renderers from OpenMP threads
+    (src/smallvcm.cxx:82-108): two host threads, two handles (seed, seed+1), same device. ctypes
+    releases the GIL, so the library calls really overlap."""
+    import threading
+    scene = sv.Scene.cornell_box(1, 128, 128)
+    out = {}
+
+    def work(k):
+        r = sv.VertexCM(scene, "vcm", seed=1234 + k); r.max_path_length = 10
+        for it in range(6):
+            r.run_iteration(it)
+            r.accum()
+        out[k] = r.accum()[0]
+        r.close()
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in threads: t.start()
+    for t in threads: t.join()
+    for k in range(2):
+        assert rel_l2(out[k], render(scene, "vcm", 6, seed=1234 + k)[0]) < 1e-5
+
+
 def test_drop_in_driver_binary(tmp_path):
     """The reference's own main()/render() with VertexCMGpu injected (smallvcm_b200/bin/
     smallvcm_gpu, built where the reference checkout exists): `-s 1 -a vcm -i 2` writes an HDR
