@@ -273,6 +273,26 @@ SVCM_API int svcm_download_accum(svcm_renderer *r, float *rgb, int32_t *iteratio
  * src/framebuffer.hxx:70-73). */
 SVCM_API int svcm_clear_accum(svcm_renderer *r);
 
+/* The 8-bit images the reference's main() writes after the path (src/smallvcm.cxx:311-320),
+ * converted on the device from the accumulated image so that a viewer moves 3 or 4 bytes per
+ * pixel over PCIe instead of 12:
+ *   SVCM_IMAGE_BMP24  Framebuffer::SaveBMP's payload (src/framebuffer.hxx:196-215): rows
+ *                     bottom-up, B G R, no row padding, byte(min(255, max(0, pow(c, 1/gamma)*255)))
+ *   SVCM_IMAGE_RGBE   Framebuffer::SaveHDR's payload (src/framebuffer.hxx:229-249): rows
+ *                     top-down, shared-exponent R G B E (gamma ignored)
+ * of GetFramebuffer's image (accumulated colour * 1.f/iterations, src/renderer.hxx:49-55).
+ * svcm_image_bytes: payload size (-1 for an unknown format). svcm_image_header: writes the file
+ * header the reference puts in front of the payload into `out` if `capacity` suffices and
+ * returns its length. svcm_save_image = header + payload into `path`, format chosen from the
+ * last three characters ("bmp" / "hdr") like main(); anything else is SVCM_E_INVALID with the
+ * reference's "Used unknown extension" text. */
+#define SVCM_IMAGE_BMP24 0
+#define SVCM_IMAGE_RGBE  1
+SVCM_API int64_t svcm_image_bytes(int32_t format, int32_t width, int32_t height);
+SVCM_API int32_t svcm_image_header(int32_t format, int32_t width, int32_t height, uint8_t *out, int32_t capacity);
+SVCM_API int svcm_download_image(svcm_renderer *r, int32_t format, float gamma, uint8_t *out, int32_t *iterationsDone);
+SVCM_API int svcm_save_image(svcm_renderer *r, const char *path, float gamma);
+
 SVCM_API int svcm_get_stats(svcm_renderer *r, SvcmStats *out);
 SVCM_API int svcm_get_profile(svcm_renderer *r, SvcmProfile *out);
 
@@ -404,6 +424,11 @@ SVCM_API int svcm_bsdf_evaluate_batch(const SvcmSceneDesc *scene, const float *i
 SVCM_API int svcm_bsdf_sample_batch(const SvcmSceneDesc *scene, const float *in,
                                     int64_t count, int32_t fixIsLight, int32_t device,
                                     float *out, uint32_t *events);
+
+/* The image conversions of svcm_download_image on a caller-supplied accumulated image
+ * [height][width][3] (host memory); out holds svcm_image_bytes(format, width, height). */
+SVCM_API int svcm_image_convert_batch(const float *accum, int32_t width, int32_t height, int32_t iterations,
+                                      int32_t format, float gamma, int32_t device, uint8_t *out);
 
 /* The per-path random stream shared by this library and the parity oracle (DESIGN.md
  * "random numbers"): fills out[i*draws + k] with draw k of path `firstPath + i` for

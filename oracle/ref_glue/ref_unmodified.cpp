@@ -96,6 +96,23 @@ REF_API float ref_total_luminance(const float *rgb, int width, int height)
     return fb.TotalLuminance();
 }
 
+// Framebuffer::SaveBMP / SaveHDR (src/framebuffer.hxx:170-251) of a caller-supplied accumulated
+// image after AbstractRenderer::GetFramebuffer's scaling (src/renderer.hxx:49-55): the reference
+// writes the file itself; the tests read it back to pin the oracle's restatement of the pixel
+// conversions and the product's file headers. format 0 = bmp, 1 = hdr.
+REF_API int ref_save_image(const float *accum, int width, int height, int iterations, int format,
+                           float gamma, const char *path)
+{
+    Framebuffer fb;
+    fb.Setup(Vec2f(float(width), float(height)));
+    memcpy(&fb.mColor[0], accum, sizeof(float) * 3 * size_t(width) * size_t(height));
+    if(iterations > 0) fb.Scale(1.f / iterations);
+    if(format == 0) fb.SaveBMP(path, gamma);
+    else if(format == 1) fb.SaveHDR(path);
+    else return -1;
+    return 0;
+}
+
 // Flattens the reference's own Scene for `sceneId` with the product's host glue
 // (smallvcm_b200/host/flatten_scene.hxx) into caller-provided arrays; used to check the
 // library's built-in scene builder (svcm_scene_cornell_box) field by field.

@@ -1907,6 +1907,63 @@ ORACLE_API float oracle_total_luminance(const float *rgb, int width, int height)
     return lum;
 }
 
+// The x86 float -> unsigned char conversion the reference's `byte(float)` casts compile to
+// (cvttss2si to a 32-bit integer, low byte kept; NaN and out-of-range give the "integer
+// indefinite" 0x80000000, i.e. byte 0). Written out so the device code can restate it.
+static inline unsigned char ByteOfFloat(float f)
+{
+    if(!(std::fabs(f) < 2147483648.f)) return 0;
+    return (unsigned char)(unsigned(int(f)) & 0xFFu);
+}
+
+// Pixel payload of Framebuffer::SaveBMP (src/framebuffer.hxx:196-215) applied to the image
+// AbstractRenderer::GetFramebuffer returns (src/renderer.hxx:49-55: accumulated colour times
+// 1.f / iterations): rows bottom-up, B G R bytes, no row padding, each byte
+// byte(min(255, max(0, pow(c, 1/gamma) * 255))) with std::min/std::max's NaN behaviour.
+ORACLE_API void oracle_bmp_payload(const float *accum, int width, int height, int iterations,
+                                   float gamma, unsigned char *out)
+{
+    const float scale = iterations > 0 ? 1.f / iterations : 1.f;
+    const float invGamma = 1.f / gamma;
+    for(int y = 0; y < height; y++)
+        for(int x = 0; x < width; x++)
+        {
+            const float *src = accum + 3 * (size_t(x) + size_t(height - y - 1) * width);
+            for(int c = 0; c < 3; c++)
+            {
+                const float value = iterations > 0 ? src[2 - c] * scale : src[2 - c];
+                const float g = std::pow(value, invGamma) * 255.f;
+                *out++ = ByteOfFloat(std::min(255.f, std::max(0.f, g)));
+            }
+        }
+}
+
+// Pixel payload of Framebuffer::SaveHDR (src/framebuffer.hxx:229-249): rows top-down, shared-
+// exponent R G B E bytes. Whether the unqualified frexp there binds to the float or the double
+// overload does not matter: a double quotient of two 24-bit significands rounds to the same float
+// as the float quotient (53 >= 2*24+2), which a 2e8-sample sweep confirmed.
+ORACLE_API void oracle_hdr_payload(const float *accum, int width, int height, int iterations,
+                                   unsigned char *out)
+{
+    const float scale = iterations > 0 ? 1.f / iterations : 1.f;
+    for(size_t i = 0; i < size_t(width) * size_t(height); i++, out += 4)
+    {
+        float rgb[3];
+        for(int c = 0; c < 3; c++) rgb[c] = iterations > 0 ? accum[3 * i + c] * scale : accum[3 * i + c];
+        out[0] = out[1] = out[2] = out[3] = 0;
+        float v = std::max(rgb[0], std::max(rgb[1], rgb[2]));
+        if(v >= 1e-32f)
+        {
+            int e;
+            v = float(::frexp(double(v), &e) * 256.f / v);
+            out[0] = ByteOfFloat(rgb[0] * v);
+            out[1] = ByteOfFloat(rgb[1] * v);
+            out[2] = ByteOfFloat(rgb[2] * v);
+            out[3] = (unsigned char)(unsigned(e + 128) & 0xFFu);
+        }
+    }
+}
+
 // The reference's OpenMP driver loop, src/smallvcm.cxx:52-151, over oracle renderers: one
 // private renderer per thread with seed baseSeed + thread, iterations distributed by
 // `omp parallel for`, framebuffers averaged. Used as the "port" CPU baseline when

@@ -109,6 +109,7 @@ struct svcm_renderer
     long long ringHead;             // iterations recorded so far
     long long ringTail;             // first iteration not yet returned by svcm_get_profile
     float    *accum;
+    uint8_t  *image8 = NULL;        // W*H*4 bytes, allocated by the first svcm_download_image
     GridBuffers grid;
     uint32_t  gridCells, gridCapacity;
     int32_t  *bboxInit;
@@ -844,7 +845,7 @@ void svcm_destroy(svcm_renderer *r)
     devFree(r->queueCountsLight); devFree(r->queueCountsCamera);
     devFree(r->shadow.r0); devFree(r->shadow.r1); devFree(r->shadow.r2); devFree(r->shadow.counts);
     freeVerts(r); freeQueries(r); freeGridSorted(r); freeGather(r);
-    devFree(r->pathVertCount); devFree(r->counters); devFree(r->accum);
+    devFree(r->pathVertCount); devFree(r->counters); devFree(r->accum); devFree(r->image8);
     devFree(r->grid.cellCount); devFree(r->grid.blockSums); devFree(r->grid.bboxBits);
     devFree(r->qsort.cellCount); devFree(r->qsort.blockSums);
     devFree(r->bboxInit); devFree(r->devCounts64);
@@ -921,6 +922,80 @@ int svcm_download_accum(svcm_renderer *r, float *rgb, int32_t *iterationsDone)
     SVCM_CUDA(r, cudaStreamSynchronize(r->stream));
     if(iterationsDone) *iterationsDone = r->iterationsDone;
     return finishStats(r);
+}
+
+int64_t svcm_image_bytes(int32_t format, int32_t width, int32_t height)
+{
+    if(width < 0 || height < 0) return -1;
+    if(format == SVCM_IMAGE_BMP24) return int64_t(width) * height * 3;
+    if(format == SVCM_IMAGE_RGBE)  return int64_t(width) * height * 4;
+    return -1;
+}
+
+int32_t svcm_image_header(int32_t format, int32_t width, int32_t height, uint8_t *out, int32_t capacity)
+{
+    if(width < 0 || height < 0 || (!out && capacity > 0)) return -1;
+    if(format == SVCM_IMAGE_BMP24)
+    {
+        // "BM" + the 52-byte BmpHeader of src/framebuffer.hxx:149-193 (little endian)
+        const uint32_t payload = uint32_t(width) * uint32_t(height) * 3u;
+        const uint32_t words[13] = { 54u + payload, 0u, 54u, 40u, uint32_t(width), uint32_t(height),
+                                     1u | (24u << 16), 0u, payload, 2953u, 2953u, 0u, 0u };
+        if(capacity >= 54)
+        {
+            out[0] = 'B'; out[1] = 'M';
+            for(int w = 0; w < 13; w++)
+                for(int b = 0; b < 4; b++) out[2 + 4 * w + b] = uint8_t(words[w] >> (8 * b));
+        }
+        return 54;
+    }
+    if(format == SVCM_IMAGE_RGBE)
+    {
+        // src/framebuffer.hxx:224-227
+        char text[128];
+        const int n = snprintf(text, sizeof(text), "#?RADIANCE\n# SmallVCM\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n", height, width);
+        if(capacity >= n) memcpy(out, text, size_t(n));
+        return n;
+    }
+    return -1;
+}
+
+int svcm_download_image(svcm_renderer *r, int32_t format, float gamma, uint8_t *out, int32_t *iterationsDone)
+{
+    if(!r || !out) return SVCM_E_INVALID;
+    if(format != SVCM_IMAGE_BMP24 && format != SVCM_IMAGE_RGBE) return fail(r, SVCM_E_INVALID, "unknown image format %d", format);
+    if(format == SVCM_IMAGE_BMP24 && !(gamma > 0.f)) return fail(r, SVCM_E_INVALID, "gamma must be positive");
+    SVCM_CUDA(r, cudaSetDevice(r->device));
+    if(!r->image8) { const int rc = devAlloc(r, &r->image8, size_t(r->paths) * 4u); if(rc) return rc; }
+    launchImageConvert(r->accum, r->resX, r->resY, r->iterationsDone, format, gamma, r->image8, r->stream);
+    SVCM_CUDA(r, cudaGetLastError());
+    SVCM_CUDA(r, cudaMemcpyAsync(out, r->image8, size_t(svcm_image_bytes(format, r->resX, r->resY)), cudaMemcpyDeviceToHost, r->stream));
+    SVCM_CUDA(r, cudaStreamSynchronize(r->stream));
+    if(iterationsDone) *iterationsDone = r->iterationsDone;
+    return finishStats(r);
+}
+
+int svcm_save_image(svcm_renderer *r, const char *path, float gamma)
+{
+    if(!r || !path) return SVCM_E_INVALID;
+    // main() decides by the last three characters of the name (src/smallvcm.cxx:311-320)
+    const size_t len = strlen(path);
+    const char *ext = len >= 3 ? path + len - 3 : "";
+    int format;
+    if(!strcmp(ext, "bmp")) format = SVCM_IMAGE_BMP24;
+    else if(!strcmp(ext, "hdr")) format = SVCM_IMAGE_RGBE;
+    else return fail(r, SVCM_E_INVALID, "Used unknown extension %s", ext);
+    uint8_t header[128];
+    const int32_t headerBytes = svcm_image_header(format, r->resX, r->resY, header, int32_t(sizeof(header)));
+    std::vector<uint8_t> payload(size_t(svcm_image_bytes(format, r->resX, r->resY)));
+    const int rc = svcm_download_image(r, format, gamma, payload.data(), NULL);
+    if(rc) return rc;
+    FILE *f = fopen(path, "wb");
+    if(!f) return fail(r, SVCM_E_INVALID, "cannot open %s for writing", path);
+    const bool ok = fwrite(header, 1, size_t(headerBytes), f) == size_t(headerBytes) &&
+                    fwrite(payload.data(), 1, payload.size(), f) == payload.size();
+    if(fclose(f) != 0 || !ok) return fail(r, SVCM_E_INVALID, "short write to %s", path);
+    return SVCM_OK;
 }
 
 int svcm_clear_accum(svcm_renderer *r)
@@ -1370,6 +1445,27 @@ int svcm_rng_stream_device(int32_t seed, int32_t iteration, int32_t phase, uint3
         e = cudaMemcpy(out, d, sizeof(float) * n, cudaMemcpyDeviceToHost);
     }
     return cudaDone(e, "svcm_rng_stream_device");
+}
+
+int svcm_image_convert_batch(const float *accum, int32_t width, int32_t height, int32_t iterations, int32_t format,
+                             float gamma, int32_t device, uint8_t *out)
+{
+    const int64_t bytes = svcm_image_bytes(format, width, height);
+    if(!accum || !out || bytes < 0 || (format == SVCM_IMAGE_BMP24 && !(gamma > 0.f)))
+        return fail(NULL, SVCM_E_INVALID, "bad arguments");
+    int rc = checkDevice(NULL, device); if(rc) return rc;
+    cudaSetDevice(device);
+    if(bytes == 0) return SVCM_OK;
+    Scratch s; cudaError_t e = cudaSuccess; const size_t n = size_t(width) * size_t(height);
+    float *dIn = s.alloc<float>(3 * n, e);
+    uint8_t *dOut = s.alloc<uint8_t>(4 * n, e);
+    if(e == cudaSuccess) e = cudaMemcpy(dIn, accum, sizeof(float) * 3 * n, cudaMemcpyHostToDevice);
+    if(e == cudaSuccess)
+    {
+        launchImageConvert(dIn, width, height, iterations, format, gamma, dOut, 0);
+        e = cudaMemcpy(out, dOut, size_t(bytes), cudaMemcpyDeviceToHost);
+    }
+    return cudaDone(e, "svcm_image_convert_batch");
 }
 
 } // extern "C"

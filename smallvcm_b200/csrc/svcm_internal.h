@@ -213,6 +213,9 @@ void launchBsdfEvaluateBatch(const DevScene &sc, const float *in, int64_t count,
                              float *out, cudaStream_t stream);
 void launchBsdfSampleBatch(const DevScene &sc, const float *in, int64_t count, int fixIsLight,
                            float *out, uint32_t *events, cudaStream_t stream);
+// SaveBMP / SaveHDR pixel payloads of the accumulated image (src/framebuffer.hxx:170-251)
+void launchImageConvert(const float *accum, int width, int height, int iterations, int format, float gamma,
+                        uint8_t *out, cudaStream_t stream);
 void launchRngStream(uint32_t key, uint32_t firstPath, int paths, int draws, float *out,
                      cudaStream_t stream);
 // packs host-layout records into the device streams

@@ -1773,6 +1773,87 @@ void launchBsdfSampleBatch(const DevScene &sc, const float *in, int64_t count, i
     if(fixIsLight) k_bsdfSampleBatch<true><<<gridN, SVCM_BLOCK, 0, stream>>>(sc, in, count, out, events);
     else           k_bsdfSampleBatch<false><<<gridN, SVCM_BLOCK, 0, stream>>>(sc, in, count, out, events);
 }
+// ------------------------------------------------------------------------------------------
+// image conversions after the path: the 8-bit images main() writes
+// (src/smallvcm.cxx:313-320) computed from the accumulated image where it lies, so that a
+// progressive viewer downloads 3 or 4 bytes per pixel instead of 12
+// ------------------------------------------------------------------------------------------
+
+// x86 `byte(float)` as the reference's casts behave (cvttss2si, low byte; NaN / out of range -> 0)
+__device__ __forceinline__ uint32_t byteOfFloat(float f)
+{
+    if(!(fabsf(f) < 2147483648.f)) return 0u;
+    return uint32_t(__float2int_rz(f)) & 0xFFu;
+}
+
+// std::pow(float, float) of glibc evaluates in double and rounds once; the device's double pow
+// rounded to float agrees with it except on sub-ulp ties (tests/test_gpu_image.py bounds those)
+__device__ __forceinline__ uint32_t gammaByte(float c, float invGamma)
+{
+    const float g = __fmul_rn(float(pow(double(c), double(invGamma))), 255.f);
+    const float lo = (0.f < g) ? g : 0.f;       // std::max(0.f, g): NaN -> 0
+    const float hi = (lo < 255.f) ? lo : 255.f; // std::min(255.f, lo)
+    return byteOfFloat(hi);
+}
+
+// Framebuffer::SaveBMP payload, src/framebuffer.hxx:196-215: thread per OUTPUT pixel, rows
+// bottom-up, B G R. `scale` is GetFramebuffer's 1.f / mIterations (src/renderer.hxx:53-54).
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_imageBmp(const float *__restrict__ accum, int width, int height, float scale, int applyScale,
+           float invGamma, uint8_t *__restrict__ out)
+{
+    const int64_t pixels = int64_t(width) * height;
+    for(int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < pixels; i += int64_t(gridDim.x) * blockDim.x)
+    {
+        const int y = int(i / width), x = int(i - int64_t(y) * width);
+        const float *src = accum + 3 * (int64_t(x) + int64_t(height - y - 1) * width);
+        float r = src[0], g = src[1], b = src[2];
+        if(applyScale) { r = __fmul_rn(r, scale); g = __fmul_rn(g, scale); b = __fmul_rn(b, scale); }
+        uint8_t *dst = out + 3 * i;
+        dst[0] = uint8_t(gammaByte(b, invGamma));
+        dst[1] = uint8_t(gammaByte(g, invGamma));
+        dst[2] = uint8_t(gammaByte(r, invGamma));
+    }
+}
+
+// Framebuffer::SaveHDR payload, src/framebuffer.hxx:229-249: rows top-down, R G B E
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_imageRgbe(const float *__restrict__ accum, int64_t pixels, float scale, int applyScale, uchar4 *__restrict__ out)
+{
+    for(int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < pixels; i += int64_t(gridDim.x) * blockDim.x)
+    {
+        float r = accum[3 * i], g = accum[3 * i + 1], b = accum[3 * i + 2];
+        if(applyScale) { r = __fmul_rn(r, scale); g = __fmul_rn(g, scale); b = __fmul_rn(b, scale); }
+        const float gb = (g < b) ? b : g;           // std::max(g, b)
+        float v = (r < gb) ? gb : r;                // std::max(r, max(g, b))
+        uchar4 px = make_uchar4(0, 0, 0, 0);
+        if(v >= 1e-32f)
+        {
+            int e;
+            const float m = frexpf(v, &e);
+            v = __fdiv_rn(__fmul_rn(m, 256.f), v);
+            px.x = (unsigned char)byteOfFloat(__fmul_rn(r, v));
+            px.y = (unsigned char)byteOfFloat(__fmul_rn(g, v));
+            px.z = (unsigned char)byteOfFloat(__fmul_rn(b, v));
+            px.w = (unsigned char)(uint32_t(e + 128) & 0xFFu);
+        }
+        out[i] = px;
+    }
+}
+
+void launchImageConvert(const float *accum, int width, int height, int iterations, int format, float gamma,
+                        uint8_t *out, cudaStream_t stream)
+{
+    const int64_t pixels = int64_t(width) * height;
+    if(pixels <= 0) return;
+    const float scale = iterations > 0 ? 1.f / float(iterations) : 1.f;
+    const int grid = gridFor(pixels, SVCM_BLOCK, 8);
+    if(format == SVCM_IMAGE_BMP24)
+        k_imageBmp<<<grid, SVCM_BLOCK, 0, stream>>>(accum, width, height, scale, iterations > 0, 1.f / gamma, out);
+    else
+        k_imageRgbe<<<grid, SVCM_BLOCK, 0, stream>>>(accum, pixels, scale, iterations > 0, (uchar4 *)out);
+}
+
 void launchRngStream(uint32_t key, uint32_t firstPath, int paths, int draws, float *out, cudaStream_t stream)
 {
     if(paths <= 0) return;

@@ -93,6 +93,20 @@ public:
 
     svcm_renderer *Handle() const { return mHandle; }
 
+    // What main() does with the result of ONE renderer (src/smallvcm.cxx:311-320:
+    // GetFramebuffer, then SaveBMP with gamma 2.2 or SaveHDR by extension), with the pixel
+    // conversion done on the device. Returns false for an unknown extension or an unused
+    // renderer, after printing the reference's message for the former.
+    bool SaveImage(const char *aFilename, float aGamma = 2.2f)
+    {
+        if(mHandle == NULL)
+            return false;
+        if(svcm_save_image(mHandle, aFilename, aGamma) == SVCM_OK)
+            return true;
+        printf("%s\n", svcm_last_error(mHandle));
+        return false;
+    }
+
 private:
 
     // Device state is created on first use: the driver builds one renderer per hardware

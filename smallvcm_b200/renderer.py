@@ -164,6 +164,19 @@ class VertexCM:
             img *= np.float32(1.0 / n)
         return img
 
+    def image8(self, fmt="bmp", gamma=2.2):
+        """The pixel payload of Framebuffer::SaveBMP ("bmp": [H, W, 3] uint8, rows bottom-up,
+        B G R) or SaveHDR ("hdr": [H, W, 4] uint8 R G B E) of the averaged image, converted on
+        the device (svcm_download_image)."""
+        code = {"bmp": abi.IMAGE_BMP24, "hdr": abi.IMAGE_RGBE}[fmt]
+        out = np.empty((self.height, self.width, 3 if code == abi.IMAGE_BMP24 else 4), np.uint8)
+        _check(self._lib.svcm_download_image(self._h, code, gamma, _ptr(out), None), self._h)
+        return out
+
+    def save_image(self, path, gamma=2.2):
+        """main()'s image output (src/smallvcm.cxx:311-320): *.bmp or *.hdr, chosen by extension."""
+        _check(self._lib.svcm_save_image(self._h, os.fsencode(path), gamma), self._h)
+
     def was_used(self):
         return self.accum()[1] > 0
 
@@ -289,6 +302,24 @@ def rng_stream(seed, iteration, phase, first_path, paths, draws):
     out = np.zeros((paths, draws), np.float32)
     _check(load_library().svcm_rng_stream(seed, iteration, phase, first_path, paths, draws, _ptr(out)))
     return out
+
+
+def image_convert_batch(accum, iterations, fmt="bmp", gamma=2.2, device=0):
+    """svcm_image_convert_batch: SaveBMP / SaveHDR payload bytes of a host image [H, W, 3]."""
+    accum = np.ascontiguousarray(accum, np.float32)
+    h, w = accum.shape[:2]
+    code = {"bmp": abi.IMAGE_BMP24, "hdr": abi.IMAGE_RGBE}[fmt]
+    out = np.empty(h * w * (3 if code == abi.IMAGE_BMP24 else 4), np.uint8)
+    _check(load_library().svcm_image_convert_batch(_ptr(accum), w, h, iterations, code, gamma, device, _ptr(out)))
+    return out
+
+
+def image_header(fmt, width, height):
+    """The bytes the reference writes in front of the pixel payload (svcm_image_header)."""
+    code = {"bmp": abi.IMAGE_BMP24, "hdr": abi.IMAGE_RGBE}[fmt]
+    buf = np.zeros(128, np.uint8)
+    n = load_library().svcm_image_header(code, width, height, _ptr(buf), len(buf))
+    return buf[:n].tobytes()
 
 
 def rng_stream_device(seed, iteration, phase, first_path, paths, draws, device=0):

@@ -13,6 +13,8 @@ Files
   ref_noise.npz       unmodified reference 128x128 x16 iterations, two seeds (noise floor for
                       the statistical GPU-vs-reference test)
   scenes.npz          the reference's Scene for g_SceneConfigs[0..3], flattened, raw bytes
+  image_files.npz     the files Framebuffer::SaveBMP / SaveHDR wrote for one small accumulated
+                      image with hostile values (NaN, inf, negatives, denormals), 0 and 3 iterations
 """
 import ctypes as C
 import json
@@ -37,8 +39,32 @@ def raw(x):
     return np.frombuffer(C.string_at(C.addressof(x), C.sizeof(x)), np.uint8).copy()
 
 
+def image_input():
+    """A 24x16 accumulated image: smooth values, then a block of hostile ones."""
+    rng = np.random.default_rng(77)
+    img = (rng.random((16, 24, 3), dtype=np.float32) ** 4 * 3).astype(np.float32)
+    flat = img.reshape(-1)
+    flat[0:20] = [np.nan, np.inf, -np.inf, -1.5, 0, 1e-33, 1e-32, 1e-31, 255.99998, 1e30, 3.4e38, -0.0, 1, 2, 4,
+                  0.5, 0.99999994, 1.9999999, 127.99999, 1e-38]
+    flat[20:400] = np.exp(rng.uniform(-80, 80, 380)).astype(np.float32) * rng.choice([1, 1, 1, -1], 380)
+    return img
+
+
+def image_fixture():
+    import tempfile
+    img = image_input()
+    out = {"accum": img}
+    with tempfile.TemporaryDirectory() as d:
+        for it in (0, 3):
+            out["bmp_it%d" % it] = np.frombuffer(oa.ref_save_image(img, it, 0, 2.2, os.path.join(d, "a.bmp")), np.uint8)
+            out["hdr_it%d" % it] = np.frombuffer(oa.ref_save_image(img, it, 1, 1.0, os.path.join(d, "a.hdr")), np.uint8)
+    np.savez_compressed(os.path.join(HERE, "image_files.npz"), **out)
+    print("image_files.npz", {k: v.shape for k, v in out.items()})
+
+
 def main():
     oa.build_oracle()
+    image_fixture()
     assert oa.have_ref() and oa.have_ref_ctr(), "needs the reference checkout"
 
     # --- known answers of the unmodified reference (1 renderer, seed 1234, minLen 0) ---------

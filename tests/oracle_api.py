@@ -167,6 +167,10 @@ def oracle_lib():
         lib.oracle_counters.argtypes = [VP, VP]
         lib.oracle_total_luminance.restype = f32
         lib.oracle_total_luminance.argtypes = [VP, i32, i32]
+        lib.oracle_bmp_payload.restype = None
+        lib.oracle_bmp_payload.argtypes = [VP, i32, i32, i32, f32, VP]
+        lib.oracle_hdr_payload.restype = None
+        lib.oracle_hdr_payload.argtypes = [VP, i32, i32, i32, VP]
         lib.oracle_render.restype = C.c_double
         lib.oracle_render.argtypes = [PSD, i32, i32, i32, i32, i32, u32, u32, f32, f32, VP]
         _oracle = lib
@@ -213,6 +217,20 @@ def oracle_total_luminance(img):
     return float(oracle_lib().oracle_total_luminance(_ptr(img), img.shape[1], img.shape[0]))
 
 
+def oracle_bmp_payload(accum, iterations, gamma):
+    accum = np.ascontiguousarray(accum, np.float32)
+    out = np.empty(accum.shape[0] * accum.shape[1] * 3, np.uint8)
+    oracle_lib().oracle_bmp_payload(_ptr(accum), accum.shape[1], accum.shape[0], iterations, gamma, _ptr(out))
+    return out
+
+
+def oracle_hdr_payload(accum, iterations):
+    accum = np.ascontiguousarray(accum, np.float32)
+    out = np.empty(accum.shape[0] * accum.shape[1] * 4, np.uint8)
+    oracle_lib().oracle_hdr_payload(_ptr(accum), accum.shape[1], accum.shape[0], iterations, _ptr(out))
+    return out
+
+
 def oracle_render(scene, algorithm, iterations, threads, base_seed=1234, rng_mode=0,
                   max_path_length=10, min_path_length=0, radius_factor=0.003, radius_alpha=0.75,
                   want_image=True):
@@ -254,6 +272,8 @@ def ref_lib():
         lib.ref_num_procs.restype = i32
         lib.ref_scene_mask.restype = u32
         lib.ref_scene_mask.argtypes = [i32]
+        lib.ref_save_image.restype = i32
+        lib.ref_save_image.argtypes = [VP, i32, i32, i32, i32, f32, C.c_char_p]
         lib.ref_flatten_scene.restype = i32
         lib.ref_flatten_scene.argtypes = [i32, i32, i32] + [VP] * 10
         _ref = lib
@@ -271,6 +291,16 @@ def ref_render(scene_id, algorithm, width, height, iterations, threads=1, base_s
     if secs < 0:
         raise ValueError("ref_render failed")
     return secs, out
+
+
+def ref_save_image(accum, iterations, fmt, gamma, path):
+    """The bytes of the file the reference's Framebuffer::SaveBMP (fmt 0) / SaveHDR (fmt 1) writes."""
+    accum = np.ascontiguousarray(accum, np.float32)
+    rc = ref_lib().ref_save_image(_ptr(accum), accum.shape[1], accum.shape[0], iterations, fmt, gamma,
+                                  str(path).encode())
+    assert rc == 0
+    with open(path, "rb") as f:
+        return f.read()
 
 
 class FlatSceneCopy:

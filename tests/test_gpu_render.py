@@ -329,3 +329,28 @@ def test_drop_in_driver_binary(tmp_path):
     assert res.returncode == 0, res.stdout + res.stderr
     assert "vertex connection and merging" in res.stdout
     assert os.path.getsize(out) > 512 * 512
+
+
+def test_drop_in_driver_time_budget(tmp_path):
+    """`-t <sec>` of the reference's render() (src/smallvcm.cxx:79-95) with the GPU renderer: the
+    driver build substitutes a wall clock for clock(), so two seconds are two seconds of
+    rendering with two host threads (two handles on one device), not CPU-seconds."""
+    import re
+    import subprocess
+    import time
+    exe = os.path.abspath(os.path.join(os.path.dirname(GOLD), "..", "smallvcm_b200", "bin", "smallvcm_gpu"))
+    if not os.path.exists(exe):
+        pytest.skip("drop-in driver not built (needs the reference checkout)")
+    out = str(tmp_path / "timed.bmp")
+    env = dict(os.environ, OMP_NUM_THREADS="2", SVCM_DEVICE="0")
+    t0 = time.time()
+    res = subprocess.run([exe, "-s", "1", "-a", "vcm", "-t", "2", "-o", out], capture_output=True, text=True,
+                         env=env, timeout=600)
+    wall = time.time() - t0
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "Target:  2 seconds render time" in res.stdout
+    reported = float(re.search(r"done in ([0-9.]+) s", res.stdout).group(1))
+    assert 2.0 <= reported < 4.0 and reported <= wall + 0.05, (reported, wall)
+    assert os.path.getsize(out) == 54 + 512 * 512 * 3
+    pixels = np.fromfile(out, np.uint8, offset=54)
+    assert 40 < pixels.mean() < 200         # a converged-looking picture, many iterations averaged
