@@ -1311,11 +1311,11 @@ k_merge(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst i
 // ------------------------------------------------------------------------------------------
 #define MERGE_WARPS (SVCM_BLOCK / 32)
 #define MERGE_QWORDS 20     // per-query words parked in shared memory for the pair evaluation
-#define MERGE_IDX_BITS 27   // queue entry = owner lane << 27 | sorted particle index
 
 struct MergeWarpSmem
 {
-    uint32_t queue[64];                 // ring of accepted pairs
+    uint32_t queue[64];                 // ring of accepted pairs: sorted particle index ...
+    uint8_t  queueOwner[64];            // ... and the lane whose query accepted it
     float    q[MERGE_QWORDS][32];       // [word][owner lane]: conflict-free for distinct owners
     float    acc[3][32];                // per-owner radiance sums
     uint32_t rangeStart[8][32];
@@ -1328,8 +1328,7 @@ SVCM_D void mergeEvaluatePairs(const DevScene &sc, const IterConst &ic, const Gr
     const uint32_t lane = laneId();
     if(head + lane < tail)
     {
-        const uint32_t e = w.queue[(head + lane) & 63u];
-        const uint32_t owner = e >> MERGE_IDX_BITS, idx = e & ((1u << MERGE_IDX_BITS) - 1u);
+        const uint32_t idx = w.queue[(head + lane) & 63u], owner = w.queueOwner[(head + lane) & 63u];
         const uint32_t lvLen = __float_as_uint(g.sPosLen[idx].w);
         const uint32_t lenMat = __float_as_uint(w.q[12][owner]);
         const uint32_t camLen = lenMat & 0xFFFFu;
@@ -1474,7 +1473,8 @@ k_mergeLane(const __grid_constant__ DevScene sc, const __grid_constant__ IterCon
             {
                 if(hitIt)
                 {
-                    w.queue[(tail + uint32_t(__popc(m & ltMask))) & 63u] = (lane << MERGE_IDX_BITS) | idx;
+                    const uint32_t slot = (tail + uint32_t(__popc(m & ltMask))) & 63u;
+                    w.queue[slot] = idx; w.queueOwner[slot] = uint8_t(lane);
                     accepted++;
                 }
                 tail += uint32_t(__popc(m));
@@ -1727,8 +1727,7 @@ void launchMerge(const DevScene &sc, const IterConst &ic, const QueryStore &quer
 {
     const uint64_t maxQueries = queryCount ? queries.capacity : hostQueryCount;
     if(maxQueries == 0) return;
-    // the lane-per-query kernel packs (owner lane, particle index) into 32 bits
-    if(groupSize == 1 && particleCapacity >= (1u << MERGE_IDX_BITS)) groupSize = 8;
+    (void)particleCapacity;
     if(groupSize == 1)
     {
         k_mergeLane<<<gridFor(maxQueries, SVCM_BLOCK, 4), SVCM_BLOCK, 0, stream>>>(

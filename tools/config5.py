@@ -22,6 +22,8 @@ scene = sv.Scene.cornell_box(1, W, W)
 r = sv.VertexCM(scene, "vcm", seed=1234, device=local_rank, rank=rank, world_size=world)
 r.max_path_length = L
 r.set_option(abi.OPT_PROFILE, 1)
+if os.environ.get("MERGE_GROUP"):
+    r.set_option(abi.OPT_MERGE_GROUP, int(os.environ["MERGE_GROUP"]))
 if world > 1:
     uid = sv.comm_unique_id() if rank == 0 else None
     r.comm_init(D.broadcast_bytes(uid, abi.COMM_ID_BYTES, 0, tdev))
