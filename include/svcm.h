@@ -53,14 +53,19 @@ enum {
 };
 
 /* ----------------------------------------------------------------------------------
- * compiled-in scene limits: the whole scene travels to every kernel as a __grid_constant__
- * parameter (constant bank, ~5 KB), so concurrent handles with different scenes never
- * share state. The reference's scenes hold <= 22 primitives, 9 materials, 2 lights. A
- * spatial acceleration structure for bigger scenes is SURVEY §8(f) rank 2, not this path.
+ * compiled-in scene limits: camera, materials, lights and up to SVCM_MAX_PRIMITIVES
+ * primitives travel to every kernel as a __grid_constant__ parameter (constant bank,
+ * ~5 KB), so concurrent handles with different scenes never share state. The reference's
+ * scenes hold <= 22 primitives, 9 materials, 2 lights and are intersected by a loop over
+ * the whole list (src/geometry.hxx:65-91), which that size keeps. Longer lists (up to
+ * SVCM_MAX_PRIMITIVES_BVH) are copied to device memory under a bounding volume hierarchy
+ * built at svcm_create; traversal returns exactly what the loop
+ * would: same per-primitive test, first-in-list wins equal distances.
  * -------------------------------------------------------------------------------- */
-#define SVCM_MAX_PRIMITIVES 64
-#define SVCM_MAX_MATERIALS  16
-#define SVCM_MAX_LIGHTS     8
+#define SVCM_MAX_PRIMITIVES     64
+#define SVCM_MAX_PRIMITIVES_BVH (1 << 24)
+#define SVCM_MAX_MATERIALS      16
+#define SVCM_MAX_LIGHTS         8
 
 /* ----------------------------------------------------------------------------------
  * flattened scene (replaces the pointer graph of reference src/scene.hxx:474-485)
@@ -424,6 +429,19 @@ SVCM_API int svcm_bsdf_evaluate_batch(const SvcmSceneDesc *scene, const float *i
 SVCM_API int svcm_bsdf_sample_batch(const SvcmSceneDesc *scene, const float *in,
                                     int64_t count, int32_t fixIsLight, int32_t device,
                                     float *out, uint32_t *events);
+
+/* The hierarchy svcm_create builds for scenes of more than SVCM_MAX_PRIMITIVES primitives
+ * (host code, no GPU needed; exposed for inspection and for the CPU check of the traversal
+ * in tests/). Node 0 is the root. Inner node: count == 0, children are nodes `first` and
+ * `first + 1`. Leaf: `count` slots starting at `first`; order[slot] is the primitive's index
+ * in the caller's list. Boxes are padded (see smallvcm_b200/csrc/svcm_bvh.h). At most
+ * 2 * numPrimitives - 1 nodes; SVCM_E_NOMEM if nodeCapacity is smaller (numNodes is set). */
+typedef struct SvcmBvhNode {
+    float   lo[3]; int32_t first;
+    float   hi[3]; int32_t count;
+} SvcmBvhNode;
+SVCM_API int svcm_bvh_build(const SvcmPrimitive *primitives, int32_t numPrimitives, SvcmBvhNode *nodes,
+                            int32_t nodeCapacity, int32_t *order, int32_t *numNodes);
 
 /* The image conversions of svcm_download_image on a caller-supplied accumulated image
  * [height][width][3] (host memory); out holds svcm_image_bytes(format, width, height). */

@@ -8,11 +8,11 @@ the sizes the library itself reports.
 import ctypes as C
 
 # --- limits / enums (include/svcm.h) -------------------------------------------------------
-MAX_PRIMITIVES, MAX_MATERIALS, MAX_LIGHTS = 64, 16, 8
 PRIM_TRIANGLE, PRIM_SPHERE = 0, 1
 LIGHT_AREA, LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_BACKGROUND = 0, 1, 2, 3
 # VertexCM::AlgorithmType numbering (reference src/vertexcm.hxx:182-204)
 IMAGE_BMP24, IMAGE_RGBE = 0, 1   # SVCM_IMAGE_*
+MAX_PRIMITIVES, MAX_PRIMITIVES_BVH, MAX_MATERIALS, MAX_LIGHTS = 64, 1 << 24, 16, 8
 ALG_LIGHT_TRACE, ALG_PPM, ALG_BPM, ALG_BPT, ALG_VCM, ALG_PATH_TRACE, ALG_EYE_LIGHT = 0, 1, 2, 3, 4, 5, 6
 ALGORITHMS = {"lt": ALG_LIGHT_TRACE, "ppm": ALG_PPM, "bpm": ALG_BPM, "bpt": ALG_BPT, "vcm": ALG_VCM,
               "pt": ALG_PATH_TRACE, "el": ALG_EYE_LIGHT}
@@ -47,6 +47,10 @@ class Camera(C.Structure):
 
 class SceneSphere(C.Structure):
     _fields_ = [("center", f32 * 3), ("radius", f32), ("invRadiusSqr", f32)]
+
+
+class BvhNode(C.Structure):
+    _fields_ = [("lo", f32 * 3), ("first", i32), ("hi", f32 * 3), ("count", i32)]
 
 
 class SceneDesc(C.Structure):
@@ -122,6 +126,7 @@ PROTOTYPES = {
     "svcm_image_header": (i32, [i32, i32, i32, VP, i32]),
     "svcm_download_image": (i32, [VP, i32, f32, VP, C.POINTER(i32)]),
     "svcm_save_image": (i32, [VP, C.c_char_p, f32]),
+    "svcm_bvh_build": (i32, [VP, i32, VP, i32, VP, C.POINTER(i32)]),
     "svcm_image_convert_batch": (i32, [VP, i32, i32, i32, i32, f32, i32, VP]),
     "svcm_get_stats": (i32, [VP, C.POINTER(Stats)]),
     "svcm_get_profile": (i32, [VP, C.POINTER(Profile)]),

@@ -76,6 +76,17 @@ thread_local std::string t_createError;
 
 } // namespace
 
+// Device copy of a scene too large for the constant bank: its primitives in hierarchy order and
+// the hierarchy itself (svcm_bvh.h). Empty for scenes of up to SVCM_MAX_PRIMITIVES primitives.
+struct SceneGeometry
+{
+    DevPrimG *prims;
+    BvhNode  *nodes;
+    SceneGeometry() : prims(NULL), nodes(NULL) {}
+    void release() { if(prims) cudaFree(prims); if(nodes) cudaFree(nodes); prims = NULL; nodes = NULL; }
+    ~SceneGeometry() { release(); }
+};
+
 // ------------------------------------------------------------------------------------------
 // the renderer handle
 // ------------------------------------------------------------------------------------------
@@ -83,6 +94,7 @@ struct svcm_renderer
 {
     SvcmParams params;
     DevScene   scene;
+    SceneGeometry geometry;         // primitives + hierarchy of a large scene (scene.bvh points here)
     int        device;
     cudaStream_t stream;
     bool useVC, useVM, ppm, lightTraceOnly, pathTrace, eyeLight;
@@ -163,11 +175,11 @@ int checkDevice(svcm_renderer *r, int device)
 int buildDevScene(svcm_renderer *r, const SvcmSceneDesc *d, DevScene &s)
 {
     if(!d) return fail(r, SVCM_E_INVALID, "scene is NULL");
-    if(d->numPrimitives < 0 || d->numPrimitives > SVCM_MAX_PRIMITIVES ||
+    if(d->numPrimitives < 0 || d->numPrimitives > SVCM_MAX_PRIMITIVES_BVH ||
        d->numMaterials < 1 || d->numMaterials > SVCM_MAX_MATERIALS ||
        d->numLights < 1 || d->numLights > SVCM_MAX_LIGHTS)
         return fail(r, SVCM_E_INVALID, "scene exceeds limits: %d primitives (max %d), %d materials (1..%d), %d lights (1..%d)",
-                    d->numPrimitives, SVCM_MAX_PRIMITIVES, d->numMaterials, SVCM_MAX_MATERIALS,
+                    d->numPrimitives, SVCM_MAX_PRIMITIVES_BVH, d->numMaterials, SVCM_MAX_MATERIALS,
                     d->numLights, SVCM_MAX_LIGHTS);
     if((d->numPrimitives && !d->primitives) || !d->materials || !d->lights || !d->materialToLight)
         return fail(r, SVCM_E_INVALID, "scene arrays must not be NULL");
@@ -198,6 +210,7 @@ int buildDevScene(svcm_renderer *r, const SvcmSceneDesc *d, DevScene &s)
             return fail(r, SVCM_E_INVALID, "primitive %d has unknown type %d", i, p.type);
         if(p.matID < 0 || p.matID >= d->numMaterials)
             return fail(r, SVCM_E_INVALID, "primitive %d has material %d out of range", i, p.matID);
+        if(d->numPrimitives > SVCM_MAX_PRIMITIVES) continue;      // goes to device memory: uploadGeometry
         memcpy(s.prims[i].v, p.v, sizeof(float) * 12);
         s.prims[i].type = p.type; s.prims[i].matID = p.matID;
     }
@@ -215,6 +228,34 @@ int buildDevScene(svcm_renderer *r, const SvcmSceneDesc *d, DevScene &s)
             for(int k = 0; k < 3; k++) o.intensity[k] = l.intensity[k] * l.scale;
         o.invArea = l.invArea;
     }
+    return SVCM_OK;
+}
+
+// For a scene buildDevScene accepted with more than SVCM_MAX_PRIMITIVES primitives: builds the
+// hierarchy on the host, copies it and the reordered primitives to the current device and points
+// `s` at them. No-op for smaller scenes.
+int uploadGeometry(svcm_renderer *r, const SvcmSceneDesc *d, DevScene &s, SceneGeometry &g)
+{
+    s.bvh = NULL; s.bvhPrims = NULL;
+    // test hook: SVCM_DEBUG_FORCE_BVH sends small scenes through the hierarchy too, so that the
+    // two paths can be compared on the reference's own scenes
+    if(d->numPrimitives <= SVCM_MAX_PRIMITIVES && !(getenv("SVCM_DEBUG_FORCE_BVH") && d->numPrimitives > 0)) return SVCM_OK;
+    std::vector<BvhNode> nodes; std::vector<int32_t> order;
+    if(bvhBuild(d->primitives, d->numPrimitives, nodes, order) != 0)
+        return fail(r, SVCM_E_INVALID, "scene geometry is not finite");
+    std::vector<DevPrimG> prims(order.size());
+    for(size_t slot = 0; slot < order.size(); slot++)
+    {
+        const SvcmPrimitive &p = d->primitives[order[slot]];
+        memcpy(prims[slot].v, p.v, sizeof(float) * 12);
+        prims[slot].type = p.type; prims[slot].matID = p.matID; prims[slot].orig = order[slot]; prims[slot].pad = 0;
+    }
+    g.release();
+    SVCM_CUDA(r, cudaMalloc((void**)&g.prims, sizeof(DevPrimG) * prims.size()));
+    SVCM_CUDA(r, cudaMalloc((void**)&g.nodes, sizeof(BvhNode) * nodes.size()));
+    SVCM_CUDA(r, cudaMemcpy(g.prims, prims.data(), sizeof(DevPrimG) * prims.size(), cudaMemcpyHostToDevice));
+    SVCM_CUDA(r, cudaMemcpy(g.nodes, nodes.data(), sizeof(BvhNode) * nodes.size(), cudaMemcpyHostToDevice));
+    s.bvh = g.nodes; s.bvhPrims = g.prims;
     return SVCM_OK;
 }
 
@@ -808,6 +849,7 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
         fail(r, e_ == cudaErrorMemoryAllocation ? SVCM_E_NOMEM : SVCM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
         SVCM_CREATE_FAIL(e_ == cudaErrorMemoryAllocation ? SVCM_E_NOMEM : SVCM_E_CUDA); } } while(0)
     SVCM_TRY(cudaSetDevice(r->device));
+    if((rc = uploadGeometry(r, scene, r->scene, r->geometry))) SVCM_CREATE_FAIL(rc);
     SVCM_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
     for(int i = 0; i < SVCM_NUM_USER_EVENTS; i++) SVCM_TRY(cudaEventCreate(&r->userEv[i]));
     for(int i = 0; i < 2; i++) if((rc = allocQueue(r, r->queue[i], r->localPaths))) SVCM_CREATE_FAIL(rc);
@@ -846,6 +888,7 @@ void svcm_destroy(svcm_renderer *r)
     devFree(r->shadow.r0); devFree(r->shadow.r1); devFree(r->shadow.r2); devFree(r->shadow.counts);
     freeVerts(r); freeQueries(r); freeGridSorted(r); freeGather(r);
     devFree(r->pathVertCount); devFree(r->counters); devFree(r->accum); devFree(r->image8);
+    r->geometry.release();
     devFree(r->grid.cellCount); devFree(r->grid.blockSums); devFree(r->grid.bboxBits);
     devFree(r->qsort.cellCount); devFree(r->qsort.blockSums);
     devFree(r->bboxInit); devFree(r->devCounts64);
@@ -1183,12 +1226,15 @@ struct Scratch
     }
 };
 
-int batchPrologue(const SvcmSceneDesc *scene, int device, DevScene &sc)
+// `geo` owns the device copy of a large scene's geometry for the duration of the batch call;
+// NULL for stages that never trace a ray (BSDF, merge)
+int batchPrologue(const SvcmSceneDesc *scene, int device, DevScene &sc, SceneGeometry *geo)
 {
     int rc = checkDevice(NULL, device);
     if(rc) return rc;
     if((rc = buildDevScene(NULL, scene, sc))) return rc;
     if(cudaSetDevice(device) != cudaSuccess) return fail(NULL, SVCM_E_CUDA, "cudaSetDevice(%d) failed", device);
+    if(geo) return uploadGeometry(NULL, scene, sc, *geo);
     return SVCM_OK;
 }
 
@@ -1299,7 +1345,7 @@ int svcm_hashgrid_query(svcm_hashgrid *g, const SvcmSceneDesc *scene, const Svcm
         if(queries[i].matID < 0 || queries[i].matID >= scene->numMaterials || queries[i].pathLength > 0xFFFFu)
             return fail(NULL, SVCM_E_INVALID, "query %lld: material or path length out of range", (long long)i);
     DevScene sc;
-    int rc = batchPrologue(scene, g->device, sc);
+    int rc = batchPrologue(scene, g->device, sc, NULL);
     if(rc) return rc;
     if(count == 0) return SVCM_OK;
 
@@ -1337,7 +1383,7 @@ int svcm_intersect_batch(const SvcmSceneDesc *scene, const float *rays, int64_t 
 {
     if(count < 0 || (count && (!rays || !hit || !dist || !normal || !matID || !lightID)))
         return fail(NULL, SVCM_E_INVALID, "bad arguments");
-    DevScene sc; int rc = batchPrologue(scene, device, sc); if(rc) return rc;
+    SceneGeometry geo; DevScene sc; int rc = batchPrologue(scene, device, sc, &geo); if(rc) return rc;
     if(count == 0) return SVCM_OK;
     Scratch s; cudaError_t e = cudaSuccess; const size_t n = size_t(count);
     float *dRays = s.alloc<float>(n * 6, e); int32_t *dHit = s.alloc<int32_t>(n, e); float *dDist = s.alloc<float>(n, e);
@@ -1358,7 +1404,7 @@ int svcm_intersect_batch(const SvcmSceneDesc *scene, const float *rays, int64_t 
 int svcm_occluded_batch(const SvcmSceneDesc *scene, const float *segments, int64_t count, int32_t device, int32_t *occluded)
 {
     if(count < 0 || (count && (!segments || !occluded))) return fail(NULL, SVCM_E_INVALID, "bad arguments");
-    DevScene sc; int rc = batchPrologue(scene, device, sc); if(rc) return rc;
+    SceneGeometry geo; DevScene sc; int rc = batchPrologue(scene, device, sc, &geo); if(rc) return rc;
     if(count == 0) return SVCM_OK;
     Scratch s; cudaError_t e = cudaSuccess; const size_t n = size_t(count);
     float *dSeg = s.alloc<float>(n * 7, e); int32_t *dOcc = s.alloc<int32_t>(n, e);
@@ -1385,7 +1431,7 @@ int svcm_bsdf_evaluate_batch(const SvcmSceneDesc *scene, const float *in, int64_
                              int32_t device, float *out)
 {
     if(count < 0 || !scene || (count && (!in || !out))) return fail(NULL, SVCM_E_INVALID, "bad arguments");
-    DevScene sc; int rc = batchPrologue(scene, device, sc); if(rc) return rc;
+    DevScene sc; int rc = batchPrologue(scene, device, sc, NULL); if(rc) return rc;
     if((rc = bsdfBatchCheck(scene, in, count))) return rc;
     if(count == 0) return SVCM_OK;
     Scratch s; cudaError_t e = cudaSuccess; const size_t n = size_t(count);
@@ -1403,7 +1449,7 @@ int svcm_bsdf_sample_batch(const SvcmSceneDesc *scene, const float *in, int64_t 
                            int32_t device, float *out, uint32_t *events)
 {
     if(count < 0 || !scene || (count && (!in || !out || !events))) return fail(NULL, SVCM_E_INVALID, "bad arguments");
-    DevScene sc; int rc = batchPrologue(scene, device, sc); if(rc) return rc;
+    DevScene sc; int rc = batchPrologue(scene, device, sc, NULL); if(rc) return rc;
     if((rc = bsdfBatchCheck(scene, in, count))) return rc;
     if(count == 0) return SVCM_OK;
     Scratch s; cudaError_t e = cudaSuccess; const size_t n = size_t(count);

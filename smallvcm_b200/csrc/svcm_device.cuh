@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "svcm.h"
+#include "svcm_bvh.h"
 
 #define SVCM_HD __host__ __device__ __forceinline__
 #define SVCM_D  __device__ __forceinline__
@@ -127,6 +128,9 @@ struct PathRng
 // the scene as the kernels see it: one POD block passed as a __grid_constant__ parameter
 // ---------------------------------------------------------------------------------------
 struct DevPrim  { float v[12]; int32_t type; int32_t matID; };
+// a primitive of a scene too large for the constant bank: one 64-byte record in global memory,
+// in the hierarchy's slot order; `orig` = its index in the caller's list (svcm_bvh.h)
+struct alignas(16) DevPrimG { float v[12]; int32_t type, matID, orig, pad; };
 struct DevLight
 {
     int32_t type;
@@ -147,22 +151,25 @@ struct DevScene
     SvcmMaterial mats[SVCM_MAX_MATERIALS];
     DevLight lights[SVCM_MAX_LIGHTS];
     DevPrim  prims[SVCM_MAX_PRIMITIVES];
+    // numPrims > SVCM_MAX_PRIMITIVES: the list lives in global memory under a hierarchy instead
+    const BvhNode  *bvh;         // NULL for the constant-bank list above
+    const DevPrimG *bvhPrims;
 };
 
 struct Hit { float dist; int32_t matID; int32_t prim; f3 normal; };
 
 // Triangle::Intersect, reference src/geometry.hxx:125-156
-SVCM_D bool hitTriangle(const DevPrim &t, f3 org, f3 dir, float tmax, float &oDist)
+SVCM_D bool hitTriangle(const float *v, f3 org, f3 dir, float tmax, float &oDist)
 {
-    const f3 ao = ld3(t.v) - org;
-    const f3 bo = ld3(t.v + 3) - org;
-    const f3 co = ld3(t.v + 6) - org;
+    const f3 ao = ld3(v) - org;
+    const f3 bo = ld3(v + 3) - org;
+    const f3 co = ld3(v + 6) - org;
     const float v0d = dot(cross(co, bo), dir);
     const float v1d = dot(cross(bo, ao), dir);
     const float v2d = dot(cross(ao, co), dir);
     if(((v0d < 0.f) && (v1d < 0.f) && (v2d < 0.f)) || ((v0d >= 0.f) && (v1d >= 0.f) && (v2d >= 0.f)))
     {
-        const f3 n = ld3(t.v + 9);
+        const f3 n = ld3(v + 9);
         const float distance = dot(n, ao) / dot(n, dir);
         if((distance > 0.f) && (distance < tmax)) { oDist = distance; return true; }
     }
@@ -181,10 +188,10 @@ SVCM_D float dotUnfused(f3 a, f3 b)
 // part is evaluated unfused, in the reference's order: B*B - 4*A*C cancels catastrophically
 // for grazing rays, so a contracted evaluation would move those hits by far more than an ulp
 // (there are at most two spheres per scene, the extra instructions are noise).
-SVCM_D bool hitSphere(const DevPrim &s, f3 org, f3 dir, float tmax, float &oDist)
+SVCM_D bool hitSphere(const float *v, f3 org, f3 dir, float tmax, float &oDist)
 {
-    const f3 to = org - ld3(s.v);
-    const float radius = s.v[3];
+    const f3 to = org - ld3(v);
+    const float radius = v[3];
     const float A = dotUnfused(dir, dir);
     const float B = __fmul_rn(2.f, dotUnfused(dir, to));
     const float C = __fsub_rn(dotUnfused(to, to), __fmul_rn(radius, radius));
@@ -200,19 +207,60 @@ SVCM_D bool hitSphere(const DevPrim &s, f3 org, f3 dir, float tmax, float &oDist
     return false;
 }
 
+// The same two queries for a scene under a hierarchy (svcm_bvh.h).
+SVCM_D bool bvhSceneIntersect(const BvhNode *nodes, const DevPrimG *prims, f3 org, f3 dir, Hit &hit)
+{
+    float best = 1e36f;
+    int32_t bestOrig = 0x7FFFFFFF, bestSlot = -1;
+    bvhClosest(nodes, org.x, org.y, org.z, dir.x, dir.y, dir.z, best, bestOrig, bestSlot,
+               [&](int32_t slot, float &d, int32_t &orig) -> bool
+               {
+                   const DevPrimG p = prims[slot];
+                   orig = p.orig;
+                   return (p.type == SVCM_PRIM_TRIANGLE) ? hitTriangle(p.v, org, dir, 1e36f, d)
+                                                         : hitSphere(p.v, org, dir, 1e36f, d);
+               });
+    if(bestSlot < 0) return false;
+    const DevPrimG p = prims[bestSlot];
+    hit.dist = best; hit.prim = bestOrig; hit.matID = p.matID;
+    if(p.type == SVCM_PRIM_TRIANGLE)
+        hit.normal = ld3(p.v + 9);
+    else
+    {
+        const f3 n = mulAddUnfused(org - ld3(p.v), dir, best);
+        hit.normal = n / sqrtf(dotUnfused(n, n));
+    }
+    return true;
+}
+SVCM_D bool bvhSceneOccluded(const BvhNode *nodes, const DevPrimG *prims, f3 org, f3 dir, float tmax)
+{
+    return bvhAny(nodes, org.x, org.y, org.z, dir.x, dir.y, dir.z, tmax,
+                  [&](int32_t slot) -> bool
+                  {
+                      const DevPrimG p = prims[slot];
+                      float d;
+                      return (p.type == SVCM_PRIM_TRIANGLE) ? hitTriangle(p.v, org, dir, tmax, d)
+                                                            : hitSphere(p.v, org, dir, tmax, d);
+                  });
+}
+
 // Scene::Intersect -> GeometryList::Intersect, reference src/scene.hxx:53-70 and
 // src/geometry.hxx:65-78: closest hit over the whole list, list order kept (strict <).
 // The primitive index is warp-uniform, so every load below is a constant-bank broadcast.
+// kBvh is a compile-time property of the kernel (the launchers pick the instantiation from
+// sc.bvh): kernels of small scenes carry no trace of the hierarchy code.
+template<bool kBvh>
 SVCM_D bool sceneIntersect(const DevScene &sc, f3 org, f3 dir, Hit &hit)
 {
+    if(kBvh) return bvhSceneIntersect(sc.bvh, sc.bvhPrims, org, dir, hit);
     float best = 1e36f;
     int prim = -1;
     for(int i = 0; i < sc.numPrims; i++)
     {
         float d;
         const bool h = (sc.prims[i].type == SVCM_PRIM_TRIANGLE)
-            ? hitTriangle(sc.prims[i], org, dir, best, d)
-            : hitSphere(sc.prims[i], org, dir, best, d);
+            ? hitTriangle(sc.prims[i].v, org, dir, best, d)
+            : hitSphere(sc.prims[i].v, org, dir, best, d);
         if(h) { best = d; prim = i; }
     }
     if(prim < 0) return false;
@@ -232,16 +280,18 @@ SVCM_D bool sceneIntersect(const DevScene &sc, f3 org, f3 dir, Hit &hit)
 
 // Scene::Occluded -> GeometryList::IntersectP, reference src/scene.hxx:72-85,
 // src/geometry.hxx:80-91: any hit in (0, tMax - 2 EPS_RAY) from point + dir*EPS_RAY
+template<bool kBvh>
 SVCM_D bool sceneOccluded(const DevScene &sc, f3 point, f3 dir, float tMax)
 {
     const f3 org = point + dir * SVCM_EPS_RAY;
     const float tmax = tMax - 2.f * SVCM_EPS_RAY;
+    if(kBvh) return bvhSceneOccluded(sc.bvh, sc.bvhPrims, org, dir, tmax);
     for(int i = 0; i < sc.numPrims; i++)
     {
         float d;
         const bool h = (sc.prims[i].type == SVCM_PRIM_TRIANGLE)
-            ? hitTriangle(sc.prims[i], org, dir, tmax, d)
-            : hitSphere(sc.prims[i], org, dir, tmax, d);
+            ? hitTriangle(sc.prims[i].v, org, dir, tmax, d)
+            : hitSphere(sc.prims[i].v, org, dir, tmax, d);
         if(h) return true;
     }
     return false;

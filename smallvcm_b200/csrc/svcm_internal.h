@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <vector>
 #include "svcm.h"
 #include "svcm_device.cuh"
 
@@ -213,6 +214,9 @@ void launchBsdfEvaluateBatch(const DevScene &sc, const float *in, int64_t count,
                              float *out, cudaStream_t stream);
 void launchBsdfSampleBatch(const DevScene &sc, const float *in, int64_t count, int fixIsLight,
                            float *out, uint32_t *events, cudaStream_t stream);
+// svcm_bvh.cpp: hierarchy over a primitive list; order[slot] = original index. 0 on success.
+int bvhBuild(const SvcmPrimitive *prims, int32_t count, std::vector<BvhNode> &nodes, std::vector<int32_t> &order);
+
 // SaveBMP / SaveHDR pixel payloads of the accumulated image (src/framebuffer.hxx:170-251)
 void launchImageConvert(const float *accum, int width, int height, int iterations, int format, float gamma,
                         uint8_t *out, cudaStream_t stream);

@@ -81,6 +81,7 @@ SVCM_D f3 xyz(float4 a) { return mk3(a.x, a.y, a.z); }
 // Queue one visibility test: "add `contrib` to `pixel` unless point -> point + dir*tMax is
 // blocked" (Scene::Occluded, reference src/scene.hxx:72-85). If the queue is full the ray is
 // traced on the spot — slower, never wrong.
+template<bool kBvh>
 SVCM_D void emitShadowRay(const DevScene &sc, const ShadowQueue &q, uint32_t which, float *accum,
                           f3 point, f3 dir, float tMax, uint32_t pixel, f3 contrib)
 {
@@ -91,7 +92,7 @@ SVCM_D void emitShadowRay(const DevScene &sc, const ShadowQueue &q, uint32_t whi
         q.r1[slot] = mk4(dir, __uint_as_float(pixel));
         q.r2[slot] = mk4(contrib, 0.f);
     }
-    else if(!sceneOccluded(sc, point, dir, tMax)) addPixel(accum, pixel, contrib);
+    else if(!sceneOccluded<kBvh>(sc, point, dir, tMax)) addPixel(accum, pixel, contrib);
 }
 
 // local (per-rank) path index <-> global path index: rows are dealt round-robin to ranks
@@ -225,6 +226,7 @@ SVCM_D void generateLightSample(const DevScene &sc, const IterConst &ic, SubPath
 
 // ConnectToCamera, reference src/vertexcm.hxx:862-933: splat the light vertex onto the
 // image through the pinhole; float atomics because the target pixel is arbitrary.
+template<bool kBvh>
 SVCM_D void connectToCamera(const DevScene &sc, const IterConst &ic, const SubPath &s, f3 hitPoint,
                             const Bsdf &bsdf, const TraceArgs &a)
 {
@@ -261,10 +263,11 @@ SVCM_D void connectToCamera(const DevScene &sc, const IterConst &ic, const SubPa
 
     // Framebuffer::AddColor target, reference src/framebuffer.hxx:43-57; visibility deferred
     const uint32_t pixel = uint32_t(int(raster.x)) + uint32_t(int(raster.y)) * uint32_t(ic.resX);
-    emitShadowRay(sc, a.shadow, 0u, a.accum, hitPoint, dirToCamera, distance, pixel, contrib);
+    emitShadowRay<kBvh>(sc, a.shadow, 0u, a.accum, hitPoint, dirToCamera, distance, pixel, contrib);
 }
 
 // One bounce of every live light sub-path: reference src/vertexcm.hxx:328-393 (loop body)
+template<bool kBvh>
 __global__ void __launch_bounds__(SVCM_BLOCK)
 k_lightBounce(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
               const __grid_constant__ TraceArgs a, const uint32_t bounce)
@@ -297,7 +300,7 @@ k_lightBounce(const __grid_constant__ DevScene sc, const __grid_constant__ IterC
             // origin offset instead of tmin; dist extended after the hit point is known
             const f3 org = mulAddUnfused(s.origin, s.direction, SVCM_EPS_RAY);
             nRays++;
-            alive = sceneIntersect(sc, org, s.direction, hit);
+            alive = sceneIntersect<kBvh>(sc, org, s.direction, hit);
             if(alive)
             {
                 hitPoint = mulAddUnfused(org, s.direction, hit.dist);
@@ -338,7 +341,7 @@ k_lightBounce(const __grid_constant__ DevScene sc, const __grid_constant__ IterC
         if(alive)
         {
             if(!bsdf.isDelta() && (ic.useVC || ic.lightTraceOnly) && (s.length + 1u >= ic.minLen))
-                connectToCamera(sc, ic, s, hitPoint, bsdf, a);
+                connectToCamera<kBvh>(sc, ic, s, hitPoint, bsdf, a);
 
             // terminate if the path would become too long after scattering
             if(s.length + 2u > ic.maxLen) alive = false;
@@ -477,6 +480,7 @@ SVCM_D f3 connectVertices(const DevScene &sc, const IterConst &ic, f3 lvPos, con
 // Merging is deferred: a non-delta vertex inside the light-vertex bbox appends a query
 // record that k_merge resolves after the whole camera pass (merging draws no random
 // numbers and does not steer the walk, so the split changes nothing but summation order).
+template<bool kBvh>
 __global__ void __launch_bounds__(SVCM_BLOCK)
 k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
                const __grid_constant__ TraceArgs a, const uint32_t bounce)
@@ -516,7 +520,7 @@ k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ Iter
         {
             const f3 org = mulAddUnfused(s.origin, s.direction, SVCM_EPS_RAY);
             nRays++;
-            if(!sceneIntersect(sc, org, s.direction, hit))
+            if(!sceneIntersect<kBvh>(sc, org, s.direction, hit))
             {
                 // environment: BEFORE the MIS update (src/vertexcm.hxx:434-447)
                 if(sc.background >= 0 && s.length >= ic.minLen)
@@ -565,7 +569,7 @@ k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ Iter
                 {
                     f3 dir; float dist;
                     const f3 c = s.throughput * directIllumination(sc, ic, s, hitPoint, bsdf, dir, dist);
-                    if(!iszero(c)) emitShadowRay(sc, a.shadow, 1u, a.accum, hitPoint, dir, dist, s.extra, c);
+                    if(!iszero(c)) emitShadowRay<kBvh>(sc, a.shadow, 1u, a.accum, hitPoint, dir, dist, s.extra, c);
                 }
                 lpath = globalToLocalPath(ic, s.path);
                 // the k-th stored light vertex has path length >= k+1, so only the first
@@ -642,6 +646,7 @@ k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ Iter
 // per (camera vertex, light vertex) pair: both BSDFs are rebuilt from the stored records, the
 // connection is evaluated with its MIS weight and, if it carries energy, its visibility
 // segment is queued for k_shadow.
+template<bool kBvh>
 __global__ void __launch_bounds__(SVCM_BLOCK)
 k_connect(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
           const __grid_constant__ TraceArgs a)
@@ -681,13 +686,14 @@ k_connect(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst
         f3 dir; float dist;
         const f3 c = (xyz(q3) * xyz(tv)) *
             connectVertices(sc, ic, xyz(pl), lvBsdf, tv.w, nv4.w, camBsdf, xyz(q0), s, dir, dist);
-        if(!iszero(c)) emitShadowRay(sc, a.shadow, 1u, a.accum, xyz(q0), dir, dist, __float_as_uint(q0.w), c);
+        if(!iszero(c)) emitShadowRay<kBvh>(sc, a.shadow, 1u, a.accum, xyz(q0), dir, dist, __float_as_uint(q0.w), c);
     }
 }
 
 // The deferred Scene::Occluded tests of one pass (reference src/scene.hxx:72-85), one lane per
 // queued segment, then Framebuffer::AddColor for the unoccluded ones. Every lane runs the same
 // primitive loop: this is where the bounce kernels' divergent any-hit loops went.
+template<bool kBvh>
 __global__ void __launch_bounds__(SVCM_BLOCK)
 k_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ TraceArgs a, const uint32_t bounce)
 {
@@ -696,7 +702,7 @@ k_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ TraceArgs 
     for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
     {
         const float4 r0 = a.shadow.r0[i], r1 = a.shadow.r1[i];
-        if(!sceneOccluded(sc, xyz(r0), xyz(r1), r0.w))
+        if(!sceneOccluded<kBvh>(sc, xyz(r0), xyz(r1), r0.w))
             addPixel(a.accum, __float_as_uint(r1.w), xyz(a.shadow.r2[i]));
     }
     if(blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.counters + CNT_SHADOW_RAYS, (unsigned long long)queued);
@@ -712,6 +718,7 @@ k_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ TraceArgs 
 // roulette. Sub-path slots: s0 = ray origin (already offset) | lastPdfW, s1 = direction | -,
 // s2 = pathWeight | -, s3 = pixel index | length + flags (PATH_FLAG_SPECULAR = lastSpecular) |
 // rng draw | target pixel.
+template<bool kBvh>
 __global__ void __launch_bounds__(SVCM_BLOCK)
 k_pathTraceBounce(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
                   const __grid_constant__ TraceArgs a, const uint32_t bounce)
@@ -754,7 +761,7 @@ k_pathTraceBounce(const __grid_constant__ DevScene sc, const __grid_constant__ I
         {
             Hit hit;
             nRays++;
-            if(!sceneIntersect(sc, s.origin, s.direction, hit))
+            if(!sceneIntersect<kBvh>(sc, s.origin, s.direction, hit))
             {
                 // environment (:72-93)
                 alive = false;
@@ -830,7 +837,7 @@ k_pathTraceBounce(const __grid_constant__ DevScene sc, const __grid_constant__ I
                             const f3 contrib = s.throughput *
                                 ((weight * cosThetaOut / (lightPickProb * directPdfW)) * (radiance * factor));
                             if(!iszero(contrib))
-                                emitShadowRay(sc, a.shadow, 1u, a.accum, hitPoint, dirToLight, distance, s.extra, contrib);
+                                emitShadowRay<kBvh>(sc, a.shadow, 1u, a.accum, hitPoint, dirToLight, distance, s.extra, contrib);
                         }
                     }
                 }
@@ -875,6 +882,7 @@ k_pathTraceBounce(const __grid_constant__ DevScene sc, const __grid_constant__ I
 
 // EyeLight::RunIteration, reference src/eyelight.hxx:47-78: N.L preview, back faces in red; the
 // iteration with index 1 samples pixel centres
+template<bool kBvh>
 __global__ void __launch_bounds__(SVCM_BLOCK)
 k_eyeLight(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
            const __grid_constant__ TraceArgs a, const uint32_t iteration)
@@ -893,7 +901,7 @@ k_eyeLight(const __grid_constant__ DevScene sc, const __grid_constant__ IterCons
         const f3 dir = normalize(transformPoint(sc.rasterToWorld, mk3(sx, sy, 0.f)) - camPos);
         Hit hit;
         nRays++;
-        if(sceneIntersect(sc, camPos, dir, hit))
+        if(sceneIntersect<kBvh>(sc, camPos, dir, hit))
         {
             const float dotLN = dot(hit.normal, -dir);
             const uint32_t pixel = uint32_t(int(sx)) + uint32_t(int(sy)) * uint32_t(ic.resX);
@@ -1515,13 +1523,14 @@ k_mergeLane(const __grid_constant__ DevScene sc, const __grid_constant__ IterCon
 // ------------------------------------------------------------------------------------------
 // kernel-level batch kernels (parity tests call the same device functions as the path)
 // ------------------------------------------------------------------------------------------
+template<bool kBvh>
 __global__ void k_intersectBatch(const __grid_constant__ DevScene sc, const float *rays, int64_t count,
                                  int32_t *hitOut, float *dist, float *normal, int32_t *matID, int32_t *lightID)
 {
     for(int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x)
     {
         Hit hit;
-        const bool found = sceneIntersect(sc, ld3(rays + 6 * i), ld3(rays + 6 * i + 3), hit);
+        const bool found = sceneIntersect<kBvh>(sc, ld3(rays + 6 * i), ld3(rays + 6 * i + 3), hit);
         hitOut[i] = found ? hit.prim : -1;
         dist[i] = found ? hit.dist : 1e36f;
         normal[3 * i + 0] = found ? hit.normal.x : 0.f;
@@ -1532,10 +1541,11 @@ __global__ void k_intersectBatch(const __grid_constant__ DevScene sc, const floa
     }
 }
 
+template<bool kBvh>
 __global__ void k_occludedBatch(const __grid_constant__ DevScene sc, const float *seg, int64_t count, int32_t *occ)
 {
     for(int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x)
-        occ[i] = sceneOccluded(sc, ld3(seg + 7 * i), ld3(seg + 7 * i + 3), seg[7 * i + 6]) ? 1 : 0;
+        occ[i] = sceneOccluded<kBvh>(sc, ld3(seg + 7 * i), ld3(seg + 7 * i + 3), seg[7 * i + 6]) ? 1 : 0;
 }
 
 __global__ void k_bsdfEvaluateBatch(const __grid_constant__ DevScene sc, const float *in, int64_t count, float *out)
@@ -1642,25 +1652,29 @@ static uint32_t gridFor(uint64_t items, int perBlock, int blocksPerSM)
 void launchLightBounce(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t bounce,
                        uint32_t maxItems, cudaStream_t stream)
 {
-    k_lightBounce<<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
+    if(sc.bvh) k_lightBounce<true><<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
+    else       k_lightBounce<false><<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
 }
 
 void launchPathTraceBounce(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t bounce,
                            uint32_t maxItems, cudaStream_t stream)
 {
-    k_pathTraceBounce<<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
+    if(sc.bvh) k_pathTraceBounce<true><<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
+    else       k_pathTraceBounce<false><<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
 }
 
 void launchEyeLight(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t iteration,
                     cudaStream_t stream)
 {
-    k_eyeLight<<<gridFor(ic.localPaths, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, iteration);
+    if(sc.bvh) k_eyeLight<true><<<gridFor(ic.localPaths, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, iteration);
+    else       k_eyeLight<false><<<gridFor(ic.localPaths, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, iteration);
 }
 
 void launchCameraBounce(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t bounce,
                         uint32_t maxItems, cudaStream_t stream)
 {
-    k_cameraBounce<<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
+    if(sc.bvh) k_cameraBounce<true><<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
+    else       k_cameraBounce<false><<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
 }
 
 int launchQuerySort(const IterConst &ic, const QueryStore &queries, const unsigned long long *vertexCount,
@@ -1681,14 +1695,16 @@ int launchQuerySort(const IterConst &ic, const QueryStore &queries, const unsign
 
 void launchConnect(const DevScene &sc, const IterConst &ic, const TraceArgs &args, cudaStream_t stream)
 {
-    k_connect<<<gridFor(args.pairs.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args);
+    if(sc.bvh) k_connect<true><<<gridFor(args.pairs.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args);
+    else       k_connect<false><<<gridFor(args.pairs.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args);
 }
 
 void launchShadow(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t which,
                   cudaStream_t stream)
 {
     (void)ic;
-    k_shadow<<<gridFor(args.shadow.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, args, which);
+    if(sc.bvh) k_shadow<true><<<gridFor(args.shadow.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, args, which);
+    else       k_shadow<false><<<gridFor(args.shadow.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, args, which);
 }
 
 int launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers &grid, cudaStream_t stream)
@@ -1750,12 +1766,14 @@ void launchIntersectBatch(const DevScene &sc, const float *rays, int64_t count, 
                           float *normal, int32_t *matID, int32_t *lightID, cudaStream_t stream)
 {
     if(count <= 0) return;
-    k_intersectBatch<<<gridFor(count, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, rays, count, hit, dist, normal, matID, lightID);
+    if(sc.bvh) k_intersectBatch<true><<<gridFor(count, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, rays, count, hit, dist, normal, matID, lightID);
+    else       k_intersectBatch<false><<<gridFor(count, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, rays, count, hit, dist, normal, matID, lightID);
 }
 void launchOccludedBatch(const DevScene &sc, const float *segments, int64_t count, int32_t *occluded, cudaStream_t stream)
 {
     if(count <= 0) return;
-    k_occludedBatch<<<gridFor(count, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, segments, count, occluded);
+    if(sc.bvh) k_occludedBatch<true><<<gridFor(count, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, segments, count, occluded);
+    else       k_occludedBatch<false><<<gridFor(count, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, segments, count, occluded);
 }
 void launchBsdfEvaluateBatch(const DevScene &sc, const float *in, int64_t count, int fixIsLight, float *out,
                              cudaStream_t stream)

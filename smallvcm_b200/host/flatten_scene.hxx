@@ -151,12 +151,12 @@ inline bool FlattenScene(const Scene &aScene, FlatScene &oFlat)
         oFlat.lights.push_back(light);
     }
 
-    if(oFlat.primitives.size() > SVCM_MAX_PRIMITIVES ||
+    if(oFlat.primitives.size() > SVCM_MAX_PRIMITIVES_BVH ||
        oFlat.materials.size()  > SVCM_MAX_MATERIALS  ||
        oFlat.lights.size()     > SVCM_MAX_LIGHTS)
     {
         printf("svcm: scene exceeds the compiled-in limits (%d primitives, %d materials, %d lights)\n",
-            SVCM_MAX_PRIMITIVES, SVCM_MAX_MATERIALS, SVCM_MAX_LIGHTS);
+            SVCM_MAX_PRIMITIVES_BVH, SVCM_MAX_MATERIALS, SVCM_MAX_LIGHTS);
         return false;
     }
 

@@ -91,6 +91,48 @@ class Scene:
         _check(lib.svcm_scene_cornell_box(mask, width, height, C.byref(handle), C.byref(pdesc)))
         return cls(pdesc.contents, owner=handle, free=lib.svcm_scene_free)
 
+    def with_triangles(self, vertices, mat_ids):
+        """A new scene: this one's camera, materials, lights and primitives plus the triangles
+        `vertices` [n, 3, 3] (float32, counter-clockwise like src/geometry.hxx:99-107) with
+        materials `mat_ids` [n], appended to the primitive list. The normal is the reference's
+        Normalize(Cross(p1 - p0, p2 - p0)) evaluated in float32. The scene sphere is kept, so the
+        triangles must lie inside the existing geometry's bounds. More than 64 primitives make
+        svcm_create build a hierarchy (include/svcm.h, SVCM_MAX_PRIMITIVES)."""
+        v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3, 3)
+        mats = np.ascontiguousarray(mat_ids, np.int32).reshape(-1)
+        assert len(v) == len(mats)
+        e1, e2 = v[:, 1] - v[:, 0], v[:, 2] - v[:, 0]
+        n = np.stack([e1[:, 1] * e2[:, 2] - e1[:, 2] * e2[:, 1], e1[:, 2] * e2[:, 0] - e1[:, 0] * e2[:, 2],
+                      e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0]], 1).astype(np.float32)
+        length = np.sqrt((n[:, 0] * n[:, 0] + n[:, 1] * n[:, 1] + n[:, 2] * n[:, 2]).astype(np.float32)).astype(np.float32)
+        n = (n / length[:, None]).astype(np.float32)
+        old = self.desc.numPrimitives
+        prims = (abi.Primitive * (old + len(v)))()
+        for i in range(old):
+            prims[i] = self.desc.primitives[i]
+        raw = np.frombuffer(prims, np.uint8).reshape(old + len(v), C.sizeof(abi.Primitive))
+        rec = np.zeros((len(v), 14), np.float32)
+        rec[:, 0] = np.full(len(v), abi.PRIM_TRIANGLE, np.int32).view(np.float32)
+        rec[:, 1] = mats.view(np.float32)
+        rec[:, 2:11] = v.reshape(-1, 9)
+        rec[:, 11:14] = n
+        raw[old:] = rec.view(np.uint8).reshape(len(v), -1)
+        desc = abi.SceneDesc()
+        C.memmove(C.byref(desc), C.byref(self.desc), C.sizeof(abi.SceneDesc))
+        desc.primitives = C.cast(prims, C.POINTER(abi.Primitive))
+        desc.numPrimitives = old + len(v)
+        return Scene(desc, owner=(self, prims), free=None)
+
+    def bvh(self):
+        """(nodes structured array, order) of the hierarchy svcm_create would build (svcm_bvh_build)."""
+        n = self.desc.numPrimitives
+        nodes = (abi.BvhNode * (2 * n))()
+        order = np.zeros(n, np.int32)
+        count = C.c_int32()
+        _check(load_library().svcm_bvh_build(self.desc.primitives, n, nodes, 2 * n, _ptr(order), C.byref(count)))
+        dt = np.dtype([("lo", np.float32, 3), ("first", np.int32), ("hi", np.float32, 3), ("count", np.int32)])
+        return np.frombuffer(nodes, dt)[:count.value].copy(), order
+
     @property
     def width(self):
         return int(self.desc.camera.resolution[0])
