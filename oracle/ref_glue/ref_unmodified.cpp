@@ -86,6 +86,67 @@ REF_API double ref_render(int sceneId, int algorithm, int width, int height,
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// ref_render for a scene that is NOT one of the hard-coded boxes: g_SceneConfigs[sceneId] with
+// `numExtra` more triangles appended to the GeometryList (vertices [n][3][3], material ids [n]),
+// built by the reference's own Triangle constructor (src/geometry.hxx:112-123). The scene sphere
+// is rebuilt by the reference (src/scene.hxx BuildSceneSphere) over the enlarged list. Optionally
+// returns the flattened scene's primitives (product glue, flatten_scene.hxx) so that the caller
+// can check its own way of building the same list, normals included.
+REF_API double ref_render_extra(int sceneId, int algorithm, int width, int height, int iterations, int threads,
+                                int baseSeed, unsigned maxPathLength, unsigned minPathLength, float radiusFactor,
+                                float radiusAlpha, const float *extraVertices, const int *extraMaterials,
+                                int numExtra, float *outRgb, SvcmPrimitive *outPrims, SvcmSceneSphere *outSphere)
+{
+    if(sceneId < 0 || sceneId >= SizeOfArray(g_SceneConfigs)) return -1.0;
+    if(algorithm < 0 || algorithm >= (int)Config::kAlgorithmMax) return -1.0;
+
+    Scene *scene = new Scene;
+    scene->LoadCornellBox(Vec2i(width, height), g_SceneConfigs[sceneId]);
+    GeometryList *list = dynamic_cast<GeometryList*>(scene->mGeometry);
+    if(!list) { delete scene; return -1.0; }
+    for(int i = 0; i < numExtra; i++)
+    {
+        const float *v = extraVertices + 9 * i;
+        if(extraMaterials[i] < 0 || extraMaterials[i] >= scene->GetMaterialCount()) { delete scene; return -1.0; }
+        list->mGeometry.push_back(new Triangle(Vec3f(v[0], v[1], v[2]), Vec3f(v[3], v[4], v[5]),
+                                               Vec3f(v[6], v[7], v[8]), extraMaterials[i]));
+    }
+    scene->BuildSceneSphere();
+
+    if(outPrims || outSphere)
+    {
+        svcm_host::FlatScene flat;
+        if(!svcm_host::FlattenScene(*scene, flat)) { delete scene; return -1.0; }
+        if(outPrims) memcpy(outPrims, flat.primitives.data(), sizeof(SvcmPrimitive) * flat.primitives.size());
+        if(outSphere) *outSphere = flat.desc.sceneSphere;
+    }
+
+    Framebuffer fb;
+    Config config;
+    config.mScene         = scene;
+    config.mAlgorithm     = Config::Algorithm(algorithm);
+    config.mIterations    = iterations;
+    config.mMaxTime       = -1.f;
+    config.mRadiusFactor  = radiusFactor;
+    config.mRadiusAlpha   = radiusAlpha;
+    config.mFramebuffer   = &fb;
+    config.mNumThreads    = threads > 0 ? threads : std::max(1, omp_get_num_procs());
+    config.mBaseSeed      = baseSeed;
+    config.mMaxPathLength = maxPathLength;
+    config.mMinPathLength = minPathLength;
+    config.mOutputName    = "";
+    config.mResolution    = Vec2i(width, height);
+    config.mFullReport    = false;
+
+    const auto t0 = std::chrono::steady_clock::now();
+    if(iterations > 0) render(config);
+    const auto t1 = std::chrono::steady_clock::now();
+    if(outRgb && iterations > 0)
+        memcpy(outRgb, &fb.mColor[0], sizeof(float) * 3 * size_t(width) * size_t(height));
+    delete scene;
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
 // Framebuffer::TotalLuminance (src/framebuffer.hxx:89) of an image, float accumulation
 // in the reference's pixel order — the KAT scalar of BASELINE.md §3.
 REF_API float ref_total_luminance(const float *rgb, int width, int height)

@@ -13,6 +13,9 @@ Files
   ref_noise.npz       unmodified reference 128x128 x16 iterations, two seeds (noise floor for
                       the statistical GPU-vs-reference test)
   scenes.npz          the reference's Scene for g_SceneConfigs[0..3], flattened, raw bytes
+  ref_extra_scene.npz unmodified reference rendering box 1 + 1 160 extra triangles appended to its
+                      GeometryList (a scene that is not one of the hard-coded boxes): the triangles, the
+                      reference's flattened primitive bytes, 64x64 vcm and bpt images, 2 iterations
   image_files.npz     the files Framebuffer::SaveBMP / SaveHDR wrote for one small accumulated
                       image with hostile values (NaN, inf, negatives, denormals), 0 and 3 iterations
 """
@@ -62,9 +65,28 @@ def image_fixture():
     print("image_files.npz", {k: v.shape for k, v in out.items()})
 
 
+def extra_scene_fixture():
+    import scene_gen
+    b = scene_gen.blob((0.0, 0.25, 0.15), 0.38, 16, 32, 0.25, 5)
+    c = scene_gen.confetti(200, (-1.1, -0.9, -1.1), (1.1, 1.1, 1.1), 0.03, 6)
+    verts = np.concatenate([b, c])
+    mats = np.concatenate([np.where(np.arange(len(b)) % 2 == 0, 2, 8), np.full(len(c), 5)]).astype(np.int32)
+    out = {"vertices": verts, "materials": mats}
+    for alg in ("vcm", "bpt"):
+        img, prims, sphere = oa.ref_render_extra(1, alg, 64, 64, 2, verts, mats)
+        out["image_" + alg] = img
+    import smallvcm_b200 as sv
+    n = sv.Scene.cornell_box(1, 64, 64).desc.numPrimitives + len(verts)
+    out["primitives"] = np.frombuffer(C.string_at(prims, n * 56), np.uint8).reshape(n, 56).copy()
+    out["sphere"] = np.array(list(sphere.center) + [sphere.radius, sphere.invRadiusSqr], np.float32)
+    np.savez_compressed(os.path.join(HERE, "ref_extra_scene.npz"), **out)
+    print("ref_extra_scene.npz", {k: v.shape for k, v in out.items()})
+
+
 def main():
     oa.build_oracle()
     image_fixture()
+    extra_scene_fixture()
     assert oa.have_ref() and oa.have_ref_ctr(), "needs the reference checkout"
 
     # --- known answers of the unmodified reference (1 renderer, seed 1234, minLen 0) ---------

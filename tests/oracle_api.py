@@ -274,6 +274,8 @@ def ref_lib():
         lib.ref_scene_mask.argtypes = [i32]
         lib.ref_save_image.restype = i32
         lib.ref_save_image.argtypes = [VP, i32, i32, i32, i32, f32, C.c_char_p]
+        lib.ref_render_extra.restype = C.c_double
+        lib.ref_render_extra.argtypes = [i32] * 7 + [u32, u32, f32, f32, VP, VP, i32, VP, VP, VP]
         lib.ref_flatten_scene.restype = i32
         lib.ref_flatten_scene.argtypes = [i32, i32, i32] + [VP] * 10
         _ref = lib
@@ -291,6 +293,25 @@ def ref_render(scene_id, algorithm, width, height, iterations, threads=1, base_s
     if secs < 0:
         raise ValueError("ref_render failed")
     return secs, out
+
+
+def ref_render_extra(scene_id, algorithm, width, height, iterations, vertices, materials, threads=1,
+                     base_seed=1234, max_path_length=10, min_path_length=0, radius_factor=0.003,
+                     radius_alpha=0.75):
+    """The unmodified reference rendering box `scene_id` plus extra triangles appended to its
+    GeometryList. Returns (image, the reference's flattened primitive bytes [n, 56], scene sphere)."""
+    from smallvcm_b200 import abi
+    v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 9)
+    m = np.ascontiguousarray(materials, np.int32)
+    out = np.zeros((height, width, 3), np.float32)
+    prims = (abi.Primitive * (64 + len(v)))()
+    sphere = abi.SceneSphere()
+    secs = ref_lib().ref_render_extra(scene_id, REF_ALG[algorithm], width, height, iterations, threads, base_seed,
+                                      max_path_length, min_path_length, radius_factor, radius_alpha, _ptr(v), _ptr(m),
+                                      len(v), _ptr(out), C.cast(prims, VP), C.cast(C.byref(sphere), VP))
+    if secs < 0:
+        raise ValueError("ref_render_extra failed")
+    return out, prims, sphere
 
 
 def ref_save_image(accum, iterations, fmt, gamma, path):

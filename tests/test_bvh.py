@@ -119,6 +119,40 @@ def test_traversal_equals_list_order_loop(big, tmp_path):
         assert 0.3 < (out[0] >= 0).mean() and 0.1 < out[4].mean() < 0.95     # the rays do exercise both answers
 
 
+def test_oracle_bit_exact_on_a_scene_that_is_not_a_hard_coded_box():
+    """Pins the oracle beyond the reference's four boxes: box 1 (21 primitives) + 1 160 triangles appended to the
+    reference's GeometryList, rendered by the UNMODIFIED reference (tests/golden/
+    ref_extra_scene.npz, made by oracle/ref_glue ref_render_extra). Scene.with_triangles must build
+    byte-identical primitives (the reference's Triangle constructor computes the normal), and the
+    oracle with the reference's mt19937 stream must reproduce the images bit for bit."""
+    gold = np.load(os.path.join(HERE, "golden", "ref_extra_scene.npz"))
+    scene = sv.Scene.cornell_box(1, 64, 64).with_triangles(gold["vertices"], gold["materials"])
+    n = scene.desc.numPrimitives
+    assert n == 1181 and len(gold["primitives"]) == n
+    mine = np.frombuffer(C.string_at(scene.desc.primitives, n * 56), np.uint8).reshape(n, 56)
+    assert np.array_equal(mine, gold["primitives"])
+    sph = scene.desc.sceneSphere
+    assert np.array_equal(np.array(list(sph.center) + [sph.radius, sph.invRadiusSqr], np.float32), gold["sphere"])
+    for alg in ("vcm", "bpt"):
+        orc = oa.Oracle(scene, abi.ALGORITHMS[alg], seed=1234, rng_mode=0)
+        orc.run_iteration(0); orc.run_iteration(1)
+        img, cnt = orc.accum()
+        orc.close()
+        assert np.array_equal((img * np.float32(1.0 / cnt)).view(np.uint32), gold["image_" + alg].view(np.uint32))
+
+
+@pytest.mark.skipif(not oa.have_ref(), reason="oracle/_ref not built (no reference checkout)")
+def test_with_triangles_matches_live_reference_constructor():
+    rng = np.random.default_rng(8)
+    verts = rng.uniform(-1, 1, (500, 3, 3)).astype(np.float32)
+    mats = rng.integers(2, 9, 500).astype(np.int32)
+    _, prims, _ = oa.ref_render_extra(0, "vcm", 16, 16, 0, verts, mats)
+    scene = sv.Scene.cornell_box(0, 16, 16).with_triangles(verts, mats)
+    n = scene.desc.numPrimitives
+    assert np.array_equal(np.frombuffer(C.string_at(scene.desc.primitives, n * 56), np.uint8),
+                          np.frombuffer(C.string_at(prims, n * 56), np.uint8))
+
+
 # ---------------------------------------------------------------------------------------------
 # GPU
 # ---------------------------------------------------------------------------------------------
