@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 
 import smallvcm_b200 as sv
@@ -85,6 +86,30 @@ def test_no_cpu_fallback():
     with pytest.raises(sv.SvcmError) as e:
         sv.rng_stream_device(1, 0, 0, 0, 4, 4)
     assert e.value.code == abi.E_NO_DEVICE
+    with pytest.raises(sv.SvcmError) as e:
+        sv.image_convert_batch(np.zeros((2, 2, 3), np.float32), 1, "hdr")
+    assert e.value.code == abi.E_NO_DEVICE
+    # a scene large enough for the hierarchy is accepted by the host code and then fails the same way
+    big = scene.with_triangles(np.random.default_rng(0).uniform(-1, 1, (100, 3, 3)), np.full(100, 5))
+    with pytest.raises(sv.SvcmError) as e:
+        sv.VertexCM(big, "vcm")
+    assert e.value.code == abi.E_NO_DEVICE
+
+
+def test_host_only_entry_points_reject_bad_arguments():
+    lib = sv.load_library()
+    scene = sv.Scene.cornell_box(0, 16, 16)
+    nodes = (abi.BvhNode * 64)()
+    order = np.zeros(22, np.int32)
+    count = C.c_int32()
+    assert lib.svcm_bvh_build(None, 22, nodes, 64, order.ctypes.data, C.byref(count)) == abi.E_INVALID
+    assert lib.svcm_bvh_build(scene.desc.primitives, 0, nodes, 64, order.ctypes.data, C.byref(count)) == abi.E_INVALID
+    assert lib.svcm_bvh_build(scene.desc.primitives, 22, nodes, 2, order.ctypes.data, C.byref(count)) == abi.E_NOMEM
+    assert 11 <= count.value <= 43                     # the size the caller should have provided
+    assert lib.svcm_bvh_build(scene.desc.primitives, 22, nodes, 64, order.ctypes.data, C.byref(count)) == abi.OK
+    assert lib.svcm_image_bytes(abi.IMAGE_RGBE, -1, 4) == -1
+    assert lib.svcm_download_image(None, 0, 2.2, None, None) == abi.E_INVALID
+    assert lib.svcm_save_image(None, b"x.bmp", 2.2) == abi.E_INVALID
 
 
 def test_shard_map_is_a_partition():
