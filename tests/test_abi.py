@@ -129,3 +129,21 @@ def test_shard_map_is_a_partition():
                 assert lib.svcm_shard_local_index(w, ws, g) == l
         assert total == w * h and len(seen) == w * h
     assert lib.svcm_shard_local_paths(4, 4, 2, 2) == -1
+
+
+def test_header_is_plain_c_and_the_example_links(tmp_path):
+    """include/svcm.h must be usable from C (the drop-in boundary is a C ABI): the C99 example
+    compiles warning-free with -pedantic, links against the library, and without a GPU exits with
+    the library's "no CUDA device" error rather than computing anything."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "render_box")
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"),
+                          os.path.join(root, "examples", "render_box.c"), "-L" + os.path.dirname(sv.library_path()),
+                          "-lsvcm", "-Wl,-rpath," + os.path.dirname(sv.library_path()), "-o", exe],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    if sv.load_library().svcm_device_count() > 0:
+        return
+    run = subprocess.run([exe, "1", "vcm", "32", "1", str(tmp_path / "o.bmp")], capture_output=True, text=True)
+    assert run.returncode == 2 and "no CUDA device" in run.stderr
