@@ -334,7 +334,9 @@ def test_drop_in_driver_binary(tmp_path):
 def test_drop_in_driver_time_budget(tmp_path):
     """`-t <sec>` of the reference's render() (src/smallvcm.cxx:79-95) with the GPU renderer: the
     driver build substitutes a wall clock for clock(), so two seconds are two seconds of
-    rendering with two host threads (two handles on one device), not CPU-seconds."""
+    rendering, not CPU-seconds. main() sizes the thread pool with omp_get_num_procs()
+    (src/smallvcm.cxx:278-280; OMP_NUM_THREADS is ignored), so the process is pinned to two CPUs:
+    two host threads, two handles on one device."""
     import re
     import subprocess
     import time
@@ -342,10 +344,11 @@ def test_drop_in_driver_time_budget(tmp_path):
     if not os.path.exists(exe):
         pytest.skip("drop-in driver not built (needs the reference checkout)")
     out = str(tmp_path / "timed.bmp")
-    env = dict(os.environ, OMP_NUM_THREADS="2", SVCM_DEVICE="0")
+    env = dict(os.environ, SVCM_DEVICE="0")
+    cpus = sorted(os.sched_getaffinity(0))[:2]
     t0 = time.time()
     res = subprocess.run([exe, "-s", "1", "-a", "vcm", "-t", "2", "-o", out], capture_output=True, text=True,
-                         env=env, timeout=600)
+                         env=env, timeout=600, preexec_fn=lambda: os.sched_setaffinity(0, cpus))
     wall = time.time() - t0
     assert res.returncode == 0, res.stdout + res.stderr
     assert "Target:  2 seconds render time" in res.stdout
