@@ -697,7 +697,7 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
             count = r->counters + CNT_QUERIES;           // only the mergeable vertices are in the order
         }
         launchMerge(r->scene, ic, qs, count, 0, r->grid, r->accum, NULL, NULL,
-                    r->counters, r->mergeGroup, r->gridCapacity, st);
+                    r->counters, r->mergeGroup, st);
         launches++;
     }
     if(timed) cudaEventRecord(ev[5], st);
@@ -1371,7 +1371,7 @@ int svcm_hashgrid_query(svcm_hashgrid *g, const SvcmSceneDesc *scene, const Svcm
         const char *variant = getenv("SVCM_MERGE_GROUP");
         const int group = variant ? atoi(variant) : 1;
         launchMerge(sc, ic, qs, NULL, uint32_t(count), g->grid, NULL, dContrib, dCounts, NULL,
-                    (group == 8 || group == 16 || group == 32) ? group : 1, uint32_t(g->count), 0);
+                    (group == 8 || group == 16 || group == 32) ? group : 1, 0);
         e = cudaMemcpy(contrib, dContrib, sizeof(float) * 3 * size_t(count), cudaMemcpyDeviceToHost);
         if(e == cudaSuccess && counts) e = cudaMemcpy(counts, dCounts, sizeof(int32_t) * 2 * size_t(count), cudaMemcpyDeviceToHost);
     }

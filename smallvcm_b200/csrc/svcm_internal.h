@@ -202,7 +202,7 @@ int  launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers
 void launchMerge(const DevScene &sc, const IterConst &ic, const QueryStore &queries,
                  const unsigned long long *queryCount, uint32_t hostQueryCount,
                  const GridBuffers &grid, float *accum, float *contribOut, int32_t *countsOut,
-                 unsigned long long *counters, int groupSize, uint32_t particleCapacity, cudaStream_t stream);
+                 unsigned long long *counters, int groupSize, cudaStream_t stream);
 
 // kernel-level batch entry points (device pointers)
 void launchIntersectBatch(const DevScene &sc, const float *rays, int64_t count, int32_t *hit,

@@ -1739,11 +1739,10 @@ int launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers 
 void launchMerge(const DevScene &sc, const IterConst &ic, const QueryStore &queries,
                  const unsigned long long *queryCount, uint32_t hostQueryCount, const GridBuffers &grid,
                  float *accum, float *contribOut, int32_t *countsOut, unsigned long long *counters,
-                 int groupSize, uint32_t particleCapacity, cudaStream_t stream)
+                 int groupSize, cudaStream_t stream)
 {
     const uint64_t maxQueries = queryCount ? queries.capacity : hostQueryCount;
     if(maxQueries == 0) return;
-    (void)particleCapacity;
     if(groupSize == 1)
     {
         k_mergeLane<<<gridFor(maxQueries, SVCM_BLOCK, 4), SVCM_BLOCK, 0, stream>>>(
