@@ -226,7 +226,20 @@ enum {
     SVCM_OPT_MERGE_GROUP   = 2, /* merge kernel: 1 = one lane per range query with warp
                                    compaction of accepted pairs (default); 8, 16, 32 =
                                    that many lanes cooperating on one query            */
-    SVCM_OPT_COUNTERS      = 3  /* 0/1: maintain N_cand/N_acc counters (small cost)    */
+    SVCM_OPT_COUNTERS      = 3, /* 0/1: maintain N_cand/N_acc counters (small cost)    */
+    SVCM_OPT_GRID_LAYOUT   = 4, /* particle order of the hash grid: 0 = the reference's
+                                   hash buckets (mCellEnds / mIndices as they are);
+                                   1 = true cell order (spatially coherent rows; the
+                                   bucket collisions' double visits are reproduced
+                                   arithmetically, results identical)                   */
+    SVCM_OPT_MERGE_VARIANT = 5, /* cell layout only: 0 = lane per query from global
+                                   memory, 1 = neighbourhood staged through shared
+                                   memory by bulk async copies (default), 2 = staged
+                                   with plain loads, 3 = like 1 with smaller stages     */
+    SVCM_OPT_REF_CANDIDATES = 6 /* 0/1, cell layout: also histogram the reference's
+                                   buckets so that mergeCandidates counts what the
+                                   reference's walk would visit (statistics; off: the
+                                   distance tests this library performs)                */
 };
 
 typedef struct svcm_renderer svcm_renderer;

@@ -135,6 +135,10 @@ struct svcm_renderer
 
     int  iterationsDone;
     int  mergeGroup;
+    bool cellLayout;                // SVCM_OPT_GRID_LAYOUT
+    int  mergeVariant;              // SVCM_OPT_MERGE_VARIANT
+    bool refCandidates;             // SVCM_OPT_REF_CANDIDATES
+    ScanGen scanGenGrid, scanGenQuery;
     bool profile;
     cudaEvent_t (*ev)[6];          // [SVCM_PROFILE_RING][6], created when profiling is enabled
     cudaEvent_t userEv[SVCM_NUM_USER_EVENTS];
@@ -319,13 +323,45 @@ int ensureGridSorted(svcm_renderer *r, uint32_t capacity)
     return SVCM_OK;
 }
 
+// key space of the cell layout: 2^21 storage cells (8 MB per table), independent of the resolution
+// because the cell edge follows the radius, not the pixel count
+static const uint32_t kCellTableCapacity = 1u << 21;
+static const size_t   kScanStateWords = 4096;
+
+int allocCellTables(svcm_renderer *r, GridBuffers &grid, QuerySortBuffers *qs, uint32_t numCells)
+{
+    int rc;
+    grid.tcap = kCellTableCapacity;
+    if(!grid.cellEnd)
+    {
+        if((rc = devAlloc(r, &grid.cellEnd, size_t(grid.tcap) + 2 + 64))) return rc;
+        if((rc = devAlloc(r, &grid.dims, 1))) return rc;
+        if((rc = devAlloc(r, &grid.scanState, kScanStateWords))) return rc;
+        if((rc = devAlloc(r, &grid.scanCounter, 1))) return rc;
+        SVCM_CUDA(r, cudaMemset(grid.scanState, 0, sizeof(unsigned long long) * kScanStateWords));
+        SVCM_CUDA(r, cudaMemset(grid.scanCounter, 0, sizeof(uint32_t)));
+        SVCM_CUDA(r, cudaMemset(grid.dims, 0, sizeof(GridDims)));
+    }
+    if(!grid.refCount) if((rc = devAlloc(r, &grid.refCount, size_t(numCells)))) return rc;
+    if(qs && !qs->cellEnd)
+    {
+        if((rc = devAlloc(r, &qs->cellEnd, size_t(grid.tcap) + 2 + 64))) return rc;
+        if((rc = devAlloc(r, &qs->scanState, kScanStateWords))) return rc;
+        if((rc = devAlloc(r, &qs->scanCounter, 1))) return rc;
+        SVCM_CUDA(r, cudaMemset(qs->scanState, 0, sizeof(unsigned long long) * kScanStateWords));
+        SVCM_CUDA(r, cudaMemset(qs->scanCounter, 0, sizeof(uint32_t)));
+    }
+    return SVCM_OK;
+}
+
 int ensureGridCells(svcm_renderer *r, uint32_t numCells)
 {
     if(numCells == r->gridCells) return SVCM_OK;
-    devFree(r->grid.cellCount); devFree(r->grid.blockSums);
+    devFree(r->grid.cellCount); devFree(r->grid.blockSums); devFree(r->grid.refCount);
     int rc;
     if((rc = devAlloc(r, &r->grid.cellCount, size_t(numCells) + 1))) return rc;
     if((rc = devAlloc(r, &r->grid.blockSums, (size_t(numCells) + 1) / 2048 + 2))) return rc;
+    if((rc = allocCellTables(r, r->grid, &r->qsort, numCells))) return rc;
     r->gridCells = numCells;
     return SVCM_OK;
 }
@@ -479,6 +515,7 @@ void iterationConstants(const svcm_renderer *r, int iteration, uint32_t minLen, 
     ic.rank = r->params.rank; ic.worldSize = r->params.worldSize;
     ic.localPaths = r->localPaths;
     ic.numCells = r->paths;
+    ic.hashMagic = hashMagicFor(ic.numCells);
 }
 
 int ncclCheck(svcm_renderer *r, int rc, const char *what)
@@ -659,7 +696,8 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
             set.capacity = r->verts.capacity;
             set.segStride = r->verts.capacity; set.numSegs = 1;
         }
-        launches += launchGridBuild(ic, set, r->grid, st);
+        if(r->cellLayout) launches += launchCellGridBuild(ic, set, r->grid, r->scanGenGrid, r->refCandidates, st);
+        else launches += launchGridBuild(ic, set, r->grid, st);
     }
     if(timed) cudaEventRecord(ev[3], st);
     th[3] = hostNowMs();
@@ -690,14 +728,28 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     {
         QueryStore qs = r->queries;
         const unsigned long long *count = r->counters + CNT_CAM_VERTS;
-        if(r->sortQueries)
+        if(r->cellLayout)
         {
-            launches += launchQuerySort(ic, r->queries, r->counters + CNT_CAM_VERTS, r->grid.bboxBits, r->qsort, st);
+            // the queries take the particles' order: neighbouring lanes share rows and cells
+            launches += launchCellQuerySort(ic, r->queries, r->counters + CNT_CAM_VERTS, 0, r->grid, r->qsort,
+                                            r->scanGenQuery, st);
             qs.order = r->qsort.order;
-            count = r->counters + CNT_QUERIES;           // only the mergeable vertices are in the order
+            count = r->counters + CNT_QUERIES;
+            GridBuffers grid = r->grid;
+            if(!r->refCandidates) grid.refCount = NULL;
+            launchCellMerge(r->scene, ic, qs, count, 0, grid, r->accum, NULL, NULL, r->counters, r->mergeVariant, st);
         }
-        launchMerge(r->scene, ic, qs, count, 0, r->grid, r->accum, NULL, NULL,
-                    r->counters, r->mergeGroup, st);
+        else
+        {
+            if(r->sortQueries)
+            {
+                launches += launchQuerySort(ic, r->queries, r->counters + CNT_CAM_VERTS, r->grid.bboxBits, r->qsort, st);
+                qs.order = r->qsort.order;
+                count = r->counters + CNT_QUERIES;           // only the mergeable vertices are in the order
+            }
+            launchMerge(r->scene, ic, qs, count, 0, r->grid, r->accum, NULL, NULL,
+                        r->counters, r->mergeGroup, st);
+        }
         launches++;
     }
     if(timed) cudaEventRecord(ev[5], st);
@@ -801,6 +853,15 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     r->comm = NULL; r->gPosLen = r->gThrVcm = r->gDirVm = NULL; r->gContProb = NULL; r->gatherCapacity = 0;
     r->devCounts64 = NULL; r->hostCounts64 = NULL; r->hostCounts = NULL;
     r->iterationsDone = 0; r->mergeGroup = 1; r->profile = false;
+    {
+        // defaults; SVCM_GRID_LAYOUT / SVCM_MERGE_VARIANT override them for A/B measurements
+        const char *layout = getenv("SVCM_GRID_LAYOUT");
+        r->cellLayout = layout ? (strcmp(layout, "bucket") != 0 && strcmp(layout, "0") != 0) : false;
+        const char *variant = getenv("SVCM_MERGE_VARIANT");
+        r->mergeVariant = variant ? atoi(variant) : 1;
+        r->refCandidates = getenv("SVCM_REF_CANDIDATES") != NULL && atoi(getenv("SVCM_REF_CANDIDATES")) != 0;
+        r->scanGenGrid.value = 0; r->scanGenQuery.value = 0;
+    }
     r->ev = NULL; r->ringHead = r->ringTail = 0;
     memset(r->ringLaunches, 0, sizeof(r->ringLaunches)); memset(r->ringTimed, 0, sizeof(r->ringTimed));
     memset(r->userEv, 0, sizeof(r->userEv)); memset(&r->stats, 0, sizeof(r->stats));
@@ -890,7 +951,10 @@ void svcm_destroy(svcm_renderer *r)
     devFree(r->pathVertCount); devFree(r->counters); devFree(r->accum); devFree(r->image8);
     r->geometry.release();
     devFree(r->grid.cellCount); devFree(r->grid.blockSums); devFree(r->grid.bboxBits);
+    devFree(r->grid.cellEnd); devFree(r->grid.dims); devFree(r->grid.refCount);
+    devFree(r->grid.scanState); devFree(r->grid.scanCounter);
     devFree(r->qsort.cellCount); devFree(r->qsort.blockSums);
+    devFree(r->qsort.cellEnd); devFree(r->qsort.scanState); devFree(r->qsort.scanCounter);
     devFree(r->bboxInit); devFree(r->devCounts64);
     if(r->hostCounters) cudaFreeHost(r->hostCounters);
     if(r->hostCounts64) cudaFreeHost(r->hostCounts64);
@@ -925,6 +989,14 @@ int svcm_set_option(svcm_renderer *r, int32_t option, int64_t value)
             return fail(r, SVCM_E_INVALID, "merge group must be 1 (lane per query), 8, 16 or 32");
         r->mergeGroup = int(value); return SVCM_OK;
     case SVCM_OPT_COUNTERS: return SVCM_OK;   // counters are always maintained
+    case SVCM_OPT_GRID_LAYOUT:
+        if(value != 0 && value != 1) return fail(r, SVCM_E_INVALID, "grid layout must be 0 (hash buckets) or 1 (cell order)");
+        r->cellLayout = value != 0; return SVCM_OK;
+    case SVCM_OPT_MERGE_VARIANT:
+        if(value < 0 || value > 3) return fail(r, SVCM_E_INVALID, "merge variant must be 0..3");
+        r->mergeVariant = int(value); return SVCM_OK;
+    case SVCM_OPT_REF_CANDIDATES:
+        r->refCandidates = value != 0; return SVCM_OK;
     default: return fail(r, SVCM_E_INVALID, "unknown option %d", option);
     }
 }
@@ -1208,6 +1280,8 @@ struct svcm_hashgrid
     unsigned long long *countDev;
     GridBuffers grid;
     int32_t *bboxInit;
+    bool cellLayout;                // SVCM_GRID_LAYOUT at build time
+    ScanGen scanGen;
     std::string error;
 };
 
@@ -1265,6 +1339,11 @@ int svcm_hashgrid_build(const SvcmMergeVertex *vertices, int64_t count, float ra
     g->device = device; g->stream = NULL; g->count = count; g->numCells = uint32_t(numCells); g->radius = radius;
     g->posLen = g->thrVcm = g->dirVm = NULL; g->contProb = NULL; g->countDev = NULL; g->bboxInit = NULL;
     memset(&g->grid, 0, sizeof(g->grid));
+    {
+        const char *layout = getenv("SVCM_GRID_LAYOUT");
+        g->cellLayout = layout ? (strcmp(layout, "bucket") != 0 && strcmp(layout, "0") != 0) : false;
+        g->scanGen.value = 0;
+    }
 
     cudaError_t e = cudaSuccess;
     SvcmMergeVertex *staging = NULL;
@@ -1293,11 +1372,18 @@ int svcm_hashgrid_build(const SvcmMergeVertex *vertices, int64_t count, float ra
         launchPackMergeVertices(staging, count, g->posLen, g->thrVcm, g->dirVm, g->contProb, 0);
         IterConst ic; memset(&ic, 0, sizeof(ic));
         ic.radius = radius; ic.radiusSqr = radius * radius; ic.invCellSize = 1.f / (radius * 2.f);
-        ic.numCells = uint32_t(numCells);
+        ic.numCells = uint32_t(numCells); ic.hashMagic = hashMagicFor(ic.numCells);
         MergeSet set; memset(&set, 0, sizeof(set));
         set.posLen = g->posLen; set.thrVcm = g->thrVcm; set.dirVm = g->dirVm; set.contProb = g->contProb;
         set.singleCount = g->countDev; set.capacity = uint32_t(count); set.segStride = uint32_t(count); set.numSegs = 1;
-        launchGridBuild(ic, set, g->grid, 0);
+        if(g->cellLayout)
+        {
+            // the reference-bucket histogram rides along: svcm_hashgrid_download and the per-query
+            // candidate counts are stated in the reference's convention
+            if(allocCellTables(NULL, g->grid, NULL, uint32_t(numCells)) != SVCM_OK) e = cudaErrorMemoryAllocation;
+            else launchCellGridBuild(ic, set, g->grid, g->scanGen, true, 0);
+        }
+        else launchGridBuild(ic, set, g->grid, 0);
     }
     rc = cudaDone(e, "svcm_hashgrid_build");
     if(staging) cudaFree(staging);
@@ -1314,6 +1400,8 @@ void svcm_hashgrid_destroy(svcm_hashgrid *g)
     cudaFree(g->bboxInit); cudaFree(g->grid.cellKey); cudaFree(g->grid.cellCount); cudaFree(g->grid.blockSums);
     cudaFree(g->grid.bboxBits); cudaFree(g->grid.sPosLen); cudaFree(g->grid.sThrVcm); cudaFree(g->grid.sDirVm);
     cudaFree(g->grid.sContProb); cudaFree(g->grid.sIndex);
+    cudaFree(g->grid.cellEnd); cudaFree(g->grid.dims); cudaFree(g->grid.refCount);
+    cudaFree(g->grid.scanState); cudaFree(g->grid.scanCounter);
     delete g;
 }
 
@@ -1327,6 +1415,43 @@ int svcm_hashgrid_download(svcm_hashgrid *g, float bbox[6], int32_t *cellEnds, i
         int32_t bits[6];
         e = cudaMemcpy(bits, g->grid.bboxBits, sizeof(bits), cudaMemcpyDeviceToHost);
         for(int i = 0; i < 6; i++) bbox[i] = orderedToFloat(bits[i]);
+    }
+    if(g->cellLayout)
+    {
+        // The particles lie in cell order; mCellEnds / mIndices are restated from it: the device gives
+        // the reference bucket of the particle at every sorted slot and the per-bucket histogram, the
+        // grouping by bucket happens here (a stable counting sort of the slots).
+        if(e == cudaSuccess && (cellEnds || indices))
+        {
+            const size_t n = size_t(g->count);
+            std::vector<uint32_t> refKey(n), counts(g->numCells);
+            std::vector<int32_t> perm(n);
+            uint32_t *dKeys = NULL;
+            if(n) e = cudaMalloc((void**)&dKeys, sizeof(uint32_t) * n);
+            if(e == cudaSuccess && n)
+            {
+                IterConst ic; memset(&ic, 0, sizeof(ic));
+                ic.invCellSize = 1.f / (g->radius * 2.f); ic.numCells = g->numCells; ic.hashMagic = hashMagicFor(g->numCells);
+                launchCellRefKeys(ic, g->grid, uint32_t(n), dKeys, 0);
+                e = cudaMemcpy(refKey.data(), dKeys, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost);
+                if(e == cudaSuccess) e = cudaMemcpy(perm.data(), g->grid.sIndex, sizeof(int32_t) * n, cudaMemcpyDeviceToHost);
+            }
+            if(dKeys) cudaFree(dKeys);
+            if(e == cudaSuccess) e = cudaMemcpy(counts.data(), g->grid.refCount, sizeof(uint32_t) * g->numCells, cudaMemcpyDeviceToHost);
+            if(e == cudaSuccess)
+            {
+                std::vector<uint32_t> cursor(g->numCells);
+                uint32_t run = 0;
+                for(uint32_t c = 0; c < g->numCells; c++) { cursor[c] = run; run += counts[c]; if(cellEnds) cellEnds[c] = int32_t(run); }
+                if(run != n) return fail(NULL, SVCM_E_STATE, "bucket histogram (%u) does not add up to the particle count (%zu)", run, n);
+                if(indices) for(size_t slot = 0; slot < n; slot++)
+                {
+                    if(refKey[slot] >= g->numCells) return fail(NULL, SVCM_E_STATE, "bucket out of range");
+                    indices[cursor[refKey[slot]]++] = perm[slot];
+                }
+            }
+        }
+        return cudaDone(e, "svcm_hashgrid_download");
     }
     if(e == cudaSuccess && cellEnds)
         e = cudaMemcpy(cellEnds, g->grid.cellCount, sizeof(int32_t) * g->numCells, cudaMemcpyDeviceToHost);
@@ -1364,14 +1489,39 @@ int svcm_hashgrid_query(svcm_hashgrid *g, const SvcmSceneDesc *scene, const Svcm
         IterConst ic; memset(&ic, 0, sizeof(ic));
         ic.radius = g->radius; ic.radiusSqr = g->radius * g->radius; ic.invCellSize = 1.f / (g->radius * 2.f);
         ic.numCells = g->numCells; ic.minLen = minPathLength; ic.maxLen = maxPathLength;
+        ic.hashMagic = hashMagicFor(ic.numCells);
         ic.misVcWeightFactor = misVcWeightFactor; ic.ppm = ppm != 0; ic.useVM = 1;
         ic.vmNormalization = 1.f;             // the entry point returns the un-normalised mContrib
         launchPackMergeQueries(sc, dq, count, qs, 0);
+        if(g->cellLayout)
+        {
+            // like the path: queries sorted into the particles' order, then the merge variant the
+            // environment picks (SVCM_MERGE_VARIANT, default 1 = staged with bulk copies)
+            QuerySortBuffers sort; memset(&sort, 0, sizeof(sort));
+            sort.key = s.alloc<uint32_t>(size_t(count), e); sort.order = s.alloc<uint32_t>(size_t(count), e);
+            sort.cellEnd = s.alloc<uint32_t>(size_t(g->grid.tcap) + 2 + 64, e);
+            sort.scanState = s.alloc<unsigned long long>(kScanStateWords, e);
+            sort.scanCounter = s.alloc<uint32_t>(1, e);
+            if(e == cudaSuccess) e = cudaMemset(sort.scanState, 0, sizeof(unsigned long long) * kScanStateWords);
+            if(e == cudaSuccess) e = cudaMemset(sort.scanCounter, 0, sizeof(uint32_t));
+            if(e == cudaSuccess)
+            {
+                ScanGen gen; gen.value = 0;
+                launchCellQuerySort(ic, qs, NULL, uint32_t(count), g->grid, sort, gen, 0);
+                qs.order = sort.order;
+                const char *variant = getenv("SVCM_MERGE_VARIANT");
+                launchCellMerge(sc, ic, qs, NULL, uint32_t(count), g->grid, NULL, dContrib, dCounts, NULL,
+                                variant ? atoi(variant) : 1, 0);
+            }
+        }
+        else
+        {
         // the parity tests exercise both merge kernels: the environment picks the variant
         const char *variant = getenv("SVCM_MERGE_GROUP");
         const int group = variant ? atoi(variant) : 1;
         launchMerge(sc, ic, qs, NULL, uint32_t(count), g->grid, NULL, dContrib, dCounts, NULL,
                     (group == 8 || group == 16 || group == 32) ? group : 1, 0);
+        }
         e = cudaMemcpy(contrib, dContrib, sizeof(float) * 3 * size_t(count), cudaMemcpyDeviceToHost);
         if(e == cudaSuccess && counts) e = cudaMemcpy(counts, dCounts, sizeof(int32_t) * 2 * size_t(count), cudaMemcpyDeviceToHost);
     }

@@ -27,6 +27,7 @@ struct IterConst
     int32_t  rank, worldSize;      // path p is owned by rank (p / resX) % worldSize
     uint32_t localPaths;
     uint32_t numCells;             // hash-grid cell count (= W*H, src/vertexcm.hxx:406)
+    unsigned long long hashMagic;  // ceil(2^64 / numCells): exact x % numCells without a division (0: numCells == 1)
 };
 
 // SoA path state, one slot per queued sub-path; four 16-byte streams so that every
@@ -73,6 +74,21 @@ struct MergeSet
     uint32_t numSegs;
 };
 
+// Geometry of the cell-layout grid (svcm_grid.cu), derived on the device from the particle bbox:
+// storage cells are the reference's cells (edge 2r, src/hashgrid.hxx:47-48) with `m` of them
+// merged along x when the grid is extremely fine; a storage row (fixed y, z) is CONTIGUOUS in key
+// space with one empty guard cell either side, and rows are folded modulo (fy, fz) into a table of
+// at most `tcap` keys. Folding only aliases cells >= 4 cells apart, which the distance test rejects.
+//   key(sx, cy, cz) = ((cz mod fz) * fy + (cy mod fy)) * nxp + (sx + 1) + 1        (key 0: empty dummy)
+struct GridDims
+{
+    int32_t  m;            // reference cells per storage cell along x (1 unless the grid is extremely fine)
+    int32_t  nxp;          // storage cells along x + 2 guard cells
+    int32_t  fy, fz;       // fold moduli (>= 4, or the whole extent + 2 when that is smaller)
+    uint32_t numKeys;      // fz * fy * nxp  (<= tcap); keys run 1..numKeys
+    int32_t  nx, ny, nz;   // reference cells spanned by the bbox
+};
+
 struct GridBuffers
 {
     uint32_t *cellKey;    // [virtual index] hash bucket of each vertex (or ~0 for padding)
@@ -84,6 +100,13 @@ struct GridBuffers
     // cell-sorted merge records
     float4   *sPosLen; float4 *sThrVcm; float4 *sDirVm; float *sContProb;
     int32_t  *sIndex;     // original (virtual) index at each sorted position  (mIndices)
+    // ---- cell layout (svcm_grid.cu); NULL / 0 in the bucket layout ----
+    GridDims *dims;       // device
+    uint32_t *cellEnd;    // [tcap + 2] END offset of every storage cell; cellEnd[0] = 0 (dummy cell 0)
+    uint32_t  tcap;
+    uint32_t *refCount;   // optional [numCells]: particles per REFERENCE hash bucket (statistics / T1 only)
+    unsigned long long *scanState;  // decoupled look-back scan: one word per tile
+    uint32_t *scanCounter;          // dynamic tile ids (self-resetting)
 };
 
 // Camera vertices: every non-delta vertex of a camera sub-path that can still be connected or
@@ -109,6 +132,10 @@ struct QuerySortBuffers
     uint32_t *key;         // [query capacity]
     uint32_t *order;       // [query capacity]
     uint32_t *blockSums;
+    // cell layout: the queries are counting-sorted over the same key space as the particles
+    uint32_t *cellEnd;     // [tcap + 2]
+    unsigned long long *scanState;
+    uint32_t *scanCounter;
 };
 enum { CAMV_MERGEABLE = 1u << 24 };   // inside the light-vertex bbox and merging is on
 
@@ -203,6 +230,28 @@ void launchMerge(const DevScene &sc, const IterConst &ic, const QueryStore &quer
                  const unsigned long long *queryCount, uint32_t hostQueryCount,
                  const GridBuffers &grid, float *accum, float *contribOut, int32_t *countsOut,
                  unsigned long long *counters, int groupSize, cudaStream_t stream);
+
+// ---- cell layout (svcm_grid.cu) ------------------------------------------------------------
+// Generation counter of the look-back scan state words; bump once per scan launch.
+struct ScanGen { uint32_t value; };
+// HashGrid::Build in the cell layout: bbox -> grid dims -> keys + histogram -> single-pass
+// look-back scan -> index scatter -> record gather. `withRefCount`: also histogram the
+// reference's hash buckets into grid.refCount (numCells entries). Returns kernels launched.
+int  launchCellGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers &grid, ScanGen &gen,
+                         bool withRefCount, cudaStream_t stream);
+// counting sort of the mergeable camera vertices over the grid's key space -> qs.order
+int  launchCellQuerySort(const IterConst &ic, const QueryStore &queries, const unsigned long long *vertexCount,
+                         uint32_t hostVertexCount, const GridBuffers &grid, const QuerySortBuffers &qs, ScanGen &gen,
+                         cudaStream_t stream);
+// merge over the cell layout. variant: 0 = lane per query straight from global memory, 1 = staged
+// through shared memory with bulk async copies, 2 = staged with plain loads
+void launchCellMerge(const DevScene &sc, const IterConst &ic, const QueryStore &queries,
+                     const unsigned long long *queryCount, uint32_t hostQueryCount,
+                     const GridBuffers &grid, float *accum, float *contribOut, int32_t *countsOut,
+                     unsigned long long *counters, int variant, cudaStream_t stream);
+// per sorted slot: the reference hash bucket of that particle (T1 export of the cell layout)
+void launchCellRefKeys(const IterConst &ic, const GridBuffers &grid, uint32_t count, uint32_t *out, cudaStream_t stream);
+uint64_t hashMagicFor(uint32_t numCells);
 
 // kernel-level batch entry points (device pointers)
 void launchIntersectBatch(const DevScene &sc, const float *rays, int64_t count, int32_t *hit,

@@ -13,70 +13,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "svcm_internal.h"
+#include "svcm_kutil.cuh"
 
 namespace svcm {
-
-#define SVCM_BLOCK 256
-#define FULL_MASK 0xffffffffu
-
-// ------------------------------------------------------------------------------------------
-// small device utilities
-// ------------------------------------------------------------------------------------------
-SVCM_D uint32_t laneId() { return threadIdx.x & 31u; }
-
-// Warp-aggregated append: every lane of the warp must call it; lanes with pred get a
-// distinct slot from one atomicAdd issued by the first such lane.
-SVCM_D uint32_t warpAppend(uint32_t *counter, bool pred)
-{
-    const uint32_t m = __ballot_sync(FULL_MASK, pred);
-    if(m == 0u) return 0u;
-    const int leader = __ffs(m) - 1;
-    uint32_t base = 0u;
-    if(int(laneId()) == leader) base = atomicAdd(counter, uint32_t(__popc(m)));
-    base = __shfl_sync(FULL_MASK, base, leader);
-    return base + uint32_t(__popc(m & ((1u << laneId()) - 1u)));
-}
-SVCM_D uint32_t warpAppend64(unsigned long long *counter, bool pred)
-{
-    const uint32_t m = __ballot_sync(FULL_MASK, pred);
-    if(m == 0u) return 0u;
-    const int leader = __ffs(m) - 1;
-    unsigned long long base = 0ull;
-    if(int(laneId()) == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
-    base = __shfl_sync(FULL_MASK, base, leader);
-    return uint32_t(base) + uint32_t(__popc(m & ((1u << laneId()) - 1u)));
-}
-
-// Opportunistic aggregation for appends issued from divergent code: the lanes that happen to
-// be converged here share one atomicAdd.
-SVCM_D uint32_t activeAppend(uint32_t *counter)
-{
-    const uint32_t m = __activemask();
-    const int leader = __ffs(m) - 1;
-    uint32_t base = 0u;
-    if(int(laneId()) == leader) base = atomicAdd(counter, uint32_t(__popc(m)));
-    base = __shfl_sync(m, base, leader);
-    return base + uint32_t(__popc(m & ((1u << laneId()) - 1u)));
-}
-
-// adds a per-thread count into a 64-bit device counter with one atomic per warp
-SVCM_D void warpCount(unsigned long long *counter, uint32_t mine)
-{
-#pragma unroll
-    for(int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(FULL_MASK, mine, o);
-    if(laneId() == 0u && mine) atomicAdd(counter, (unsigned long long)mine);
-}
-
-SVCM_D void addPixel(float *accum, uint32_t pixel, f3 c)
-{
-    float *p = accum + 3ull * pixel;
-    if(c.x != 0.f) atomicAdd(p + 0, c.x);
-    if(c.y != 0.f) atomicAdd(p + 1, c.y);
-    if(c.z != 0.f) atomicAdd(p + 2, c.z);
-}
-
-SVCM_D float4 mk4(f3 a, float w) { return make_float4(a.x, a.y, a.z, w); }
-SVCM_D f3 xyz(float4 a) { return mk3(a.x, a.y, a.z); }
 
 // Queue one visibility test: "add `contrib` to `pixel` unless point -> point + dir*tMax is
 // blocked" (Scene::Occluded, reference src/scene.hxx:72-85). If the queue is full the ray is
@@ -915,24 +854,6 @@ k_eyeLight(const __grid_constant__ DevScene sc, const __grid_constant__ IterCons
 // hash grid build (HashGrid::Build, reference src/hashgrid.hxx:41-107)
 // ------------------------------------------------------------------------------------------
 
-SVCM_D uint32_t mergeSetTotal(const MergeSet &set)
-{
-    if(set.singleCount) return uint32_t(min(*set.singleCount, (unsigned long long)set.capacity));
-    return set.numSegs * set.segStride;
-}
-SVCM_D bool mergeSetValid(const MergeSet &set, uint32_t i)
-{
-    if(set.singleCount) return true;
-    const uint32_t seg = i / set.segStride;
-    return (i - seg * set.segStride) < set.segCount[seg];
-}
-
-// HashGrid::GetCellIndex(Vec3i), reference src/hashgrid.hxx:179-187
-SVCM_D uint32_t cellHash(int32_t cx, int32_t cy, int32_t cz, uint32_t numCells)
-{
-    return ((uint32_t(cx) * 73856093u) ^ (uint32_t(cy) * 19349663u) ^ (uint32_t(cz) * 83492791u)) % numCells;
-}
-
 // bounding box of the particles (reference src/hashgrid.hxx:50-61)
 __global__ void __launch_bounds__(SVCM_BLOCK)
 k_gridBBox(const __grid_constant__ MergeSet set, int32_t *bboxBits)
@@ -1631,7 +1552,7 @@ __global__ void k_packMergeQueries(const __grid_constant__ DevScene sc, const Sv
 // launchers
 // ------------------------------------------------------------------------------------------
 static int g_numSMs = 0;
-static int numSMs()
+int numSMs()
 {
     if(g_numSMs == 0)
     {
@@ -1642,7 +1563,7 @@ static int numSMs()
     return g_numSMs;
 }
 // persistent-style grid: a multiple of the SM count, capped by the work available
-static uint32_t gridFor(uint64_t items, int perBlock, int blocksPerSM)
+uint32_t gridFor(uint64_t items, int perBlock, int blocksPerSM)
 {
     const uint64_t need = (items + uint64_t(perBlock) - 1) / uint64_t(perBlock);
     const uint64_t cap = uint64_t(numSMs()) * uint64_t(blocksPerSM);

@@ -1,0 +1,101 @@
+// svcm_kutil.cuh — warp-level utilities shared by the kernel translation units
+// (svcm_kernels.cu: trace kernels + the bucket-layout grid; svcm_grid.cu: the cell-layout grid,
+// its sort and the staged merge).
+#ifndef SVCM_KUTIL_CUH_
+#define SVCM_KUTIL_CUH_
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "svcm_internal.h"
+
+namespace svcm {
+
+#define SVCM_BLOCK 256
+#define FULL_MASK 0xffffffffu
+
+// ------------------------------------------------------------------------------------------
+// small device utilities
+// ------------------------------------------------------------------------------------------
+SVCM_D uint32_t laneId() { return threadIdx.x & 31u; }
+
+// Warp-aggregated append: every lane of the warp must call it; lanes with pred get a
+// distinct slot from one atomicAdd issued by the first such lane.
+SVCM_D uint32_t warpAppend(uint32_t *counter, bool pred)
+{
+    const uint32_t m = __ballot_sync(FULL_MASK, pred);
+    if(m == 0u) return 0u;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0u;
+    if(int(laneId()) == leader) base = atomicAdd(counter, uint32_t(__popc(m)));
+    base = __shfl_sync(FULL_MASK, base, leader);
+    return base + uint32_t(__popc(m & ((1u << laneId()) - 1u)));
+}
+SVCM_D uint32_t warpAppend64(unsigned long long *counter, bool pred)
+{
+    const uint32_t m = __ballot_sync(FULL_MASK, pred);
+    if(m == 0u) return 0u;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0ull;
+    if(int(laneId()) == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(FULL_MASK, base, leader);
+    return uint32_t(base) + uint32_t(__popc(m & ((1u << laneId()) - 1u)));
+}
+
+// Opportunistic aggregation for appends issued from divergent code: the lanes that happen to
+// be converged here share one atomicAdd.
+SVCM_D uint32_t activeAppend(uint32_t *counter)
+{
+    const uint32_t m = __activemask();
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0u;
+    if(int(laneId()) == leader) base = atomicAdd(counter, uint32_t(__popc(m)));
+    base = __shfl_sync(m, base, leader);
+    return base + uint32_t(__popc(m & ((1u << laneId()) - 1u)));
+}
+
+// adds a per-thread count into a 64-bit device counter with one atomic per warp
+SVCM_D void warpCount(unsigned long long *counter, uint32_t mine)
+{
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(FULL_MASK, mine, o);
+    if(laneId() == 0u && mine) atomicAdd(counter, (unsigned long long)mine);
+}
+
+SVCM_D void addPixel(float *accum, uint32_t pixel, f3 c)
+{
+    float *p = accum + 3ull * pixel;
+    if(c.x != 0.f) atomicAdd(p + 0, c.x);
+    if(c.y != 0.f) atomicAdd(p + 1, c.y);
+    if(c.z != 0.f) atomicAdd(p + 2, c.z);
+}
+
+SVCM_D float4 mk4(f3 a, float w) { return make_float4(a.x, a.y, a.z, w); }
+SVCM_D f3 xyz(float4 a) { return mk3(a.x, a.y, a.z); }
+
+
+// the particle set of one grid build: a single device-counted array, or the padded segments of
+// an all-gather
+SVCM_D uint32_t mergeSetTotal(const MergeSet &set)
+{
+    if(set.singleCount) return uint32_t(min(*set.singleCount, (unsigned long long)set.capacity));
+    return set.numSegs * set.segStride;
+}
+SVCM_D bool mergeSetValid(const MergeSet &set, uint32_t i)
+{
+    if(set.singleCount) return true;
+    const uint32_t seg = i / set.segStride;
+    return (i - seg * set.segStride) < set.segCount[seg];
+}
+
+// HashGrid::GetCellIndex(Vec3i), reference src/hashgrid.hxx:179-187
+SVCM_D uint32_t cellHash(int32_t cx, int32_t cy, int32_t cz, uint32_t numCells)
+{
+    return ((uint32_t(cx) * 73856093u) ^ (uint32_t(cy) * 19349663u) ^ (uint32_t(cz) * 83492791u)) % numCells;
+}
+
+
+// persistent-style grid: a multiple of the SM count, capped by the work available
+int numSMs();
+uint32_t gridFor(uint64_t items, int perBlock, int blocksPerSM);
+
+} // namespace svcm
+#endif

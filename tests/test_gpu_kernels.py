@@ -132,9 +132,16 @@ def cells_as_sets(ends, idx):
     return [frozenset(idx[s:e].tolist()) for s, e in zip(starts, ends) if e > s]
 
 
+LAYOUTS = ["bucket", "cell"]
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
 @pytest.mark.parametrize("scene_id,alg,w", [(1, "vcm", 96), (3, "bpm", 128), (2, "vcm", 64)])
-def test_hashgrid_build_exact(scene_id, alg, w):
-    """HashGrid::Build: bbox, mCellEnds and per-cell membership identical to the oracle."""
+def test_hashgrid_build_exact(scene_id, alg, w, layout, monkeypatch):
+    """HashGrid::Build: bbox, mCellEnds and per-cell membership identical to the oracle — in the
+    reference's bucket order, and restated from the cell-ordered layout (the device supplies the
+    bucket of every sorted particle and the per-bucket histogram)."""
+    monkeypatch.setenv("SVCM_GRID_LAYOUT", layout)
     scene, orc = oracle_iteration(scene_id, alg, w)
     verts = orc.light_vertices()[0]
     radius = orc.iteration_constants(0)[0]
@@ -149,7 +156,10 @@ def test_hashgrid_build_exact(scene_id, alg, w):
     assert ends[-1] == len(verts) and (np.diff(ends) >= 0).all()
 
 
-def test_hashgrid_edge_cases():
+@pytest.mark.parametrize("layout,variant", [("bucket", "1"), ("cell", "0"), ("cell", "1"), ("cell", "2"), ("cell", "3")])
+def test_hashgrid_edge_cases(layout, variant, monkeypatch):
+    monkeypatch.setenv("SVCM_GRID_LAYOUT", layout)
+    monkeypatch.setenv("SVCM_MERGE_VARIANT", variant)
     scene = sv.Scene.cornell_box(1, 32, 32)
     # empty vertex set: bbox stays (+1e36, -1e36), every query is rejected
     grid = sv.hashgrid_build(np.zeros(0, abi.MERGE_VERTEX_DTYPE), 0.01, 64)
@@ -176,15 +186,21 @@ def test_hashgrid_edge_cases():
     assert close(gc, oc).all()
 
 
-@pytest.mark.parametrize("merge_kernel", ["1", "8", "32"])
+@pytest.mark.parametrize("merge_kernel", ["1", "8", "32", "cell0", "cell1", "cell2", "cell3"])
 @pytest.mark.parametrize("scene_id,alg,w,ppm", [(1, "vcm", 128, False), (3, "bpm", 128, False), (1, "ppm", 96, True),
                                                 (0, "vcm", 96, False)])
 def test_hashgrid_query_against_oracle(scene_id, alg, w, ppm, merge_kernel, monkeypatch):
     """HashGrid::Process + RangeQuery::Process on the oracle's light vertices: visited and
     accepted counts exact, merged radiance within 1e-5 relative."""
     from test_oracle import synthetic_queries
-    # both merge kernels (lane-per-query with compaction, cooperative groups) are product code
-    monkeypatch.setenv("SVCM_MERGE_GROUP", merge_kernel)
+    # every merge kernel is product code: bucket layout (lane-per-query with compaction, cooperative
+    # groups) and cell layout (lane-per-query, staged with bulk copies / plain loads / small stages)
+    if merge_kernel.startswith("cell"):
+        monkeypatch.setenv("SVCM_GRID_LAYOUT", "cell")
+        monkeypatch.setenv("SVCM_MERGE_VARIANT", merge_kernel[4:])
+    else:
+        monkeypatch.setenv("SVCM_GRID_LAYOUT", "bucket")
+        monkeypatch.setenv("SVCM_MERGE_GROUP", merge_kernel)
     scene, orc = oracle_iteration(scene_id, alg, w)
     verts, _, mats, normals, _ = orc.light_vertices()
     radius, _, _, mis_vc = orc.iteration_constants(0)
@@ -207,3 +223,33 @@ def test_hashgrid_query_against_oracle(scene_id, alg, w, ppm, merge_kernel, monk
     gc2, _ = grid.query(scene, q, 3, 4, mis_vc, ppm)
     assert (np.abs(gc2 - oc2) / (np.abs(oc2).max(1, keepdims=True) + 1e-30)).max() < 2e-5
     assert np.abs(oc2).sum() < np.abs(oc).sum()
+
+
+@pytest.mark.parametrize("layout,variant", [("bucket", "1"), ("cell", "0"), ("cell", "1"), ("cell", "2")])
+@pytest.mark.parametrize("num_cells", [2, 7, 64, 1000])
+def test_hashgrid_bucket_collisions(num_cells, layout, variant, monkeypatch):
+    """With few buckets most queries see two or more of their 8 cells share a bucket; the reference
+    visits such a bucket once per cell (src/hashgrid.hxx:142-155) and counts its in-range particles
+    that often. Visited and accepted counts must stay exact in every layout."""
+    from test_oracle import synthetic_queries
+    monkeypatch.setenv("SVCM_GRID_LAYOUT", layout)
+    monkeypatch.setenv("SVCM_MERGE_VARIANT", variant)
+    scene, orc = oracle_iteration(1, "vcm", 64)
+    verts, _, mats, normals, _ = orc.light_vertices()
+    radius, _, _, mis_vc = orc.iteration_constants(0)
+    radius *= 2.0
+    q = synthetic_queries(verts, normals, mats, 20000, 7, radius * 0.6)
+    orc.set_light_vertices(verts, radius, num_cells, mis_vc, False, 10, 0)
+    oc, on = orc.merge_queries(q, True)
+    grid = sv.hashgrid_build(verts, radius, num_cells)
+    bbox, ends, idx = grid.download()
+    obbox, oends, oidx = orc.grid(num_cells)
+    assert np.array_equal(ends, oends) and cells_as_sets(ends, idx) == cells_as_sets(oends, oidx)
+    gc, gn = grid.query(scene, q, 0, 10, mis_vc, False)
+    assert np.array_equal(gn, on)
+    # collisions really happen: more accepted visits than distinct in-range particles
+    orc.set_light_vertices(verts, radius, 1 << 24, mis_vc, False, 10, 0)
+    _, on_sparse = orc.merge_queries(q, True)
+    assert on[:, 1].sum() > on_sparse[:, 1].sum()
+    scale = np.abs(oc).max(1, keepdims=True) + 1e-30
+    assert (np.abs(gc - oc) / scale).max() < 2e-5

@@ -40,9 +40,15 @@ def rel_l2(a, b):
                  np.linalg.norm(b.astype(np.float64)))
 
 
-def render(scene, alg, iterations, seed=1234, max_len=10, min_len=0, first=0, **kw):
+def render(scene, alg, iterations, seed=1234, max_len=10, min_len=0, first=0, layout=None, variant=None, **kw):
     r = sv.VertexCM(scene, alg, seed=seed, **kw)
     r.max_path_length, r.min_path_length = max_len, min_len
+    # mergeCandidates in the reference's convention (buckets visited) whatever the particle order
+    r.set_option(abi.OPT_REF_CANDIDATES, 1)
+    if layout is not None:
+        r.set_option(abi.OPT_GRID_LAYOUT, layout)
+    if variant is not None:
+        r.set_option(abi.OPT_MERGE_VARIANT, variant)
     r.run_iterations(first, iterations)
     img, n = r.accum()
     st = r.stats()
@@ -73,6 +79,30 @@ def test_t2_same_stream_parity(scene_id, alg):
                       ("mergeQueries", "mergeQueries"), ("mergeCandidates", "mergeCandidates"),
                       ("mergeAccepted", "mergeAccepted")]:
         assert abs(st[key] - cnt[okey]) <= 2e-3 * cnt[okey] + 8, (key, st[key], cnt[okey])
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("scene_id,alg", [(1, "vcm"), (3, "bpm"), (1, "ppm"), (2, "vcm"), (0, "vcm")])
+def test_t2_cell_layout_parity(scene_id, alg, variant):
+    """T2 with the particles in true cell order (every merge variant) and, for comparison, in the
+    reference's bucket order: same bars, and the two layouts agree with each other to summation order."""
+    w, iters = 128, 3
+    scene = sv.Scene.cornell_box(scene_id, w, w)
+    img, n, st = render(scene, alg, iters, layout=abi.GRID_CELL, variant=variant)
+    bucket, _, stb = render(scene, alg, iters, layout=abi.GRID_BUCKET)
+    orc = oa.Oracle(scene, abi.ALGORITHMS[alg], seed=1234, rng_mode=1)
+    for it in range(iters):
+        orc.run_iteration(it)
+    ref, _ = orc.accum()
+    cnt = orc.counters()
+    assert rel_l2(img, ref) <= 6e-2
+    assert rel_l2(img, bucket) < 1e-5
+    pix = np.abs(img - ref).max(2) / (np.abs(ref).max(2) + 1e-3)
+    assert (pix > 1e-3).mean() <= 1e-2
+    for key in ("lightVertices", "mergeQueries", "mergeCandidates", "mergeAccepted"):
+        assert st[key] == stb[key], (key, st[key], stb[key])
+    for key in ("mergeQueries", "mergeCandidates", "mergeAccepted"):
+        assert abs(st[key] - cnt[key]) <= 2e-3 * cnt[key] + 8, (key, st[key], cnt[key])
 
 
 def test_t2_path_length_limits():
