@@ -443,6 +443,31 @@ SVCM_API int svcm_bsdf_sample_batch(const SvcmSceneDesc *scene, const float *in,
                                     int64_t count, int32_t fixIsLight, int32_t device,
                                     float *out, uint32_t *events);
 
+/* The light classes, light `lightIndex` of the scene, 8 floats in and 12 floats out per item
+ * (unused slots are ignored on input and zero on output):
+ *   emit       AbstractLight::Emit (src/lights.hxx:168-196 area, :267-292 directional, :354-375
+ *              point, :438-478 background). in: dirRnd.xy, posRnd.xy. out: energy.rgb, position.xyz,
+ *              direction.xyz, emissionPdfW, directPdfA, cosThetaLight.
+ *   illuminate AbstractLight::Illuminate (:131-166, :244-265, :329-352, :410-436). in:
+ *              receivingPosition.xyz, rnd.xy. out: radiance.rgb, directionToLight.xyz, distance,
+ *              directPdfW, emissionPdfW, cosAtLight (the three pdfs are zero when no radiance comes
+ *              back: the reference leaves them unset there).
+ *   radiance   AbstractLight::GetRadiance (:198-220, :296-304, :377-385, :480-502). in:
+ *              rayDirection.xyz, hitPoint.xyz (unused by every light). out: radiance.rgb, directPdfA,
+ *              emissionPdfW. */
+SVCM_API int svcm_light_emit_batch(const SvcmSceneDesc *scene, int32_t lightIndex, const float *in,
+                                   int64_t count, int32_t device, float *out);
+SVCM_API int svcm_light_illuminate_batch(const SvcmSceneDesc *scene, int32_t lightIndex, const float *in,
+                                         int64_t count, int32_t device, float *out);
+SVCM_API int svcm_light_radiance_batch(const SvcmSceneDesc *scene, int32_t lightIndex, const float *in,
+                                       int64_t count, int32_t device, float *out);
+
+/* Camera::GenerateRay (src/camera.hxx:108-117) and Camera::WorldToRaster + CheckRaster (:95-105).
+ * in, 5 floats: raster.xy of the ray, a world point.xyz. out, 6 floats: ray direction.xyz (the
+ * origin is the camera position), raster.xy of the point, 1 or 0 = inside the image. */
+SVCM_API int svcm_camera_ray_batch(const SvcmSceneDesc *scene, const float *in, int64_t count,
+                                   int32_t device, float *out);
+
 /* The hierarchy svcm_create builds for scenes of more than SVCM_MAX_PRIMITIVES primitives
  * (host code, no GPU needed; exposed for inspection and for the CPU check of the traversal
  * in tests/). Node 0 is the root. Inner node: count == 0, children are nodes `first` and

@@ -363,6 +363,54 @@ REF_API void refctr_bsdf_sample(void *handle, const float *in, long long count,
     }
 }
 
+// The reference's light classes and camera on the same inputs (layouts: include/svcm.h,
+// svcm_light_*_batch / svcm_camera_ray_batch). op 0 Emit, 1 Illuminate, 2 GetRadiance.
+REF_API void refctr_light(void *handle, int op, int lightIndex, const float *in, long long count, float *out)
+{
+    Handle *h = (Handle*)handle;
+    const AbstractLight *l = h->scene->GetLightPtr(lightIndex);
+    const SceneSphere &ss = h->scene->mSceneSphere;
+    for(long long i = 0; i < count; i++)
+    {
+        const float *p = in + 8 * i; float *r = out + 12 * i;
+        for(int k = 0; k < 12; k++) r[k] = 0;
+        if(op == 0)
+        {
+            Vec3f pos(0), dir(0); float emissionPdfW = 0, directPdfA = 0, cosLight = 0;
+            const Vec3f e = l->Emit(ss, Vec2f(p[0], p[1]), Vec2f(p[2], p[3]), pos, dir, emissionPdfW, &directPdfA, &cosLight);
+            Put3(r, e); Put3(r + 3, pos); Put3(r + 6, dir);
+            r[9] = emissionPdfW; r[10] = directPdfA; r[11] = cosLight;
+        }
+        else if(op == 1)
+        {
+            Vec3f dir(0); float dist = 0, directPdfW = 0, emissionPdfW = 0, cosAtLight = 0;
+            const Vec3f e = l->Illuminate(ss, Get3(p), Vec2f(p[3], p[4]), dir, dist, directPdfW, &emissionPdfW, &cosAtLight);
+            Put3(r, e); Put3(r + 3, dir); r[6] = dist;
+            if(!e.IsZero()) { r[7] = directPdfW; r[8] = emissionPdfW; r[9] = cosAtLight; }
+        }
+        else
+        {
+            float directPdfA = 0, emissionPdfW = 0;
+            const Vec3f e = l->GetRadiance(ss, Get3(p), Get3(p + 3), &directPdfA, &emissionPdfW);
+            Put3(r, e); r[3] = directPdfA; r[4] = emissionPdfW;
+        }
+    }
+}
+
+REF_API void refctr_camera(void *handle, const float *in, long long count, float *out)
+{
+    Handle *h = (Handle*)handle;
+    const Camera &cam = h->scene->mCamera;
+    for(long long i = 0; i < count; i++)
+    {
+        const float *p = in + 5 * i; float *r = out + 6 * i;
+        const Ray ray = cam.GenerateRay(Vec2f(p[0], p[1]));
+        const Vec2f raster = cam.WorldToRaster(Get3(p + 2));
+        Put3(r, ray.dir); r[3] = raster.x; r[4] = raster.y;
+        r[5] = cam.CheckRaster(raster) ? 1.f : 0.f;
+    }
+}
+
 // the replaced generator, for pinning the three restatements of it against each other
 REF_API void refctr_rng_stream(int seed, int iteration, int phase, unsigned firstPath,
                                int paths, int draws, float *out)

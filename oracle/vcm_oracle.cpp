@@ -921,8 +921,19 @@ struct Oracle
     HashGrid                 grid;
     float                    lastRadius;
     Counters                 cnt;
+    // Path-parallel iterations (RunIterationParallel, per-path random streams only): a worker is a
+    // copy of the renderer that traces a contiguous block of path indices into PRIVATE light
+    // vertices / framebuffer / counters; in the camera phase it reads the master's complete light
+    // vertices, path ends and grid through these views. A serial renderer views itself.
+    const std::vector<LightVertex> *lvView;
+    const std::vector<int>         *peView;
+    const HashGrid                 *gridView;
+    int                             pathBase;     // first path index of a worker's block (pathEnds is block-local)
+    std::vector<Oracle*>            workers;
 
-    Oracle(int seed, int rngMode) : rng(seed, rngMode) {}
+    Oracle(int seed, int rngMode) : rng(seed, rngMode), lvView(&lightVertices), peView(&pathEnds),
+        gridView(&grid), pathBase(0) {}
+    ~Oracle() { for(size_t i = 0; i < workers.size(); i++) delete workers[i]; }
 
     float Mis(float pdf) const { return pdf; }   // balance heuristic, src/vertexcm.hxx:553-557
 
@@ -972,6 +983,8 @@ struct Oracle
                   long long *oQueries, long long *oCandidates, long long *oAccepted) const
     {
         V3 contrib(0);
+        const HashGrid &grid = *gridView;
+        const std::vector<LightVertex> &lightVertices = *lvView;
         const V3 distMin = queryPos - grid.bboxMin;
         const V3 distMax = grid.bboxMax - queryPos;
         if(distMin.x < 0.f || distMax.x < 0.f) return contrib;
@@ -1339,7 +1352,7 @@ struct Oracle
             if(st.pathLength + 2 > maxPathLength) break;
             if(!SampleScattering(bsdf, hitPoint, st)) break;
         }
-        pathEnds[pathIdx] = int(lightVertices.size());
+        pathEnds[pathIdx - pathBase] = int(lightVertices.size());
     }
 
     // one camera sub-path, src/vertexcm.hxx:415-545 (loop body)
@@ -1398,6 +1411,8 @@ struct Oracle
 
             if(!bsdf.isDelta && useVC)
             {
+                const std::vector<int> &pathEnds = *peView;
+                const std::vector<LightVertex> &lightVertices = *lvView;
                 const int begin = (pathIdx == 0) ? 0 : pathEnds[pathIdx - 1];
                 const int end   = pathEnds[pathIdx];
                 for(int i = begin; i < end; i++)
@@ -1621,6 +1636,90 @@ struct Oracle
 
         iterations++;
     }
+
+    // The same iteration with the path loops of src/vertexcm.hxx:321-396 and :415-545 split into
+    // `threads` contiguous blocks. Only meaningful with per-path random streams (rng mode 1), where
+    // a path's result does not depend on which paths ran before it. Light vertices and path ends
+    // come out in path order exactly as in RunIteration; framebuffer contributions are summed
+    // per block and the blocks added in order, so the image differs from RunIteration's only in
+    // the order of float additions.
+    void RunIterationParallel(int aIteration, int threads)
+    {
+        const int pathCount = resX * resY;
+        threads = std::max(1, std::min(threads, std::max(1, pathCount / 64)));
+        if(threads == 1 || rng.mMode != 1) { RunIteration(aIteration); return; }
+        const bool walkOnly = algorithm == SVCM_ALG_PATH_TRACE || algorithm == SVCM_ALG_EYE_LIGHT;
+        const float radius = walkOnly ? 0.f : SetupIteration(aIteration);
+        memset(&cnt, 0, sizeof(cnt));
+        while(int(workers.size()) < threads)
+        {
+            Oracle *w = new Oracle(int(rng.mSeed), rng.mMode);
+            w->scene = scene;
+            workers.push_back(w);
+        }
+        for(int t = 0; t < threads; t++)
+        {
+            Oracle *w = workers[t];
+            w->useVM = useVM; w->useVC = useVC; w->lightTraceOnly = lightTraceOnly; w->ppm = ppm;
+            w->algorithm = algorithm;
+            w->radiusAlpha = radiusAlpha; w->baseRadius = baseRadius;
+            w->misVmWeightFactor = misVmWeightFactor; w->misVcWeightFactor = misVcWeightFactor;
+            w->screenPixelCount = screenPixelCount; w->lightSubPathCount = lightSubPathCount;
+            w->vmNormalization = vmNormalization;
+            w->maxPathLength = maxPathLength; w->minPathLength = minPathLength;
+            w->resX = resX; w->resY = resY; w->lastRadius = lastRadius;
+            w->framebuffer.assign(framebuffer.size(), V3(0));
+            memset(&w->cnt, 0, sizeof(w->cnt));
+            w->pathBase = int((long long)pathCount * t / threads);
+            w->lightVertices.clear();
+            w->pathEnds.assign(size_t((long long)pathCount * (t + 1) / threads - w->pathBase), 0);
+            w->lvView = &lightVertices; w->peView = &pathEnds; w->gridView = &grid;
+        }
+        omp_set_num_threads(threads);
+        if(!walkOnly)
+        {
+#pragma omp parallel for schedule(static, 1)
+            for(int t = 0; t < threads; t++)
+            {
+                Oracle *w = workers[t];
+                const int lo = w->pathBase, hi = lo + int(w->pathEnds.size());
+                for(int pathIdx = lo; pathIdx < hi; pathIdx++) w->TraceLightPath(aIteration, pathIdx);
+            }
+            pathEnds.assign(pathCount, 0);
+            lightVertices.clear();
+            for(int t = 0; t < threads; t++)
+            {
+                Oracle *w = workers[t];
+                const int offset = int(lightVertices.size());
+                lightVertices.insert(lightVertices.end(), w->lightVertices.begin(), w->lightVertices.end());
+                for(size_t k = 0; k < w->pathEnds.size(); k++) pathEnds[size_t(w->pathBase) + k] = offset + w->pathEnds[k];
+                w->lightVertices.clear(); w->lightVertices.shrink_to_fit();
+            }
+            if(useVM) grid.Build(lightVertices, radius, pathCount);
+        }
+        else lightVertices.clear();
+#pragma omp parallel for schedule(static, 1)
+        for(int t = 0; t < threads; t++)
+        {
+            Oracle *w = workers[t];
+            const int lo = w->pathBase, hi = lo + int(w->pathEnds.size());
+            for(int pathIdx = lo; pathIdx < hi && !lightTraceOnly; pathIdx++)
+            {
+                if(algorithm == SVCM_ALG_PATH_TRACE)     w->TracePathTracerPixel(aIteration, pathIdx);
+                else if(algorithm == SVCM_ALG_EYE_LIGHT) w->TraceEyeLightPixel(aIteration, pathIdx);
+                else                                     w->TraceCameraPath(aIteration, pathIdx);
+            }
+        }
+        for(int t = 0; t < threads; t++)
+        {
+            Oracle *w = workers[t];
+            for(size_t k = 0; k < framebuffer.size(); k++) framebuffer[k] = framebuffer[k] + w->framebuffer[k];
+            cnt.lightRays += w->cnt.lightRays; cnt.cameraRays += w->cnt.cameraRays; cnt.shadowRays += w->cnt.shadowRays;
+            cnt.mergeQueries += w->cnt.mergeQueries; cnt.mergeCandidates += w->cnt.mergeCandidates;
+            cnt.mergeAccepted += w->cnt.mergeAccepted; cnt.connections += w->cnt.connections;
+        }
+        iterations++;
+    }
 };
 
 void CopyScene(const SvcmSceneDesc *d, Scene &s)
@@ -1700,6 +1799,13 @@ ORACLE_API void *oracle_create(const SvcmSceneDesc *scene, int algorithm, float 
 ORACLE_API void oracle_destroy(void *h) { delete (Oracle*)h; }
 
 ORACLE_API void oracle_run_iteration(void *h, int iteration) { ((Oracle*)h)->RunIteration(iteration); }
+
+// Path-parallel iteration (per-path random streams only; falls back to the serial loop otherwise).
+// threads <= 0: all hardware threads.
+ORACLE_API void oracle_run_iteration_parallel(void *h, int iteration, int threads)
+{
+    ((Oracle*)h)->RunIterationParallel(iteration, threads > 0 ? threads : omp_get_num_procs());
+}
 
 ORACLE_API int oracle_accum(void *h, float *outRgb)
 {
@@ -1872,6 +1978,55 @@ ORACLE_API void oracle_bsdf_sample(void *h, const float *in, long long count, in
         if(IsZero(f)) continue;
         Store3(r, f); Store3(r + 3, dirGen); r[6] = pdfW; r[7] = cosGen;
         events[i] = ev;
+    }
+}
+
+// The light classes and the camera on random inputs (layouts: include/svcm.h, svcm_light_*_batch
+// and svcm_camera_ray_batch). op 0 Emit, 1 Illuminate, 2 GetRadiance.
+ORACLE_API void oracle_light(void *h, int op, int lightIndex, const float *in, long long count, float *out)
+{
+    Oracle *o = (Oracle*)h;
+    const SvcmLight &l = o->scene.lights[size_t(lightIndex)];
+    for(long long i = 0; i < count; i++)
+    {
+        const float *p = in + 8 * i; float *r = out + 12 * i;
+        for(int k = 0; k < 12; k++) r[k] = 0;
+        if(op == 0)
+        {
+            V3 pos(0), dir(0); float emissionPdfW = 0, directPdfA = 0, cosLight = 0;
+            const V3 e = LightEmit(l, o->scene.sphere, p[0], p[1], p[2], p[3], pos, dir, emissionPdfW, directPdfA, cosLight);
+            Store3(r, e); Store3(r + 3, pos); Store3(r + 6, dir);
+            r[9] = emissionPdfW; r[10] = directPdfA; r[11] = cosLight;
+        }
+        else if(op == 1)
+        {
+            V3 dir(0); float dist = 0, directPdfW = 0, emissionPdfW = 0, cosAtLight = 0;
+            const V3 e = LightIlluminate(l, o->scene.sphere, Load3(p), p[3], p[4], dir, dist, directPdfW,
+                                         emissionPdfW, cosAtLight);
+            Store3(r, e); Store3(r + 3, dir); r[6] = dist;
+            if(!IsZero(e)) { r[7] = directPdfW; r[8] = emissionPdfW; r[9] = cosAtLight; }
+        }
+        else
+        {
+            float directPdfA = 0, emissionPdfW = 0;
+            const V3 e = LightGetRadiance(l, o->scene.sphere, Load3(p), directPdfA, emissionPdfW);
+            Store3(r, e); r[3] = directPdfA; r[4] = emissionPdfW;
+        }
+    }
+}
+
+ORACLE_API void oracle_camera(void *h, const float *in, long long count, float *out)
+{
+    Oracle *o = (Oracle*)h;
+    const SvcmCamera &cam = o->scene.camera;
+    for(long long i = 0; i < count; i++)
+    {
+        const float *p = in + 5 * i; float *r = out + 6 * i;
+        const V3 camPos = Load3(cam.position);
+        const V3 dir = Normalize(TransformPoint(cam.rasterToWorld, V3(p[0], p[1], 0)) - camPos);   // src/camera.hxx:108-117
+        const V3 raster = TransformPoint(cam.worldToRaster, Load3(p + 2));                          // :95-99
+        Store3(r, dir); r[3] = raster.x; r[4] = raster.y;
+        r[5] = (raster.x >= 0 && raster.y >= 0 && raster.x < cam.resolution[0] && raster.y < cam.resolution[1]) ? 1.f : 0.f;
     }
 }
 

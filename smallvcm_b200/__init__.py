@@ -10,8 +10,9 @@ and never computes anything itself — without the compiled library it raises.
 from . import abi
 from .renderer import (Scene, VertexCM, SvcmError, load_library, library_path, hashgrid_build,
                        intersect_batch, occluded_batch, bsdf_evaluate_batch, bsdf_sample_batch,
+                       light_batch, camera_ray_batch,
                        rng_stream, rng_stream_device, image_convert_batch, image_header, comm_unique_id, SCENE_NAMES)
 
 __all__ = ["abi", "Scene", "VertexCM", "SvcmError", "load_library", "library_path",
            "hashgrid_build", "intersect_batch", "occluded_batch", "bsdf_evaluate_batch",
-           "bsdf_sample_batch", "rng_stream", "rng_stream_device", "image_convert_batch", "image_header", "comm_unique_id", "SCENE_NAMES"]
+           "bsdf_sample_batch", "light_batch", "camera_ray_batch", "rng_stream", "rng_stream_device", "image_convert_batch", "image_header", "comm_unique_id", "SCENE_NAMES"]

@@ -154,6 +154,10 @@ PROTOTYPES = {
     "svcm_bsdf_sample_batch": (i32, [PSD, VP, i64, i32, i32, VP, VP]),
     "svcm_rng_stream": (i32, [i32, i32, i32, u32, i32, i32, VP]),
     "svcm_rng_stream_device": (i32, [i32, i32, i32, u32, i32, i32, i32, VP]),
+    "svcm_light_emit_batch": (i32, [PSD, i32, VP, i64, i32, VP]),
+    "svcm_light_illuminate_batch": (i32, [PSD, i32, VP, i64, i32, VP]),
+    "svcm_light_radiance_batch": (i32, [PSD, i32, VP, i64, i32, VP]),
+    "svcm_camera_ray_batch": (i32, [PSD, VP, i64, i32, VP]),
     "svcm_scene_config_mask": (u32, [i32]),
     "svcm_scene_cornell_box": (i32, [u32, i32, i32, C.POINTER(VP), C.POINTER(PSD)]),
     "svcm_scene_free": (None, [VP]),

@@ -1614,6 +1614,52 @@ int svcm_bsdf_sample_batch(const SvcmSceneDesc *scene, const float *in, int64_t 
     return cudaDone(e, "svcm_bsdf_sample_batch");
 }
 
+static int lightBatch(const SvcmSceneDesc *scene, int op, int32_t lightIndex, const float *in, int64_t count,
+                      int32_t device, float *out, const char *what)
+{
+    if(count < 0 || !scene || (count && (!in || !out))) return fail(NULL, SVCM_E_INVALID, "bad arguments");
+    if(lightIndex < 0 || lightIndex >= scene->numLights) return fail(NULL, SVCM_E_INVALID, "light %d out of range", lightIndex);
+    DevScene sc; int rc = batchPrologue(scene, device, sc, NULL); if(rc) return rc;
+    if(count == 0) return SVCM_OK;
+    Scratch s; cudaError_t e = cudaSuccess; const size_t n = size_t(count);
+    float *dIn = s.alloc<float>(n * 8, e); float *dOut = s.alloc<float>(n * 12, e);
+    if(e == cudaSuccess) e = cudaMemcpy(dIn, in, sizeof(float) * 8 * n, cudaMemcpyHostToDevice);
+    if(e == cudaSuccess)
+    {
+        launchLightBatch(sc, op, lightIndex, dIn, count, dOut, 0);
+        e = cudaMemcpy(out, dOut, sizeof(float) * 12 * n, cudaMemcpyDeviceToHost);
+    }
+    return cudaDone(e, what);
+}
+
+int svcm_light_emit_batch(const SvcmSceneDesc *scene, int32_t lightIndex, const float *in, int64_t count,
+                          int32_t device, float *out)
+{ return lightBatch(scene, 0, lightIndex, in, count, device, out, "svcm_light_emit_batch"); }
+
+int svcm_light_illuminate_batch(const SvcmSceneDesc *scene, int32_t lightIndex, const float *in, int64_t count,
+                                int32_t device, float *out)
+{ return lightBatch(scene, 1, lightIndex, in, count, device, out, "svcm_light_illuminate_batch"); }
+
+int svcm_light_radiance_batch(const SvcmSceneDesc *scene, int32_t lightIndex, const float *in, int64_t count,
+                              int32_t device, float *out)
+{ return lightBatch(scene, 2, lightIndex, in, count, device, out, "svcm_light_radiance_batch"); }
+
+int svcm_camera_ray_batch(const SvcmSceneDesc *scene, const float *in, int64_t count, int32_t device, float *out)
+{
+    if(count < 0 || !scene || (count && (!in || !out))) return fail(NULL, SVCM_E_INVALID, "bad arguments");
+    DevScene sc; int rc = batchPrologue(scene, device, sc, NULL); if(rc) return rc;
+    if(count == 0) return SVCM_OK;
+    Scratch s; cudaError_t e = cudaSuccess; const size_t n = size_t(count);
+    float *dIn = s.alloc<float>(n * 5, e); float *dOut = s.alloc<float>(n * 6, e);
+    if(e == cudaSuccess) e = cudaMemcpy(dIn, in, sizeof(float) * 5 * n, cudaMemcpyHostToDevice);
+    if(e == cudaSuccess)
+    {
+        launchCameraBatch(sc, dIn, count, dOut, 0);
+        e = cudaMemcpy(out, dOut, sizeof(float) * 6 * n, cudaMemcpyDeviceToHost);
+    }
+    return cudaDone(e, "svcm_camera_ray_batch");
+}
+
 int svcm_rng_stream(int32_t seed, int32_t iteration, int32_t phase, uint32_t firstPath, int32_t paths, int32_t draws,
                     float *out)
 {

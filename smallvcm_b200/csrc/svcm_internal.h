@@ -263,6 +263,11 @@ void launchBsdfEvaluateBatch(const DevScene &sc, const float *in, int64_t count,
                              float *out, cudaStream_t stream);
 void launchBsdfSampleBatch(const DevScene &sc, const float *in, int64_t count, int fixIsLight,
                            float *out, uint32_t *events, cudaStream_t stream);
+// op 0 Emit, 1 Illuminate, 2 GetRadiance of light `lightIndex`: 8 floats in, 12 out per item
+void launchLightBatch(const DevScene &sc, int op, int lightIndex, const float *in, int64_t count, float *out,
+                      cudaStream_t stream);
+// Camera::GenerateRay + WorldToRaster: 5 floats in, 6 out per item
+void launchCameraBatch(const DevScene &sc, const float *in, int64_t count, float *out, cudaStream_t stream);
 // svcm_bvh.cpp: hierarchy over a primitive list; order[slot] = original index. 0 on success.
 int bvhBuild(const SvcmPrimitive *prims, int32_t count, std::vector<BvhNode> &nodes, std::vector<int32_t> &order);
 

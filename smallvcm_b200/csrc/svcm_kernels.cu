@@ -1508,6 +1508,55 @@ __global__ void k_bsdfSampleBatch(const __grid_constant__ DevScene sc, const flo
     }
 }
 
+// AbstractLight::Emit / Illuminate / GetRadiance of light `lightIndex` on `count` inputs of 8
+// floats, 12 floats out (layouts: include/svcm.h, svcm_light_*_batch)
+__global__ void k_lightBatch(const __grid_constant__ DevScene sc, int op, int lightIndex, const float *in, int64_t count,
+                             float *out)
+{
+    const DevLight &l = sc.lights[lightIndex];
+    for(int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x)
+    {
+        const float *p = in + 8 * i; float *r = out + 12 * i;
+        for(int k = 0; k < 12; k++) r[k] = 0.f;
+        if(op == 0)
+        {
+            f3 pos = mk3(0.f), dir = mk3(0.f); float emissionPdfW = 0.f, directPdfA = 0.f, cosLight = 0.f;
+            const f3 e = lightEmit(sc, l, p[0], p[1], p[2], p[3], pos, dir, emissionPdfW, directPdfA, cosLight);
+            r[0] = e.x; r[1] = e.y; r[2] = e.z; r[3] = pos.x; r[4] = pos.y; r[5] = pos.z;
+            r[6] = dir.x; r[7] = dir.y; r[8] = dir.z; r[9] = emissionPdfW; r[10] = directPdfA; r[11] = cosLight;
+        }
+        else if(op == 1)
+        {
+            f3 dir = mk3(0.f); float dist = 0.f, directPdfW = 0.f, emissionPdfW = 0.f, cosAtLight = 0.f;
+            const f3 e = lightIlluminate(sc, l, ld3(p), p[3], p[4], dir, dist, directPdfW, emissionPdfW, cosAtLight);
+            r[0] = e.x; r[1] = e.y; r[2] = e.z; r[3] = dir.x; r[4] = dir.y; r[5] = dir.z; r[6] = dist;
+            // the pdfs are only defined when radiance comes back (src/lights.hxx:150-152 returns early)
+            if(!iszero(e)) { r[7] = directPdfW; r[8] = emissionPdfW; r[9] = cosAtLight; }
+        }
+        else
+        {
+            float directPdfA = 0.f, emissionPdfW = 0.f;
+            const f3 e = lightRadiance(sc, l, ld3(p), directPdfA, emissionPdfW);
+            r[0] = e.x; r[1] = e.y; r[2] = e.z; r[3] = directPdfA; r[4] = emissionPdfW;
+        }
+    }
+}
+
+// Camera::GenerateRay (src/camera.hxx:108-117) of a raster position and Camera::WorldToRaster +
+// CheckRaster (:95-105) of a world point: 5 floats in, 6 out
+__global__ void k_cameraBatch(const __grid_constant__ DevScene sc, const float *in, int64_t count, float *out)
+{
+    for(int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x)
+    {
+        const float *p = in + 5 * i; float *r = out + 6 * i;
+        const f3 camPos = ld3(sc.camPos);
+        const f3 dir = normalize(transformPoint(sc.rasterToWorld, mk3(p[0], p[1], 0.f)) - camPos);
+        const f3 raster = transformPoint(sc.worldToRaster, ld3(p + 2));
+        r[0] = dir.x; r[1] = dir.y; r[2] = dir.z; r[3] = raster.x; r[4] = raster.y;
+        r[5] = (raster.x >= 0.f && raster.y >= 0.f && raster.x < sc.resX && raster.y < sc.resY) ? 1.f : 0.f;
+    }
+}
+
 __global__ void k_rngStream(uint32_t key, uint32_t firstPath, int paths, int draws, float *out)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1709,6 +1758,17 @@ void launchBsdfSampleBatch(const DevScene &sc, const float *in, int64_t count, i
     const uint32_t gridN = gridFor(count, SVCM_BLOCK, 8);
     if(fixIsLight) k_bsdfSampleBatch<true><<<gridN, SVCM_BLOCK, 0, stream>>>(sc, in, count, out, events);
     else           k_bsdfSampleBatch<false><<<gridN, SVCM_BLOCK, 0, stream>>>(sc, in, count, out, events);
+}
+void launchLightBatch(const DevScene &sc, int op, int lightIndex, const float *in, int64_t count, float *out,
+                      cudaStream_t stream)
+{
+    if(count <= 0) return;
+    k_lightBatch<<<gridFor(count, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, op, lightIndex, in, count, out);
+}
+void launchCameraBatch(const DevScene &sc, const float *in, int64_t count, float *out, cudaStream_t stream)
+{
+    if(count <= 0) return;
+    k_cameraBatch<<<gridFor(count, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, in, count, out);
 }
 // ------------------------------------------------------------------------------------------
 // image conversions after the path: the 8-bit images main() writes

@@ -340,6 +340,23 @@ def bsdf_sample_batch(scene, items, fix_is_light, device=0):
     return out, ev
 
 
+def light_batch(scene, op, light_index, items, device=0):
+    """op in ("emit", "illuminate", "radiance"): svcm_light_*_batch, items [n, 8] -> [n, 12]."""
+    items = np.ascontiguousarray(items, np.float32).reshape(-1, 8)
+    out = np.zeros((len(items), 12), np.float32)
+    fn = getattr(load_library(), "svcm_light_%s_batch" % op)
+    _check(fn(C.byref(scene.desc), int(light_index), _ptr(items), len(items), device, _ptr(out)))
+    return out
+
+
+def camera_ray_batch(scene, items, device=0):
+    """svcm_camera_ray_batch: items [n, 5] (raster.xy, world point) -> [n, 6]."""
+    items = np.ascontiguousarray(items, np.float32).reshape(-1, 5)
+    out = np.zeros((len(items), 6), np.float32)
+    _check(load_library().svcm_camera_ray_batch(C.byref(scene.desc), _ptr(items), len(items), device, _ptr(out)))
+    return out
+
+
 def rng_stream(seed, iteration, phase, first_path, paths, draws):
     out = np.zeros((paths, draws), np.float32)
     _check(load_library().svcm_rng_stream(seed, iteration, phase, first_path, paths, draws, _ptr(out)))

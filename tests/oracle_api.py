@@ -44,6 +44,8 @@ _COMMON = {
     "occluded": (None, [VP, VP, i64, VP]),
     "bsdf_evaluate": (None, [VP, VP, i64, i32, VP]),
     "bsdf_sample": (None, [VP, VP, i64, i32, VP, VP]),
+    "light": (None, [VP, i32, i32, VP, i64, VP]),
+    "camera": (None, [VP, VP, i64, VP]),
 }
 
 
@@ -69,8 +71,14 @@ class _Checker:
         except Exception:
             pass
 
-    def run_iteration(self, iteration):
-        self._f("run_iteration")(self._h, iteration)
+    def run_iteration(self, iteration, threads=None):
+        """threads=None: the serial loop. threads=N (0: all hardware threads): the oracle's
+        path-parallel iteration — per-path random streams only, same light vertices and counters,
+        image equal up to the order of float additions (tests/test_oracle.py pins that)."""
+        if threads is None or self._p != "oracle_":
+            self._f("run_iteration")(self._h, iteration)
+        else:
+            oracle_lib().oracle_run_iteration_parallel(self._h, iteration, int(threads))
 
     def accum(self):
         out = np.zeros((self.height, self.width, 3), np.float32)
@@ -143,6 +151,26 @@ class _Checker:
         return out, ev
 
 
+_LIGHT_OPS = {"emit": 0, "illuminate": 1, "radiance": 2}
+
+
+def _light(self, op, light_index, items):
+    items = np.ascontiguousarray(items, np.float32).reshape(-1, 8)
+    out = np.zeros((len(items), 12), np.float32)
+    self._f("light")(self._h, _LIGHT_OPS[op], int(light_index), _ptr(items), len(items), _ptr(out))
+    return out
+
+
+def _camera(self, items):
+    items = np.ascontiguousarray(items, np.float32).reshape(-1, 5)
+    out = np.zeros((len(items), 6), np.float32)
+    self._f("camera")(self._h, _ptr(items), len(items), _ptr(out))
+    return out
+
+
+_Checker.light = _light
+_Checker.camera = _camera
+
 _oracle = None
 
 
@@ -156,6 +184,8 @@ def oracle_lib():
             fn = getattr(lib, "oracle_" + name)
             fn.restype, fn.argtypes = res, args
         lib.oracle_create.restype = VP
+        lib.oracle_run_iteration_parallel.restype = None
+        lib.oracle_run_iteration_parallel.argtypes = [VP, i32, i32]
         lib.oracle_create.argtypes = [PSD, i32, f32, f32, i32, i32, u32, u32]
         lib.oracle_merge_queries.restype = None
         lib.oracle_merge_queries.argtypes = [VP, VP, i64, VP, VP]

@@ -253,3 +253,32 @@ def test_hashgrid_bucket_collisions(num_cells, layout, variant, monkeypatch):
     assert on[:, 1].sum() > on_sparse[:, 1].sum()
     scale = np.abs(oc).max(1, keepdims=True) + 1e-30
     assert (np.abs(gc - oc) / scale).max() < 2e-5
+
+
+@pytest.mark.parametrize("scene_id", [0, 1, 2, 3])
+def test_lights_and_camera(scene_id):
+    """AbstractLight::Emit / Illuminate / GetRadiance for every light of the four scenes
+    (directional, area, point, background) and Camera::GenerateRay / WorldToRaster on random
+    inputs: device functions vs the oracle (itself bit-exact to the reference classes,
+    tests/test_oracle.py). Decisions (zero radiance, inside-the-image) exact, values 1e-5."""
+    from test_oracle import light_camera_inputs
+    rng = np.random.default_rng(70 + scene_id)
+    scene = sv.Scene.cornell_box(scene_id, 96, 64)
+    orc = oa.Oracle(scene, abi.ALG_VCM)
+    emit, illum, rad, cam = light_camera_inputs(rng, scene, 100000)
+    for light in range(scene.desc.numLights):
+        for op, items in (("emit", emit), ("illuminate", illum), ("radiance", rad)):
+            g, o = sv.light_batch(scene, op, light, items), orc.light(op, light, items)
+            assert np.array_equal((g[:, :3] == 0).all(1), (o[:, :3] == 0).all(1)), (light, op)   # same zero / non-zero decision
+            ok = close(g, o, rtol=1e-5, atol=2e-6)
+            # sin/cos of the sphere and disc samplers: a handful of arguments next to a multiple of
+            # pi/2 lose relative accuracy in a component that is ~0 there
+            assert ok.all(1).mean() > 0.9999 and close(g, o, rtol=1e-3, atol=2e-5).all(), (light, op, (~ok).sum())
+    g, o = sv.camera_ray_batch(scene, cam), orc.camera(cam)
+    border = np.minimum(np.abs(o[:, 3:5] - np.round(o[:, 3:5])).min(1), 1.0) < 1e-3     # raster within 1e-3 of a pixel edge
+    assert np.array_equal(g[~border, 5], o[~border, 5])
+    assert close(g[:, :3], o[:, :3], rtol=1e-5, atol=1e-6).all()
+    assert close(g[:, 3:5], o[:, 3:5], rtol=2e-5, atol=1e-3).all()
+    assert sv.light_batch(scene, "emit", 0, np.zeros((0, 8), np.float32)).shape == (0, 12)     # empty input
+    with pytest.raises(sv.SvcmError):
+        sv.light_batch(scene, "emit", 7, emit[:4])
