@@ -115,8 +115,49 @@ def merge_algorithmic_bytes(nq, ncand, nacc):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own path on the host cores
 # ------------------------------------------------------------------------------------------------
+def host_cpu_info():
+    """What the host really offers this process: the CPU model, the CPUs it may be scheduled on
+    (sched_getaffinity) and the cgroup CPU quota (cpu.max) — os.cpu_count() alone says none of it."""
+    info = {"model": None, "os_cpu_count": os.cpu_count(), "affinity": None, "cgroup_cpu_max": None, "quota_cpus": None}
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                info["model"] = line.split(":", 1)[1].strip(); break
+    except Exception:
+        pass
+    try:
+        info["affinity"] = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            text = open(path).read().split()
+            if path.endswith("cpu.max"):
+                info["cgroup_cpu_max"] = " ".join(text)
+                if text[0] != "max":
+                    info["quota_cpus"] = float(text[0]) / float(text[1])
+            else:
+                quota = float(text[0]); period = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                info["cgroup_cpu_max"] = "%d %d" % (quota, period)
+                if quota > 0:
+                    info["quota_cpus"] = quota / period
+            break
+        except Exception:
+            continue
+    try:
+        info["loadavg_1m"] = float(open("/proc/loadavg").read().split()[0])
+    except Exception:
+        pass
+    return info
+
+
 def host_threads():
-    cores = os.cpu_count() or 1
+    """Threads the CPU arm uses: the CPUs this process may run on (affinity, capped by the cgroup
+    quota), and no more renderers than memory holds."""
+    info = host_cpu_info()
+    cores = info["affinity"] or os.cpu_count() or 1
+    if info["quota_cpus"]:
+        cores = max(1, min(cores, int(info["quota_cpus"] + 0.5)))
     try:
         avail_kb = [int(l.split()[1]) for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
         # one private renderer per thread: ~0.6 GB at 1024^2 (vertices 120 B x 2.2 M + vectors + framebuffer)
@@ -179,8 +220,12 @@ def run_reference_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3 / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "paths_per_step": WIDTH * HEIGHT * iters, "seed": SEED,
-                       "radiusFactor": RADIUS_FACTOR, "radiusAlpha": RADIUS_ALPHA},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+                       "radiusFactor": RADIUS_FACTOR, "radiusAlpha": RADIUS_ALPHA,
+                       "iteration_window": [0, iters],
+                       "iteration_window_note": "render() numbers its iterations 0..N-1 (src/smallvcm.cxx:99-108); the "
+                                                "GPU arm times global iterations 0..steps-1, the same radius schedule"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                             "host": host_cpu_info()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -218,6 +263,12 @@ def measure(sv, D, args, rank, world, device, tdev, sharded, want_e2e, clocks=No
     r.set_option(abi.OPT_PROFILE, 1)
     stride = 1 if sharded else world
     state = {"next": first}
+    window_first = first
+
+    def rewind():
+        """Every timed region covers the SAME global iterations (the radius, hence the merge work,
+        shrinks with the iteration index, src/vertexcm.hxx:295-298): 0 .. steps*N - 1."""
+        state["next"] = window_first
 
     def run_steps(n):
         if sharded:
@@ -244,6 +295,7 @@ def measure(sv, D, args, rank, world, device, tdev, sharded, want_e2e, clocks=No
             r.synchronize()
     sync_all()
     r.profile()
+    rewind()
 
     # timed: K steps, device time on the launching stream, max over ranks
     t_begin = time.perf_counter()
@@ -259,7 +311,7 @@ def measure(sv, D, args, rank, world, device, tdev, sharded, want_e2e, clocks=No
     paths_per_step = WIDTH * HEIGHT * world          # both modes: W*H paths per GPU per step
     out = {"value": paths_per_step * args.steps / (ms * 1e-3) / 1e6, "ms_per_step": ms / args.steps,
            "paths_per_step": paths_per_step, "prof": prof, "window": (t_begin, t_end),
-           "iterations_per_step": world}
+           "iterations_per_step": world, "iteration_window": [0, args.steps * world]}
 
     if want_e2e:
         # the plugin's call sequence with a HOST framebuffer every iteration
@@ -267,6 +319,7 @@ def measure(sv, D, args, rank, world, device, tdev, sharded, want_e2e, clocks=No
         lib = sv.load_library()
         lib.svcm_host_register(host_fb.ctypes.data, host_fb.nbytes)     # what VertexCMGpu does once
         st = r.stats()
+        rewind()
         sync_all()
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -286,6 +339,64 @@ def measure(sv, D, args, rank, world, device, tdev, sharded, want_e2e, clocks=No
                               "inputs of a step are the iteration index and the kernel parameter blocks"}
     r.close()
     return out
+
+
+def sharded_parity(sv, D, rank, world, device, tdev, iterations=2, width=512):
+    """rel. L2 between the pixel-sharded render (all ranks, light vertices all-gathered, images
+    summed with svcm_reduce_accum) and ONE GPU rendering the same iterations: the only place the
+    driver's records can show that the N-rank image is the 1-rank image (its test box has one GPU)."""
+    import numpy as np
+    from smallvcm_b200 import abi
+    scene = sv.Scene.cornell_box(SCENE, width, width)
+    r = sv.VertexCM(scene, ALG, radius_factor=RADIUS_FACTOR, radius_alpha=RADIUS_ALPHA, seed=SEED, device=device,
+                    rank=rank, world_size=world)
+    uid = sv.comm_unique_id() if rank == 0 else None
+    r.comm_init(D.broadcast_bytes(uid, abi.COMM_ID_BYTES, 0, tdev))
+    r.max_path_length, r.min_path_length = MAXLEN, MINLEN
+    r.run_iterations(0, iterations)
+    r.reduce_accum(0)
+    img, _ = r.accum()
+    r.close()
+    out = None
+    if rank == 0:
+        one = sv.VertexCM(scene, ALG, radius_factor=RADIUS_FACTOR, radius_alpha=RADIUS_ALPHA, seed=SEED, device=device)
+        one.max_path_length, one.min_path_length = MAXLEN, MINLEN
+        one.run_iterations(0, iterations)
+        ref, _ = one.accum()
+        one.close()
+        out = float(np.linalg.norm(img.astype(np.float64) - ref) / np.linalg.norm(ref.astype(np.float64)))
+    D.barrier(tdev)
+    return out
+
+
+def config5_record(sv, D, rank, world, device, tdev, iterations=2):
+    """BASELINE config #5 (scene 1 vcm 4096^2 maxPathLength 20), ONE iteration strong-scaled over
+    the ranks by the pixel-sharded mode; a bounded side measurement (1 warm-up + `iterations`)."""
+    from smallvcm_b200 import abi
+    W, L = 4096, 20
+    scene = sv.Scene.cornell_box(SCENE, W, W)
+    r = sv.VertexCM(scene, ALG, radius_factor=RADIUS_FACTOR, radius_alpha=RADIUS_ALPHA, seed=SEED, device=device,
+                    rank=rank, world_size=world)
+    if world > 1:
+        uid = sv.comm_unique_id() if rank == 0 else None
+        r.comm_init(D.broadcast_bytes(uid, abi.COMM_ID_BYTES, 0, tdev))
+    r.max_path_length = L
+    r.set_option(abi.OPT_PROFILE, 1)
+    r.run_iterations(0, 1); r.synchronize()
+    if world > 1:
+        D.barrier(tdev)
+    r.profile()
+    r.event_record(0); r.run_iterations(1, iterations); r.event_record(1)
+    ms = r.event_elapsed_ms(0, 1)
+    if world > 1:
+        ms = D.max_over_ranks(ms, tdev)
+    p = r.profile()
+    r.close()
+    n = max(1, p["timedIterations"])
+    return {"workload": "scene 1 -a vcm %dx%d maxPathLength %d, iterations 1..%d" % (W, W, L, iterations), "n_gpus": world,
+            "ms_per_iteration": ms / iterations, "mpaths_s": W * W * iterations / (ms * 1e-3) / 1e6,
+            "stage_ms": {k: p[k] / n for k in ("msLightTrace", "msGather", "msGridBuild", "msCameraTrace", "msMerge")},
+            "light_vertices": p["lightVertices"] / n, "merge_queries": p["mergeQueries"] / n}
 
 
 def run_gpu_arm(args):
@@ -314,6 +425,13 @@ def run_gpu_arm(args):
     clk = clocks.stop(*head["window"]) if clocks is not None else None
     # N > 1: also the pixel-sharded mode with the NCCL all-gather of light vertices
     shard = measure(sv, D, args, rank, world, device, tdev, sharded=True, want_e2e=False) if world > 1 else None
+    parity = sharded_parity(sv, D, rank, world, device, tdev) if world > 1 else None
+    config5 = None
+    if not args.no_config5:
+        try:
+            config5 = config5_record(sv, D, rank, world, device, tdev)
+        except Exception as exc:                      # a side record must never cost the headline
+            config5 = {"error": str(exc)[:200]}
 
     # roofline of the merge kernel (one launch per iteration)
     prof = head["prof"]
@@ -322,25 +440,47 @@ def run_gpu_arm(args):
     merge_ms = prof["msMerge"] / n
     peak, peak_kind = measured_peak_gbs()
     achieved = merge_algorithmic_bytes(nq, ncand, nacc) / (merge_ms * 1e-3) / 1e9 if merge_ms > 0 else 0.0
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "merge_traffic.json")))["dram_bytes_per_launch"]
-    except Exception:
-        pass
+    # DRAM bytes of the merge kernel cannot be read without a profiler: the figure is the committed
+    # ncu capture of this workload on ONE GPU (profiles/merge_traffic.json names kernel, iteration,
+    # commit); it is not reported for N > 1, where every rank runs a different share
+    traffic, traffic_source = None, None
+    if world == 1:
+        try:
+            rec = json.load(open(os.path.join(ROOT, "profiles", "merge_traffic.json")))
+            traffic = rec["dram_bytes_per_launch"]
+            traffic_source = {k: rec.get(k) for k in ("kernel", "iteration", "n_gpus", "captured", "how")}
+        except Exception:
+            pass
     stage = lambda p: {k: p[k] / max(1, p["timedIterations"]) for k in
                        ("msLightTrace", "msGather", "msGridBuild", "msCameraTrace", "msMerge", "msTotal")}
-    roofline = {"kernel": "k_querySort + k_mergeLane (HashGrid::Process + RangeQuery::Process)", "bound": "hbm",
+    st_ms = stage(prof)
+    build_bytes = prof["lightVertices"] / n * 136 + WIDTH * HEIGHT * 8
+    trace_s = (st_ms["msLightTrace"] + st_ms["msCameraTrace"]) * 1e-3
+    rays = {k: prof[k] / n for k in ("lightRays", "cameraRays", "shadowRays")}
+    trace = {"closest_hit_rays_per_iteration": rays["lightRays"] + rays["cameraRays"],
+             "shadow_rays_per_iteration": rays["shadowRays"],
+             "grays_per_s": (rays["lightRays"] + rays["cameraRays"] + rays["shadowRays"]) / trace_s / 1e9 if trace_s > 0 else None,
+             "ms_light_plus_camera": trace_s * 1e3,
+             "note": "light + camera passes (closest-hit rays of both walks, deferred any-hit segments, vertex "
+                     "connection): instruction-bound on 22 primitives in the constant bank, reported as rays/s, not "
+                     "against the HBM roofline (SURVEY 8d)"}
+    roofline = {"kernel": "merge stage: query sort + merge kernel (HashGrid::Process + RangeQuery::Process)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_source,
                 "peak_source": peak_kind, "ms_per_launch": merge_ms, "queries": nq, "candidates": ncand,
                 "accepted": nacc, "algorithmic_bytes_per_launch": merge_algorithmic_bytes(nq, ncand, nacc),
-                "stage_ms_per_iteration": stage(prof)}
+                "stage_ms_per_iteration": st_ms,
+                "grid_build": {"algorithmic_bytes": build_bytes, "ms": st_ms["msGridBuild"],
+                               "achieved": build_bytes / (st_ms["msGridBuild"] * 1e-3) / 1e9 if st_ms["msGridBuild"] > 0 else None,
+                               "frac": build_bytes / (st_ms["msGridBuild"] * 1e-3) / 1e9 / peak if st_ms["msGridBuild"] > 0 else None,
+                               "formula": "N_v*136 + cells*8 (SURVEY 8d)"}}
 
     # CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         v, secs, kind = cpu_reference_step(threads, threads)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "host": host_cpu_info(),
                "sample": "%d iterations of the full %dx%d workload, one private renderer and one iteration per "
                          "thread (the reference's own OpenMP model, src/smallvcm.cxx:61-108), %.1f s wall"
                          % (threads, WIDTH, HEIGHT, secs)}
@@ -352,6 +492,10 @@ def run_gpu_arm(args):
                 "config": {"workload": WORKLOAD, "paths_per_step": head["paths_per_step"],
                            "iterations_per_step": head["iterations_per_step"], "seed": SEED,
                            "radiusFactor": RADIUS_FACTOR, "radiusAlpha": RADIUS_ALPHA,
+                           "iteration_window": head["iteration_window"],
+                           "iteration_window_note": "value and e2e both time global iterations 0..steps*N-1 (warm-up "
+                                                    "runs first, then the index rewinds); the reference arm's render() "
+                                                    "numbers its iterations from 0 as well",
                            "parallelism": "1 GPU" if world == 1 else
                            "%d iteration-parallel replicas (one renderer per GPU, seed + rank, global iteration "
                            "indices interleaved: the reference's own model, src/smallvcm.cxx:61-142); no data-path "
@@ -359,11 +503,14 @@ def run_gpu_arm(args):
                            "l2": "per-iteration working set (path state, light vertices, camera vertices, pair and "
                                  "shadow queues, grid: ~0.8 GB) exceeds the 126 MB L2; no flush needed"},
                 "clocks": clk, "e2e": head["e2e"], "gpu_launches": int(prof["kernelLaunches"]), "roofline": roofline,
-                "cpu_baseline": cpu}
+                "trace": trace, "cpu_baseline": cpu, "config5": config5}
         if shard is not None:
             line["sharded"] = {"value": shard["value"], "unit": UNIT, "ms_per_step": shard["ms_per_step"],
                                "iterations_per_step": world, "stage_ms_per_iteration": stage(shard["prof"]),
                                "gpu_launches": int(shard["prof"]["kernelLaunches"]),
+                               "parity_rel_l2": parity,
+                               "parity_note": "||reduce_accum(N-rank render) - 1-GPU render|| / ||1-GPU render||, scene 1 "
+                                              "vcm 512^2, iterations 0..1 (differs only by the order of float atomics)",
                                "note": "every iteration split over the GPUs by image rows (round robin); per "
                                        "iteration one NCCL all-gather of the 52-byte light-vertex merge records "
                                        "(counts first, then one group of four ncclAllGather) before the grid build; "
@@ -384,6 +531,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs)")
+    ap.add_argument("--no-config5", action="store_true", help="skip the BASELINE config #5 side record")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)
