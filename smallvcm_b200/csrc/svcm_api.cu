@@ -125,13 +125,23 @@ struct svcm_renderer
     GridBuffers grid;
     uint32_t  gridCells, gridCapacity;
     int32_t  *bboxInit;
-    // multi-rank
+    // multi-rank: ONE buffer of worldSize blocks [GatherHeader | posLen | thrVcm | dirVm | contProb];
+    // block `rank` is where the local light pass writes, ncclAllGather fills the others in place
     ncclComm_t comm;
-    float4 *gPosLen, *gThrVcm, *gDirVm; float *gContProb;   // gathered records
-    uint32_t gatherCapacity;        // records per gathered stream
-    unsigned long long *devCounts64;   // [worldSize] per-rank vertex counts (device)
-    unsigned long long *hostCounts64;  // pinned
-    uint32_t *hostCounts;           // clamped copy
+    unsigned char *gatherBuf;
+    size_t   gatherBytes;
+    uint32_t gatherSlots;           // record slots per block the buffer was sized for
+    uint32_t gatherStride;          // record slots per block in use (<= gatherSlots)
+    uint32_t strideMaxLen;          // maxPathLength the stride was chosen for
+    uint32_t lastMaxCount;          // largest per-rank vertex count seen at the last synchronisation (0: unknown)
+    uint32_t *segCountDev;          // [8] valid records per block (device, from the headers)
+    unsigned long long *devCounts64;   // [8] per-rank vertex counts (device, unclamped)
+    unsigned long long *hostCounts64;  // pinned ring [SVCM_PROFILE_RING][8]
+    float    *accumReduced;         // root of svcm_reduce_accum: sum over ranks (accum itself stays per-rank)
+    bool      reducedValid;
+    // the grid is built on its own stream, concurrently with the camera pass
+    cudaStream_t gridStream;
+    cudaEvent_t  evLightDone, evGridDone;
 
     int  iterationsDone;
     int  mergeGroup;
@@ -140,7 +150,9 @@ struct svcm_renderer
     bool refCandidates;             // SVCM_OPT_REF_CANDIDATES
     ScanGen scanGenGrid, scanGenQuery;
     bool profile;
-    cudaEvent_t (*ev)[6];          // [SVCM_PROFILE_RING][6], created when profiling is enabled
+    cudaEvent_t (*ev)[9];          // [SVCM_PROFILE_RING][9], created when profiling is enabled:
+                                   // 0 start, 1 light pass done, 4 camera pass done, 5 merge done (main
+                                   // stream); 6 grid stream starts, 7 gather done, 8 build done
     cudaEvent_t userEv[SVCM_NUM_USER_EVENTS];
     SvcmStats stats;
     bool statsPending;
@@ -283,11 +295,37 @@ int allocQueue(svcm_renderer *r, PathQueue &q, size_t n)
 }
 void freeQueue(PathQueue &q) { devFree(q.s0); devFree(q.s1); devFree(q.s2); devFree(q.s3); }
 
+void freeGather(svcm_renderer *r)
+{
+    devFree(r->gatherBuf);
+    r->gatherBytes = 0; r->gatherSlots = 0; r->gatherStride = 0;
+}
 void freeVerts(svcm_renderer *r)
 {
+    if(r->gatherBuf)
+    {
+        // the merge streams live inside the gather buffer
+        r->verts.posLen = r->verts.thrVcm = r->verts.dirVm = NULL; r->verts.contProb = NULL;
+        freeGather(r);
+    }
     devFree(r->verts.posLen); devFree(r->verts.thrVcm); devFree(r->verts.dirVm); devFree(r->verts.contProb);
     devFree(r->verts.nrmVc); devFree(r->verts.ldfMat); devFree(r->verts.pathVerts);
     r->verts.capacity = 0; r->vertSlots = 0;
+}
+
+// bytes of one all-gather block holding `slots` records, and the stream offsets inside it
+size_t gatherBlockBytes(uint32_t slots) { return (sizeof(GatherHeader) + size_t(slots) * 52u + 255u) & ~size_t(255u); }
+
+// points the local merge streams at block `rank` of the gather buffer laid out for `stride` slots
+void pointGatherStreams(svcm_renderer *r, uint32_t stride)
+{
+    unsigned char *block = r->gatherBuf + size_t(r->params.rank) * gatherBlockBytes(stride);
+    r->verts.posLen   = reinterpret_cast<float4*>(block + sizeof(GatherHeader));
+    r->verts.thrVcm   = r->verts.posLen + stride;
+    r->verts.dirVm    = r->verts.thrVcm + stride;
+    r->verts.contProb = reinterpret_cast<float*>(r->verts.dirVm + stride);
+    r->verts.capacity = stride;
+    r->gatherStride   = stride;
 }
 void freeQueries(svcm_renderer *r)
 {
@@ -302,12 +340,6 @@ void freeGridSorted(svcm_renderer *r)
     devFree(r->grid.sContProb); devFree(r->grid.sIndex);
     r->gridCapacity = 0;
 }
-void freeGather(svcm_renderer *r)
-{
-    devFree(r->gPosLen); devFree(r->gThrVcm); devFree(r->gDirVm); devFree(r->gContProb);
-    r->gatherCapacity = 0;
-}
-
 int ensureGridSorted(svcm_renderer *r, uint32_t capacity)
 {
     if(capacity <= r->gridCapacity) return SVCM_OK;
@@ -395,23 +427,49 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
         freeGridSorted(r);
         cudaMemGetInfo(&freeB, &totalB);
         const uint64_t worst = uint64_t(r->localPaths) * lightBounces;
-        // bytes per vertex: local record 84 + sorted copy/key (60, single rank only grows with it)
+        const uint32_t ws = uint32_t(r->params.worldSize);
+        // bytes per local vertex: merge record 52 + connection extras 32, plus per rank the gathered
+        // copy (sharded runs) and the cell-sorted copy with its key
+        const uint64_t perVertex = 84u + (r->useVM ? (ws > 1u ? 112u * ws : 60u) : 0u) + 6u;
         const uint64_t budget = uint64_t(double(freeB) * 0.45);
-        uint64_t cap = std::min<uint64_t>(worst, budget / 150u);
-        cap = std::min<uint64_t>(cap, 0xFFFFFF00u);
+        uint64_t cap = std::min<uint64_t>(worst, budget / perVertex);
+        cap = std::min<uint64_t>(cap, 0xFFFFFF00u / ws);
         cap = std::max<uint64_t>(cap, std::min<uint64_t>(worst, uint64_t(r->localPaths)));
         cap = (cap + 255u) & ~uint64_t(255u);
-        if((rc = devAlloc(r, &r->verts.posLen, cap))) return rc;
-        if((rc = devAlloc(r, &r->verts.thrVcm, cap))) return rc;
-        if((rc = devAlloc(r, &r->verts.dirVm, cap))) return rc;
-        if((rc = devAlloc(r, &r->verts.contProb, cap))) return rc;
+        if(ws > 1u && r->useVM)
+        {
+            // all-gather blocks, sized once (no reallocation inside the iteration loop)
+            r->gatherBytes = gatherBlockBytes(uint32_t(cap)) * ws;
+            if((rc = devAlloc(r, &r->gatherBuf, r->gatherBytes))) return rc;
+            r->gatherSlots = uint32_t(cap);
+            pointGatherStreams(r, uint32_t(cap));
+            r->lastMaxCount = 0; r->strideMaxLen = 0;
+        }
+        else
+        {
+            if((rc = devAlloc(r, &r->verts.posLen, cap))) return rc;
+            if((rc = devAlloc(r, &r->verts.thrVcm, cap))) return rc;
+            if((rc = devAlloc(r, &r->verts.dirVm, cap))) return rc;
+            if((rc = devAlloc(r, &r->verts.contProb, cap))) return rc;
+        }
         if((rc = devAlloc(r, &r->verts.nrmVc, cap))) return rc;
         if((rc = devAlloc(r, &r->verts.ldfMat, cap))) return rc;
         if((rc = devAlloc(r, &r->verts.pathVerts, size_t(lightBounces) * r->localPaths))) return rc;
         r->verts.capacity = uint32_t(cap);
         r->vertSlots = lightBounces;
-        if(r->useVM && r->params.worldSize == 1)
-            if((rc = ensureGridSorted(r, r->verts.capacity))) return rc;
+        if(r->useVM)
+            if((rc = ensureGridSorted(r, uint32_t(std::min<uint64_t>(cap * ws, 0xFFFFFF00u))))) return rc;
+    }
+    if(r->gatherBuf)
+    {
+        // Slots per block for this call: the whole capacity until a synchronisation has shown the real
+        // counts, then the largest count + 12.5 % (they wobble by a fraction of a percent between
+        // iterations). Every rank sees the same headers, hence decides the same stride.
+        uint32_t stride = r->gatherSlots;
+        if(r->lastMaxCount && maxLen <= r->strideMaxLen)
+            stride = uint32_t(std::min<uint64_t>(r->gatherSlots, (uint64_t(r->lastMaxCount) + r->lastMaxCount / 8u + 4096u + 255u) & ~uint64_t(255u)));
+        else { r->strideMaxLen = maxLen; r->lastMaxCount = 0; }
+        if(stride != r->gatherStride) pointGatherStreams(r, stride);
     }
 
     // camera vertices: at most one per camera bounce that can still connect or merge
@@ -524,64 +582,45 @@ int ncclCheck(svcm_renderer *r, int rc, const char *what)
     return fail(r, SVCM_E_NCCL, "%s failed: %s", what, ncclApi()->GetErrorString ? ncclApi()->GetErrorString(rc) : "?");
 }
 
-// all-gather of the merge records of every rank's light vertices: exchange the
-// per-rank counts, then ONE NCCL group of four all-gathers padded to the largest count.
-int gatherLightVertices(svcm_renderer *r, MergeSet &set)
+// All-gather of the merge records of every rank's light vertices: ONE ncclAllGather of
+// fixed-size blocks, in place (block `rank` is where the local light pass wrote). Count and bbox of
+// every rank ride in the block headers, so there is no host round trip and no second collective;
+// everything is enqueued on `st` and the call returns at once.
+int gatherLightVertices(svcm_renderer *r, MergeSet &set, cudaStream_t st, int slot)
 {
     NcclApi *n = ncclApi();
     const int ws = r->params.worldSize;
     if(!r->comm) return fail(r, SVCM_E_STATE, "worldSize %d but svcm_comm_init was not called", ws);
+    const uint32_t stride = r->gatherStride;
+    const size_t blockBytes = gatherBlockBytes(stride);
 
-    // per-rank counts: the 64-bit device counters are all-gathered as they are (no host round
-    // trip before the collective), then ONE stream synchronisation brings them to the host
+    MergeSet local; memset(&local, 0, sizeof(local));
+    local.posLen = r->verts.posLen; local.thrVcm = r->verts.thrVcm; local.dirVm = r->verts.dirVm;
+    local.contProb = r->verts.contProb;
+    local.singleCount = r->counters + CNT_LIGHT_VERTS;
+    local.capacity = stride; local.segStride = stride; local.numSegs = 1;
+    unsigned char *mine = r->gatherBuf + size_t(r->params.rank) * blockBytes;
+    launchGatherPackHeader(local, r->bboxInit, reinterpret_cast<GatherHeader*>(mine), st);
+
     int rc;
-    if((rc = ncclCheck(r, n->AllGather(r->counters + CNT_LIGHT_VERTS, r->devCounts64, 2, NCCL_UINT32, r->comm, r->stream),
-                       "ncclAllGather(counts)"))) return rc;
-    SVCM_CUDA(r, cudaMemcpyAsync(r->hostCounts64, r->devCounts64, sizeof(unsigned long long) * ws,
-                                 cudaMemcpyDeviceToHost, r->stream));
-    SVCM_CUDA(r, cudaStreamSynchronize(r->stream));
-    for(int i = 0; i < ws; i++)
-        r->hostCounts[i] = uint32_t(std::min<unsigned long long>(r->hostCounts64[i], r->verts.capacity));
-
-    uint32_t maxCount = 0;
-    for(int i = 0; i < ws; i++) maxCount = std::max(maxCount, r->hostCounts[i]);
-    const uint32_t stride = (maxCount + 255u) & ~255u;
-    if(stride > r->verts.capacity)
-        return fail(r, SVCM_E_STATE, "rank vertex count %u exceeds the local store (%u)", maxCount, r->verts.capacity);
-
-    const uint64_t need = uint64_t(stride) * ws;
-    if(need > r->gatherCapacity)
-    {
-        freeGather(r);
-        const uint64_t cap = need + need / 8;
-        if((rc = devAlloc(r, &r->gPosLen, cap))) return rc;
-        if((rc = devAlloc(r, &r->gThrVcm, cap))) return rc;
-        if((rc = devAlloc(r, &r->gDirVm, cap))) return rc;
-        if((rc = devAlloc(r, &r->gContProb, cap))) return rc;
-        r->gatherCapacity = uint32_t(std::min<uint64_t>(cap, 0xFFFFFFFFu));
-    }
-    // (slack: the per-iteration counts wobble by a fraction of a percent and a reallocation is a
-    // device-wide synchronisation worth tens of milliseconds at config #5 sizes)
-    if(need > r->gridCapacity)
-        if((rc = ensureGridSorted(r, uint32_t(std::min<uint64_t>(need + need / 8, 0xFFFFFF00u))))) return rc;
-
-    if(stride > 0)
-    {
-        if((rc = ncclCheck(r, n->GroupStart(), "ncclGroupStart"))) return rc;
-        n->AllGather(r->verts.posLen, r->gPosLen, size_t(stride) * 4, NCCL_FLOAT32, r->comm, r->stream);
-        n->AllGather(r->verts.thrVcm, r->gThrVcm, size_t(stride) * 4, NCCL_FLOAT32, r->comm, r->stream);
-        n->AllGather(r->verts.dirVm, r->gDirVm, size_t(stride) * 4, NCCL_FLOAT32, r->comm, r->stream);
-        n->AllGather(r->verts.contProb, r->gContProb, size_t(stride), NCCL_FLOAT32, r->comm, r->stream);
-        if((rc = ncclCheck(r, n->GroupEnd(), "ncclGroupEnd(all-gather light vertices)"))) return rc;
-    }
+    if((rc = ncclCheck(r, n->AllGather(mine, r->gatherBuf, blockBytes, NCCL_UINT8, r->comm, st),
+                       "ncclAllGather(light vertices)"))) return rc;
+    launchGatherUnpackHeaders(r->gatherBuf, blockBytes, uint32_t(ws), stride, r->segCountDev, r->grid.bboxBits,
+                              r->devCounts64, st);
+    SVCM_CUDA(r, cudaMemcpyAsync(r->hostCounts64 + size_t(slot) * 8, r->devCounts64, sizeof(unsigned long long) * 8,
+                                 cudaMemcpyDeviceToHost, st));
 
     memset(&set, 0, sizeof(set));
-    set.posLen = r->gPosLen; set.thrVcm = r->gThrVcm; set.dirVm = r->gDirVm; set.contProb = r->gContProb;
+    set.posLen   = reinterpret_cast<const float4*>(r->gatherBuf + sizeof(GatherHeader));
+    set.thrVcm   = set.posLen + stride;
+    set.dirVm    = set.thrVcm + stride;
+    set.contProb = reinterpret_cast<const float*>(set.dirVm + stride);
     set.singleCount = NULL;
-    set.capacity = uint32_t(need);
+    set.capacity = stride * uint32_t(ws);
     set.segStride = stride;
     set.numSegs = uint32_t(ws);
-    for(int i = 0; i < ws; i++) set.segCount[i] = r->hostCounts[i];
+    set.segBytes = blockBytes;
+    set.segCountDev = r->segCountDev;
     return SVCM_OK;
 }
 
@@ -625,7 +664,7 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     // ---- the unidirectional integrators ---------------------------------
     if(r->pathTrace || r->eyeLight)
     {
-        if(timed) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); cudaEventRecord(ev[3], st); }
+        if(timed) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[6], st); cudaEventRecord(ev[7], st); cudaEventRecord(ev[8], st); }
         a.queueCounts = r->queueCountsCamera;
         if(r->eyeLight)
         {
@@ -677,15 +716,21 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     th[2] = hostNowMs();
 
     // ---- hash grid over ALL light vertices (src/vertexcm.hxx:403-408) ----------------------
-    if(timed) cudaEventRecord(ev[2], st);
+    // On its own stream: the camera pass needs nothing from it (its vertices are tested against the
+    // particle bbox when they are keyed for the merge), so the all-gather and the build run
+    // concurrently with the camera sub-paths and only the merge waits for them.
     if(r->useVM)
     {
+        cudaStream_t sg = r->gridStream;
+        SVCM_CUDA(r, cudaEventRecord(r->evLightDone, st));
+        SVCM_CUDA(r, cudaStreamWaitEvent(sg, r->evLightDone, 0));
+        if(timed) cudaEventRecord(ev[6], sg);
         MergeSet set;
         if(r->params.worldSize > 1)
         {
-            const int rc = gatherLightVertices(r, set);
+            const int rc = gatherLightVertices(r, set, sg, slot);
             if(rc) return rc;
-            if(timed) cudaEventRecord(ev[2], st);
+            launches += 4;
         }
         else
         {
@@ -696,10 +741,13 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
             set.capacity = r->verts.capacity;
             set.segStride = r->verts.capacity; set.numSegs = 1;
         }
-        if(r->cellLayout) launches += launchCellGridBuild(ic, set, r->grid, r->scanGenGrid, r->refCandidates, st);
-        else launches += launchGridBuild(ic, set, r->grid, st);
+        if(timed) cudaEventRecord(ev[7], sg);
+        if(r->cellLayout) launches += launchCellGridBuild(ic, set, r->grid, r->scanGenGrid, r->refCandidates, sg);
+        else launches += launchGridBuild(ic, set, r->grid, sg);
+        if(timed) cudaEventRecord(ev[8], sg);
+        SVCM_CUDA(r, cudaEventRecord(r->evGridDone, sg));
     }
-    if(timed) cudaEventRecord(ev[3], st);
+    else if(timed) { cudaEventRecord(ev[6], st); cudaEventRecord(ev[7], st); cudaEventRecord(ev[8], st); }
     th[3] = hostNowMs();
 
     // ---- camera sub-paths (src/vertexcm.hxx:415-545) ---------------------------------------
@@ -724,29 +772,27 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     th[4] = hostNowMs();
 
     // ---- deferred merging of all queued camera vertices ------------------------------------
+    if(r->useVM) SVCM_CUDA(r, cudaStreamWaitEvent(st, r->evGridDone, 0));
     if(r->useVM && !r->lightTraceOnly)
     {
         QueryStore qs = r->queries;
-        const unsigned long long *count = r->counters + CNT_CAM_VERTS;
+        // the queries take the particles' order (neighbouring lanes then share cells); the keying
+        // kernel applies HashGrid::Process' bbox early-out and counts the queries
+        const unsigned long long *count = r->counters + CNT_QUERIES;
         if(r->cellLayout)
         {
-            // the queries take the particles' order: neighbouring lanes share rows and cells
             launches += launchCellQuerySort(ic, r->queries, r->counters + CNT_CAM_VERTS, 0, r->grid, r->qsort,
-                                            r->scanGenQuery, st);
+                                            r->scanGenQuery, r->counters, st);
             qs.order = r->qsort.order;
-            count = r->counters + CNT_QUERIES;
             GridBuffers grid = r->grid;
             if(!r->refCandidates) grid.refCount = NULL;
             launchCellMerge(r->scene, ic, qs, count, 0, grid, r->accum, NULL, NULL, r->counters, r->mergeVariant, st);
         }
         else
         {
-            if(r->sortQueries)
-            {
-                launches += launchQuerySort(ic, r->queries, r->counters + CNT_CAM_VERTS, r->grid.bboxBits, r->qsort, st);
-                qs.order = r->qsort.order;
-                count = r->counters + CNT_QUERIES;           // only the mergeable vertices are in the order
-            }
+            launches += launchQuerySort(ic, r->queries, r->counters + CNT_CAM_VERTS, r->grid.bboxBits, r->qsort,
+                                        r->counters, st);
+            qs.order = r->qsort.order;
             launchMerge(r->scene, ic, qs, count, 0, r->grid, r->accum, NULL, NULL,
                         r->counters, r->mergeGroup, st);
         }
@@ -783,8 +829,11 @@ int finishStats(svcm_renderer *r)
     s.lightVertices = s.localLightVertices;
     if(r->params.worldSize > 1 && r->useVM)
     {
+        const unsigned long long *per = r->hostCounts64 + size_t(slot) * 8;
         s.lightVertices = 0;
-        for(int i = 0; i < r->params.worldSize; i++) s.lightVertices += r->hostCounts[i];
+        unsigned long long mx = 0;
+        for(int i = 0; i < r->params.worldSize; i++) { s.lightVertices += (int64_t)per[i]; mx = std::max(mx, per[i]); }
+        r->lastMaxCount = uint32_t(std::min<unsigned long long>(mx, 0xFFFFFFFFull));   // sizes the next call's blocks
     }
     s.mergeQueries = (int64_t)c[CNT_QUERIES];
     s.mergeCandidates = (int64_t)c[CNT_CANDIDATES];
@@ -797,10 +846,12 @@ int finishStats(svcm_renderer *r)
     if(r->ringTimed[slot])
     {
         cudaEvent_t *ev = r->ev[slot];
+        // gather and build run on the grid stream, concurrently with the camera pass: the stage
+        // times no longer add up to the total, that is the point
         cudaEventElapsedTime(&s.msLightTrace, ev[0], ev[1]);
-        cudaEventElapsedTime(&s.msGather, ev[1], ev[2]);
-        cudaEventElapsedTime(&s.msGridBuild, ev[2], ev[3]);
-        cudaEventElapsedTime(&s.msCameraTrace, ev[3], ev[4]);
+        cudaEventElapsedTime(&s.msGather, ev[6], ev[7]);
+        cudaEventElapsedTime(&s.msGridBuild, ev[7], ev[8]);
+        cudaEventElapsedTime(&s.msCameraTrace, ev[1], ev[4]);
         cudaEventElapsedTime(&s.msMerge, ev[4], ev[5]);
         cudaEventElapsedTime(&s.msTotal, ev[0], ev[5]);
     }
@@ -850,8 +901,11 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     memset(&r->qsort, 0, sizeof(r->qsort)); r->sortQueries = getenv("SVCM_NO_QUERY_SORT") == NULL;
     r->counters = NULL; r->hostCounters = NULL; r->accum = NULL;
     memset(&r->grid, 0, sizeof(r->grid)); r->gridCells = 0; r->gridCapacity = 0; r->bboxInit = NULL;
-    r->comm = NULL; r->gPosLen = r->gThrVcm = r->gDirVm = NULL; r->gContProb = NULL; r->gatherCapacity = 0;
-    r->devCounts64 = NULL; r->hostCounts64 = NULL; r->hostCounts = NULL;
+    r->comm = NULL; r->gatherBuf = NULL; r->gatherBytes = 0; r->gatherSlots = 0; r->gatherStride = 0;
+    r->strideMaxLen = 0; r->lastMaxCount = 0; r->segCountDev = NULL;
+    r->devCounts64 = NULL; r->hostCounts64 = NULL;
+    r->accumReduced = NULL; r->reducedValid = false;
+    r->gridStream = NULL; r->evLightDone = NULL; r->evGridDone = NULL;
     r->iterationsDone = 0; r->mergeGroup = 1; r->profile = false;
     {
         // defaults; SVCM_GRID_LAYOUT / SVCM_MERGE_VARIANT override them for A/B measurements
@@ -920,11 +974,14 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     if((rc = devAlloc(r, &r->grid.bboxBits, 6))) SVCM_CREATE_FAIL(rc);
     if((rc = devAlloc(r, &r->bboxInit, 6))) SVCM_CREATE_FAIL(rc);
     if((rc = devAlloc(r, &r->devCounts64, 8))) SVCM_CREATE_FAIL(rc);
+    if((rc = devAlloc(r, &r->segCountDev, 8))) SVCM_CREATE_FAIL(rc);
+    SVCM_TRY(cudaStreamCreateWithFlags(&r->gridStream, cudaStreamNonBlocking));
+    SVCM_TRY(cudaEventCreateWithFlags(&r->evLightDone, cudaEventDisableTiming));
+    SVCM_TRY(cudaEventCreateWithFlags(&r->evGridDone, cudaEventDisableTiming));
     SVCM_TRY(cudaMallocHost((void**)&r->hostCounters, sizeof(unsigned long long) * CNT_WORDS * SVCM_PROFILE_RING));
-    SVCM_TRY(cudaMallocHost((void**)&r->hostCounts64, sizeof(unsigned long long) * 8));
-    r->hostCounts = new uint32_t[8];
+    SVCM_TRY(cudaMallocHost((void**)&r->hostCounts64, sizeof(unsigned long long) * 8 * SVCM_PROFILE_RING));
     memset(r->hostCounters, 0, sizeof(unsigned long long) * CNT_WORDS * SVCM_PROFILE_RING);
-    memset(r->hostCounts64, 0, sizeof(unsigned long long) * 8); memset(r->hostCounts, 0, sizeof(uint32_t) * 8);
+    memset(r->hostCounts64, 0, sizeof(unsigned long long) * 8 * SVCM_PROFILE_RING);
     const int32_t init[6] = { floatToOrdered(1e36f), floatToOrdered(1e36f), floatToOrdered(1e36f),
                               floatToOrdered(-1e36f), floatToOrdered(-1e36f), floatToOrdered(-1e36f) };
     SVCM_TRY(cudaMemcpy(r->bboxInit, init, sizeof(init), cudaMemcpyHostToDevice));
@@ -932,6 +989,7 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     r->grid.bboxInit = r->bboxInit;
     SVCM_TRY(cudaMemset(r->accum, 0, sizeof(float) * 3 * size_t(r->paths)));
     SVCM_TRY(cudaMemset(r->devCounts64, 0, sizeof(unsigned long long) * 8));
+    SVCM_TRY(cudaMemset(r->segCountDev, 0, sizeof(uint32_t) * 8));
 #undef SVCM_TRY
 #undef SVCM_CREATE_FAIL
     *out = r;
@@ -947,7 +1005,7 @@ void svcm_destroy(svcm_renderer *r)
     freeQueue(r->queue[0]); freeQueue(r->queue[1]);
     devFree(r->queueCountsLight); devFree(r->queueCountsCamera);
     devFree(r->shadow.r0); devFree(r->shadow.r1); devFree(r->shadow.r2); devFree(r->shadow.counts);
-    freeVerts(r); freeQueries(r); freeGridSorted(r); freeGather(r);
+    freeVerts(r); freeQueries(r); freeGridSorted(r);
     devFree(r->pathVertCount); devFree(r->counters); devFree(r->accum); devFree(r->image8);
     r->geometry.release();
     devFree(r->grid.cellCount); devFree(r->grid.blockSums); devFree(r->grid.bboxBits);
@@ -955,13 +1013,15 @@ void svcm_destroy(svcm_renderer *r)
     devFree(r->grid.scanState); devFree(r->grid.scanCounter);
     devFree(r->qsort.cellCount); devFree(r->qsort.blockSums);
     devFree(r->qsort.cellEnd); devFree(r->qsort.scanState); devFree(r->qsort.scanCounter);
-    devFree(r->bboxInit); devFree(r->devCounts64);
+    devFree(r->bboxInit); devFree(r->devCounts64); devFree(r->segCountDev); devFree(r->accumReduced);
+    if(r->gridStream) { cudaStreamSynchronize(r->gridStream); cudaStreamDestroy(r->gridStream); }
+    if(r->evLightDone) cudaEventDestroy(r->evLightDone);
+    if(r->evGridDone) cudaEventDestroy(r->evGridDone);
     if(r->hostCounters) cudaFreeHost(r->hostCounters);
     if(r->hostCounts64) cudaFreeHost(r->hostCounts64);
-    delete[] r->hostCounts;
     if(r->ev)
     {
-        for(int k = 0; k < SVCM_PROFILE_RING; k++) for(int i = 0; i < 6; i++) if(r->ev[k][i]) cudaEventDestroy(r->ev[k][i]);
+        for(int k = 0; k < SVCM_PROFILE_RING; k++) for(int i = 0; i < 9; i++) if(r->ev[k][i]) cudaEventDestroy(r->ev[k][i]);
         delete[] r->ev;
     }
     for(int i = 0; i < SVCM_NUM_USER_EVENTS; i++) if(r->userEv[i]) cudaEventDestroy(r->userEv[i]);
@@ -978,9 +1038,9 @@ int svcm_set_option(svcm_renderer *r, int32_t option, int64_t value)
         if(value != 0 && !r->ev)
         {
             SVCM_CUDA(r, cudaSetDevice(r->device));
-            r->ev = new cudaEvent_t[SVCM_PROFILE_RING][6];
-            memset(r->ev, 0, sizeof(cudaEvent_t) * 6 * SVCM_PROFILE_RING);
-            for(int k = 0; k < SVCM_PROFILE_RING; k++) for(int i = 0; i < 6; i++) SVCM_CUDA(r, cudaEventCreate(&r->ev[k][i]));
+            r->ev = new cudaEvent_t[SVCM_PROFILE_RING][9];
+            memset(r->ev, 0, sizeof(cudaEvent_t) * 9 * SVCM_PROFILE_RING);
+            for(int k = 0; k < SVCM_PROFILE_RING; k++) for(int i = 0; i < 9; i++) SVCM_CUDA(r, cudaEventCreate(&r->ev[k][i]));
         }
         r->profile = value != 0;
         return SVCM_OK;
@@ -1012,6 +1072,7 @@ int svcm_run_iterations(svcm_renderer *r, int32_t firstIteration, int32_t count,
     SVCM_CUDA(r, cudaSetDevice(r->device));
     int rc = ensureCapacity(r, maxPathLength);
     if(rc) return rc;
+    if(count > 0) r->reducedValid = false;
     for(int i = 0; i < count; i++)
     {
         // per-iteration counters of the previous iteration are overwritten: check overflow first
@@ -1033,7 +1094,9 @@ int svcm_download_accum(svcm_renderer *r, float *rgb, int32_t *iterationsDone)
 {
     if(!r || !rgb) return SVCM_E_INVALID;
     SVCM_CUDA(r, cudaSetDevice(r->device));
-    SVCM_CUDA(r, cudaMemcpyAsync(rgb, r->accum, sizeof(float) * 3 * size_t(r->paths), cudaMemcpyDeviceToHost, r->stream));
+    // after svcm_reduce_accum the root serves the sum over ranks (until more iterations are rendered)
+    const float *src = (r->reducedValid && r->accumReduced) ? r->accumReduced : r->accum;
+    SVCM_CUDA(r, cudaMemcpyAsync(rgb, src, sizeof(float) * 3 * size_t(r->paths), cudaMemcpyDeviceToHost, r->stream));
     SVCM_CUDA(r, cudaStreamSynchronize(r->stream));
     if(iterationsDone) *iterationsDone = r->iterationsDone;
     return finishStats(r);
@@ -1118,7 +1181,7 @@ int svcm_clear_accum(svcm_renderer *r)
     if(!r) return SVCM_E_INVALID;
     SVCM_CUDA(r, cudaSetDevice(r->device));
     SVCM_CUDA(r, cudaMemsetAsync(r->accum, 0, sizeof(float) * 3 * size_t(r->paths), r->stream));
-    r->iterationsDone = 0;
+    r->iterationsDone = 0; r->reducedValid = false;
     return SVCM_OK;
 }
 
@@ -1152,8 +1215,8 @@ int svcm_get_profile(svcm_renderer *r, SvcmProfile *out)
         {
             cudaEvent_t *ev = r->ev[slot];
             float ms[6] = { 0, 0, 0, 0, 0, 0 };
-            cudaEventElapsedTime(&ms[0], ev[0], ev[1]); cudaEventElapsedTime(&ms[1], ev[1], ev[2]);
-            cudaEventElapsedTime(&ms[2], ev[2], ev[3]); cudaEventElapsedTime(&ms[3], ev[3], ev[4]);
+            cudaEventElapsedTime(&ms[0], ev[0], ev[1]); cudaEventElapsedTime(&ms[1], ev[6], ev[7]);
+            cudaEventElapsedTime(&ms[2], ev[7], ev[8]); cudaEventElapsedTime(&ms[3], ev[1], ev[4]);
             cudaEventElapsedTime(&ms[4], ev[4], ev[5]); cudaEventElapsedTime(&ms[5], ev[0], ev[5]);
             out->msLightTrace += ms[0]; out->msGather += ms[1]; out->msGridBuild += ms[2];
             out->msCameraTrace += ms[3]; out->msMerge += ms[4]; out->msTotal += ms[5];
@@ -1259,9 +1322,20 @@ int svcm_reduce_accum(svcm_renderer *r, int32_t root)
     if(!r) return SVCM_E_INVALID;
     if(r->params.worldSize == 1) return SVCM_OK;
     if(!r->comm) return fail(r, SVCM_E_STATE, "svcm_comm_init was not called");
+    if(root < 0 || root >= r->params.worldSize) return fail(r, SVCM_E_INVALID, "root %d out of range", root);
     SVCM_CUDA(r, cudaSetDevice(r->device));
-    return ncclCheck(r, ncclApi()->Reduce(r->accum, r->accum, size_t(r->paths) * 3, NCCL_FLOAT32, NCCL_SUM, root,
-                                          r->comm, r->stream), "ncclReduce(accum)");
+    // The sum goes to a buffer of its own on the root: every rank's accum stays what that rank
+    // rendered, so rendering more iterations and reducing again counts nothing twice.
+    if(r->params.rank == root && !r->accumReduced)
+    {
+        const int rc = devAlloc(r, &r->accumReduced, size_t(r->paths) * 3);
+        if(rc) return rc;
+    }
+    const int rc = ncclCheck(r, ncclApi()->Reduce(r->accum, r->params.rank == root ? r->accumReduced : r->accum,
+                                                  size_t(r->paths) * 3, NCCL_FLOAT32, NCCL_SUM, root, r->comm, r->stream),
+                             "ncclReduce(accum)");
+    if(rc == SVCM_OK && r->params.rank == root) r->reducedValid = true;
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1507,7 +1581,7 @@ int svcm_hashgrid_query(svcm_hashgrid *g, const SvcmSceneDesc *scene, const Svcm
             if(e == cudaSuccess)
             {
                 ScanGen gen; gen.value = 0;
-                launchCellQuerySort(ic, qs, NULL, uint32_t(count), g->grid, sort, gen, 0);
+                launchCellQuerySort(ic, qs, NULL, uint32_t(count), g->grid, sort, gen, NULL, 0);
                 qs.order = sort.order;
                 const char *variant = getenv("SVCM_MERGE_VARIANT");
                 launchCellMerge(sc, ic, qs, NULL, uint32_t(count), g->grid, NULL, dContrib, dCounts, NULL,

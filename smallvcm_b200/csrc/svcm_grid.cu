@@ -104,9 +104,10 @@ k_cellKeys(const __grid_constant__ MergeSet set, const __grid_constant__ IterCon
     for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
     {
         uint32_t k = 0xFFFFFFFFu;
-        if(mergeSetValid(set, i))
+        const MergeSlot ms = mergeSetSlot(set, i);
+        if(mergeSetValid(set, ms))
         {
-            const float4 p = set.posLen[i];
+            const float4 p = *mergeSetStream(set, set.posLen, ms);
             const int32_t cx = cellCoord(p.x, bbMin.x, ic.invCellSize), cy = cellCoord(p.y, bbMin.y, ic.invCellSize),
                           cz = cellCoord(p.z, bbMin.z, ic.invCellSize);
             k = cellKey(d, storageX(cx, d.m), foldCoord(cy, d.fy), foldCoord(cz, d.fz));
@@ -121,31 +122,70 @@ k_cellKeys(const __grid_constant__ MergeSet set, const __grid_constant__ IterCon
 __global__ void __launch_bounds__(SVCM_BLOCK)
 k_cellQueryKeys(const __grid_constant__ QueryStore qs, const unsigned long long *vertexCount, uint32_t hostCount,
                 const __grid_constant__ IterConst ic, const int32_t *bboxBits, const GridDims *dims, uint32_t *key,
-                uint32_t *cellEnd)
+                uint32_t *cellEnd, unsigned long long *counters)
 {
     const GridDims d = *dims;
     const uint32_t n = vertexCount ? uint32_t(min(*vertexCount, (unsigned long long)qs.capacity)) : hostCount;
     const f3 bbMin = mk3(orderedToFloat(bboxBits[0]), orderedToFloat(bboxBits[1]), orderedToFloat(bboxBits[2]));
     const f3 bbMax = mk3(orderedToFloat(bboxBits[3]), orderedToFloat(bboxBits[4]), orderedToFloat(bboxBits[5]));
-    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    uint32_t nInside = 0u;
+    for(uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x)
     {
+        const uint32_t i = i0 + threadIdx.x;
         uint32_t k = 0xFFFFFFFFu;
-        if(__float_as_uint(qs.q1[i].w) & CAMV_MERGEABLE)
+        if(i < n && (__float_as_uint(qs.q1[i].w) & CAMV_MERGEABLE))
         {
             const float4 p = qs.q0[i];
-            // queries outside the particle bbox do nothing (src/hashgrid.hxx:116-122): park them in
-            // the dummy cell so that they still receive a slot (zero contribution, zero counts)
+            // HashGrid::Process early-out (src/hashgrid.hxx:116-122): a vertex outside the particle
+            // bbox issues no query. In the path it is left out of the order; the kernel-level entry
+            // point parks it in the dummy cell so that it still receives its (zero) result.
             const bool inside = !(p.x - bbMin.x < 0.f || bbMax.x - p.x < 0.f || p.y - bbMin.y < 0.f ||
                                   bbMax.y - p.y < 0.f || p.z - bbMin.z < 0.f || bbMax.z - p.z < 0.f);
-            k = 0u;
             if(inside)
+            {
                 k = cellKey(d, storageX(cellCoord(p.x, bbMin.x, ic.invCellSize), d.m),
                             foldCoord(cellCoord(p.y, bbMin.y, ic.invCellSize), d.fy),
                             foldCoord(cellCoord(p.z, bbMin.z, ic.invCellSize), d.fz));
-            atomicAdd(cellEnd + k, 1u);
+                nInside++;
+            }
+            else if(!counters) k = 0u;
+            if(k != 0xFFFFFFFFu) atomicAdd(cellEnd + k, 1u);
         }
-        key[i] = k;
+        if(i < n) key[i] = k;
     }
+    if(counters) warpCount(counters + CNT_QUERIES, nInside);
+}
+
+// bbox + count of the LOCAL light vertices into this rank's all-gather header
+__global__ void k_gatherHeaderCount(const unsigned long long *count, GatherHeader *header)
+{
+    if(blockIdx.x == 0 && threadIdx.x == 0) header->count = *count;
+}
+
+// after the all-gather: per-block counts (clamped to the slots a block has), the union of the
+// blocks' bboxes = the bbox of all particles (src/hashgrid.hxx:50-61), and the totals
+__global__ void k_gatherUnpackHeaders(const unsigned char *blocks, uint64_t blockBytes, uint32_t numSegs, uint32_t segStride,
+                                      uint32_t *segCountDev, int32_t *bboxBits, unsigned long long *totals)
+{
+    const uint32_t lane = threadIdx.x;
+    int32_t bb[6] = { floatToOrdered(1e36f), floatToOrdered(1e36f), floatToOrdered(1e36f),
+                      floatToOrdered(-1e36f), floatToOrdered(-1e36f), floatToOrdered(-1e36f) };
+    unsigned long long cnt = 0ull;
+    if(lane < numSegs)
+    {
+        const GatherHeader *h = reinterpret_cast<const GatherHeader*>(blocks + uint64_t(lane) * blockBytes);
+        cnt = h->count;
+        if(cnt > 0ull) for(int k = 0; k < 6; k++) bb[k] = h->bbox[k];
+        segCountDev[lane] = uint32_t(min(cnt, (unsigned long long)segStride));
+        totals[lane] = cnt;
+    }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1)
+    {
+        for(int k = 0; k < 3; k++) bb[k] = min(bb[k], __shfl_xor_sync(FULL_MASK, bb[k], o));
+        for(int k = 3; k < 6; k++) bb[k] = max(bb[k], __shfl_xor_sync(FULL_MASK, bb[k], o));
+    }
+    if(lane < 6u) bboxBits[lane] = bb[lane];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -305,11 +345,11 @@ k_cellGather(const __grid_constant__ MergeSet set, const __grid_constant__ GridB
     const uint32_t total = g.cellEnd[g.dims->numKeys];      // end of the last key = number of particles
     for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += gridDim.x * blockDim.x)
     {
-        const uint32_t i = uint32_t(g.sIndex[slot]);
-        g.sPosLen[slot]   = set.posLen[i];
-        g.sThrVcm[slot]   = set.thrVcm[i];
-        g.sDirVm[slot]    = set.dirVm[i];
-        g.sContProb[slot] = set.contProb[i];
+        const MergeSlot ms = mergeSetSlot(set, uint32_t(g.sIndex[slot]));
+        g.sPosLen[slot]   = *mergeSetStream(set, set.posLen, ms);
+        g.sThrVcm[slot]   = *mergeSetStream(set, set.thrVcm, ms);
+        g.sDirVm[slot]    = *mergeSetStream(set, set.dirVm, ms);
+        g.sContProb[slot] = *mergeSetStream(set, set.contProb, ms);
     }
 }
 
@@ -334,8 +374,9 @@ k_cellBBox(const __grid_constant__ MergeSet set, int32_t *bboxBits)
     const uint32_t total = mergeSetTotal(set);
     for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
     {
-        if(!mergeSetValid(set, i)) continue;
-        const float4 p = set.posLen[i];
+        const MergeSlot ms = mergeSetSlot(set, i);
+        if(!mergeSetValid(set, ms)) continue;
+        const float4 p = *mergeSetStream(set, set.posLen, ms);
         mn = mk3(fminf(mn.x, p.x), fminf(mn.y, p.y), fminf(mn.z, p.z));
         mx = mk3(fmaxf(mx.x, p.x), fmaxf(mx.y, p.y), fmaxf(mx.z, p.z));
     }
@@ -985,12 +1026,14 @@ int launchCellGridBuild(const IterConst &ic, const MergeSet &set, const GridBuff
 {
     int launches = 0;
     const uint32_t n = grid.tcap + 2u;
-    cudaMemcpyAsync(grid.bboxBits, grid.bboxInit, sizeof(int32_t) * 6, cudaMemcpyDeviceToDevice, stream);
+    // all-gathered blocks: the bbox is the union of the block headers' (launchGatherUnpackHeaders)
+    const bool bboxReady = set.singleCount == NULL;
+    if(!bboxReady) cudaMemcpyAsync(grid.bboxBits, grid.bboxInit, sizeof(int32_t) * 6, cudaMemcpyDeviceToDevice, stream);
     cudaMemsetAsync(grid.cellEnd, 0, sizeof(uint32_t) * n, stream);
     if(withRefCount && grid.refCount) cudaMemsetAsync(grid.refCount, 0, sizeof(uint32_t) * ic.numCells, stream);
     const uint32_t maxTotal = set.singleCount ? set.capacity : set.numSegs * set.segStride;
     const uint32_t gridN = gridFor(maxTotal ? maxTotal : 1u, SVCM_BLOCK, 8);
-    if(maxTotal > 0u) { k_cellBBox<<<gridN, SVCM_BLOCK, 0, stream>>>(set, grid.bboxBits); launches++; }
+    if(maxTotal > 0u && !bboxReady) { k_cellBBox<<<gridN, SVCM_BLOCK, 0, stream>>>(set, grid.bboxBits); launches++; }
     k_cellDims<<<1, 32, 0, stream>>>(grid.bboxBits, ic.invCellSize, grid.tcap, grid.dims);
     launches++;
     if(maxTotal > 0u)
@@ -1013,7 +1056,7 @@ int launchCellGridBuild(const IterConst &ic, const MergeSet &set, const GridBuff
 
 int launchCellQuerySort(const IterConst &ic, const QueryStore &queries, const unsigned long long *vertexCount,
                         uint32_t hostVertexCount, const GridBuffers &grid, const QuerySortBuffers &qs, ScanGen &gen,
-                        cudaStream_t stream)
+                        unsigned long long *counters, cudaStream_t stream)
 {
     const uint32_t n = grid.tcap + 2u;
     cudaMemsetAsync(qs.cellEnd, 0, sizeof(uint32_t) * n, stream);
@@ -1021,7 +1064,7 @@ int launchCellQuerySort(const IterConst &ic, const QueryStore &queries, const un
     if(maxCount == 0u) return 0;
     const uint32_t gridN = gridFor(maxCount, SVCM_BLOCK, 8);
     k_cellQueryKeys<<<gridN, SVCM_BLOCK, 0, stream>>>(queries, vertexCount, hostVertexCount, ic, grid.bboxBits, grid.dims,
-                                                      qs.key, qs.cellEnd);
+                                                      qs.key, qs.cellEnd, counters);
     launchLookbackScan(qs.cellEnd, grid.dims, n, qs.scanState, qs.scanCounter, gen, stream);
     k_cellScatterIndex<<<gridFor((maxCount + 3u) / 4u, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(
         qs.key, vertexCount, hostVertexCount, queries.capacity, qs.cellEnd, qs.order);
@@ -1074,6 +1117,20 @@ void launchCellMerge(const DevScene &sc, const IterConst &ic, const QueryStore &
                                     counters, maxQueries, stream);
         break;
     }
+}
+
+void launchGatherPackHeader(const MergeSet &localSet, const int32_t *bboxInit, GatherHeader *header, cudaStream_t stream)
+{
+    cudaMemcpyAsync(header->bbox, bboxInit, sizeof(int32_t) * 6, cudaMemcpyDeviceToDevice, stream);
+    if(localSet.capacity > 0u)
+        k_cellBBox<<<gridFor(localSet.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(localSet, header->bbox);
+    k_gatherHeaderCount<<<1, 32, 0, stream>>>(localSet.singleCount, header);
+}
+
+void launchGatherUnpackHeaders(const unsigned char *blocks, uint64_t blockBytes, uint32_t numSegs, uint32_t segStride,
+                               uint32_t *segCountDev, int32_t *bboxBits, unsigned long long *totals, cudaStream_t stream)
+{
+    k_gatherUnpackHeaders<<<1, 32, 0, stream>>>(blocks, blockBytes, numSegs, segStride, segCountDev, bboxBits, totals);
 }
 
 void launchCellRefKeys(const IterConst &ic, const GridBuffers &grid, uint32_t count, uint32_t *out, cudaStream_t stream)

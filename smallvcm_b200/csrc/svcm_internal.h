@@ -60,18 +60,30 @@ struct VertexStore
     uint32_t capacity;
 };
 
-// The gathered (all ranks) merge records and their cell-sorted copy + grid
+// The particle set of one grid build: the merge records of ALL light vertices.
+//   single rank : the local streams, `*singleCount` records (device counter, clamped to capacity).
+//   all ranks   : numSegs blocks of one all-gather, `segBytes` apart; the four pointers address the
+//                 streams of block 0, every block holds `segStride` record slots of which the
+//                 first segCountDev[seg] are valid (device array filled from the block headers).
 struct MergeSet
 {
-    // unsorted merge records. Single rank: `*singleCount` records (device counter, clamped
-    // to capacity). Gathered from all ranks: numSegs segments of `segStride` records of which
-    // the first segCount[r] are valid (the rest is all-gather padding).
     const float4 *posLen; const float4 *thrVcm; const float4 *dirVm; const float *contProb;
     const unsigned long long *singleCount;
     uint32_t capacity;
     uint32_t segStride;
-    uint32_t segCount[8];
     uint32_t numSegs;
+    uint64_t segBytes;
+    const uint32_t *segCountDev;
+};
+
+// Header of one rank's block in the light-vertex all-gather ("padded to equal per-rank
+// capacity with the true count in a header slot"): the count and the rank's bbox, so that neither
+// needs a host round trip or a second collective.
+struct GatherHeader
+{
+    unsigned long long count;      // light vertices this rank stored (may exceed the slots: overflow)
+    int32_t bbox[6];               // ordered-int min xyz / max xyz of them
+    uint32_t pad[56];              // 256 bytes: the record streams behind it stay 256-byte aligned
 };
 
 // Geometry of the cell-layout grid (svcm_grid.cu), derived on the device from the particle bbox:
@@ -207,7 +219,7 @@ void launchCameraBounce(const DevScene &sc, const IterConst &ic, const TraceArgs
 // groups the mergeable camera vertices by cell (counting sort of indices): neighbouring lanes of
 // the merge kernel then walk the same cell ranges. Returns the number of kernels launched.
 int launchQuerySort(const IterConst &ic, const QueryStore &queries, const unsigned long long *vertexCount,
-                    const int32_t *bboxBits, const QuerySortBuffers &qs, cudaStream_t stream);
+                    const int32_t *bboxBits, const QuerySortBuffers &qs, unsigned long long *counters, cudaStream_t stream);
 // vertex connection of every queued (camera vertex, light vertex) pair
 void launchConnect(const DevScene &sc, const IterConst &ic, const TraceArgs &args, cudaStream_t stream);
 // any-hit tests + splats for the rays queued by pass `which` (0 light, 1 camera; count read on
@@ -240,9 +252,17 @@ struct ScanGen { uint32_t value; };
 int  launchCellGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers &grid, ScanGen &gen,
                          bool withRefCount, cudaStream_t stream);
 // counting sort of the mergeable camera vertices over the grid's key space -> qs.order
+// `counters` != NULL (the path): vertices outside the particle bbox issue no query and are left out;
+// the number of queries is added to counters[CNT_QUERIES]. NULL (kernel-level entry point): they
+// are kept, parked in the dummy cell, so that every input receives its (zero) result.
 int  launchCellQuerySort(const IterConst &ic, const QueryStore &queries, const unsigned long long *vertexCount,
                          uint32_t hostVertexCount, const GridBuffers &grid, const QuerySortBuffers &qs, ScanGen &gen,
-                         cudaStream_t stream);
+                         unsigned long long *counters, cudaStream_t stream);
+// the all-gather block headers (GatherHeader): bbox + count of the local vertices into `header`,
+// and after the collective the per-block counts, the union bbox and the total out of all headers
+void launchGatherPackHeader(const MergeSet &localSet, const int32_t *bboxInit, GatherHeader *header, cudaStream_t stream);
+void launchGatherUnpackHeaders(const unsigned char *blocks, uint64_t blockBytes, uint32_t numSegs, uint32_t segStride,
+                               uint32_t *segCountDev, int32_t *bboxBits, unsigned long long *totals, cudaStream_t stream);
 // merge over the cell layout. variant: 0 = lane per query straight from global memory, 1 = staged
 // through shared memory with bulk async copies, 2 = staged with plain loads
 void launchCellMerge(const DevScene &sc, const IterConst &ic, const QueryStore &queries,

@@ -427,13 +427,6 @@ k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ Iter
     const uint32_t count = (bounce == 1u) ? ic.localPaths : a.queueCounts[bounce];
     uint32_t nRays = 0u;
 
-    f3 bbMin = mk3(0.f), bbMax = mk3(0.f);
-    if(ic.useVM)
-    {
-        bbMin = mk3(orderedToFloat(a.bboxBits[0]), orderedToFloat(a.bboxBits[1]), orderedToFloat(a.bboxBits[2]));
-        bbMax = mk3(orderedToFloat(a.bboxBits[3]), orderedToFloat(a.bboxBits[4]), orderedToFloat(a.bboxBits[5]));
-    }
-
     for(uint32_t i0 = blockIdx.x * blockDim.x; i0 < count; i0 += gridDim.x * blockDim.x)
     {
         const uint32_t i = i0 + threadIdx.x;
@@ -516,14 +509,11 @@ k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ Iter
                 nv = a.pathVertCount[lpath];
                 nv = min(nv, ic.maxLen - 1u - s.length);
             }
-            if(ic.useVM)
-            {
-                // HashGrid::Process early-out: query outside the particle bbox
-                // (reference src/hashgrid.hxx:116-122)
-                const f3 dMin = hitPoint - bbMin, dMax = bbMax - hitPoint;
-                mergeable = !(dMin.x < 0.f || dMax.x < 0.f || dMin.y < 0.f || dMax.y < 0.f ||
-                              dMin.z < 0.f || dMax.z < 0.f);
-            }
+            // Every non-delta vertex is a merge candidate; HashGrid::Process' early-out for queries
+            // outside the particle bbox (src/hashgrid.hxx:116-122) is applied when the queries are
+            // keyed for the merge — the camera pass then needs nothing from the grid build (nor
+            // from the all-gather before it) and runs concurrently with both.
+            mergeable = ic.useVM != 0;
             record = mergeable || nv > 0u;
         }
 
@@ -562,7 +552,6 @@ k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ Iter
             }
             else atomicAdd(a.counters + CNT_OVERFLOW, 1ull);
         }
-        warpCount(a.counters + CNT_QUERIES, mergeable ? 1u : 0u);
 
         if(alive)
         {
@@ -862,8 +851,9 @@ k_gridBBox(const __grid_constant__ MergeSet set, int32_t *bboxBits)
     const uint32_t total = mergeSetTotal(set);
     for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
     {
-        if(!mergeSetValid(set, i)) continue;
-        const float4 p = set.posLen[i];
+        const MergeSlot ms = mergeSetSlot(set, i);
+        if(!mergeSetValid(set, ms)) continue;
+        const float4 p = *mergeSetStream(set, set.posLen, ms);
         mn = mk3(fminf(mn.x, p.x), fminf(mn.y, p.y), fminf(mn.z, p.z));
         mx = mk3(fmaxf(mx.x, p.x), fmaxf(mx.y, p.y), fmaxf(mx.z, p.z));
     }
@@ -898,9 +888,10 @@ k_gridKeys(const __grid_constant__ MergeSet set, const int32_t *bboxBits, float 
     for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
     {
         uint32_t key = 0xFFFFFFFFu;
-        if(mergeSetValid(set, i))
+        const MergeSlot ms = mergeSetSlot(set, i);
+        if(mergeSetValid(set, ms))
         {
-            const float4 p = set.posLen[i];
+            const float4 p = *mergeSetStream(set, set.posLen, ms);
             const f3 distMin = xyz(p) - bbMin;
             key = cellHash(int32_t(floorf(invCellSize * distMin.x)), int32_t(floorf(invCellSize * distMin.y)),
                            int32_t(floorf(invCellSize * distMin.z)), numCells);
@@ -1017,10 +1008,11 @@ k_gridScatter(const __grid_constant__ MergeSet set, const __grid_constant__ Grid
         {
             if(key[k] == 0xFFFFFFFFu) continue;
             const uint32_t i = i0 + uint32_t(k) * blockDim.x;
-            g.sPosLen[dst[k]]   = set.posLen[i];
-            g.sThrVcm[dst[k]]   = set.thrVcm[i];
-            g.sDirVm[dst[k]]    = set.dirVm[i];
-            g.sContProb[dst[k]] = set.contProb[i];
+            const MergeSlot ms = mergeSetSlot(set, i);
+            g.sPosLen[dst[k]]   = *mergeSetStream(set, set.posLen, ms);
+            g.sThrVcm[dst[k]]   = *mergeSetStream(set, set.thrVcm, ms);
+            g.sDirVm[dst[k]]    = *mergeSetStream(set, set.dirVm, ms);
+            g.sContProb[dst[k]] = *mergeSetStream(set, set.contProb, ms);
             g.sIndex[dst[k]]    = int32_t(i);
         }
     }
@@ -1034,22 +1026,33 @@ k_gridScatter(const __grid_constant__ MergeSet set, const __grid_constant__ Grid
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SVCM_BLOCK)
 k_queryKeys(const __grid_constant__ QueryStore qs, const unsigned long long *vertexCount, const int32_t *bboxBits,
-            float invCellSize, uint32_t numCells, uint32_t *key, uint32_t *cellCount)
+            float invCellSize, uint32_t numCells, uint32_t *key, uint32_t *cellCount, unsigned long long *counters)
 {
     const uint32_t n = uint32_t(min(*vertexCount, (unsigned long long)qs.capacity));
     const f3 bbMin = mk3(orderedToFloat(bboxBits[0]), orderedToFloat(bboxBits[1]), orderedToFloat(bboxBits[2]));
-    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    const f3 bbMax = mk3(orderedToFloat(bboxBits[3]), orderedToFloat(bboxBits[4]), orderedToFloat(bboxBits[5]));
+    uint32_t nInside = 0u;
+    for(uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x)
     {
+        const uint32_t i = i0 + threadIdx.x;
         uint32_t k = 0xFFFFFFFFu;
-        if(__float_as_uint(qs.q1[i].w) & CAMV_MERGEABLE)
+        if(i < n && (__float_as_uint(qs.q1[i].w) & CAMV_MERGEABLE))
         {
             const float4 p = qs.q0[i];
-            k = cellHash(int32_t(floorf(invCellSize * (p.x - bbMin.x))), int32_t(floorf(invCellSize * (p.y - bbMin.y))),
-                         int32_t(floorf(invCellSize * (p.z - bbMin.z))), numCells);
-            atomicAdd(cellCount + k, 1u);
+            // HashGrid::Process early-out (src/hashgrid.hxx:116-122): such a vertex issues no query
+            const bool inside = !(p.x - bbMin.x < 0.f || bbMax.x - p.x < 0.f || p.y - bbMin.y < 0.f ||
+                                  bbMax.y - p.y < 0.f || p.z - bbMin.z < 0.f || bbMax.z - p.z < 0.f);
+            if(inside)
+            {
+                k = cellHash(int32_t(floorf(invCellSize * (p.x - bbMin.x))), int32_t(floorf(invCellSize * (p.y - bbMin.y))),
+                             int32_t(floorf(invCellSize * (p.z - bbMin.z))), numCells);
+                atomicAdd(cellCount + k, 1u);
+                nInside++;
+            }
         }
-        key[i] = k;
+        if(i < n) key[i] = k;
     }
+    warpCount(counters + CNT_QUERIES, nInside);
 }
 
 __global__ void __launch_bounds__(SVCM_BLOCK)
@@ -1648,13 +1651,13 @@ void launchCameraBounce(const DevScene &sc, const IterConst &ic, const TraceArgs
 }
 
 int launchQuerySort(const IterConst &ic, const QueryStore &queries, const unsigned long long *vertexCount,
-                    const int32_t *bboxBits, const QuerySortBuffers &qs, cudaStream_t stream)
+                    const int32_t *bboxBits, const QuerySortBuffers &qs, unsigned long long *counters, cudaStream_t stream)
 {
     const uint32_t n = ic.numCells + 1u;
     cudaMemsetAsync(qs.cellCount, 0, sizeof(uint32_t) * n, stream);
     const uint32_t gridN = gridFor(queries.capacity, SVCM_BLOCK, 8);
     k_queryKeys<<<gridN, SVCM_BLOCK, 0, stream>>>(queries, vertexCount, bboxBits, ic.invCellSize, ic.numCells,
-                                                  qs.key, qs.cellCount);
+                                                  qs.key, qs.cellCount, counters);
     const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     k_scanTiles<<<tiles, SVCM_BLOCK, 0, stream>>>(qs.cellCount, n, qs.blockSums);
     k_scanSums<<<1, SVCM_BLOCK, 0, stream>>>(qs.blockSums, tiles);
@@ -1680,15 +1683,17 @@ void launchShadow(const DevScene &sc, const IterConst &ic, const TraceArgs &args
 int launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers &grid, cudaStream_t stream)
 {
     const uint32_t n = ic.numCells + 1u;
-    // bbox init: (+1e36, -1e36) like the reference (src/hashgrid.hxx:50-51)
-    cudaMemcpyAsync(grid.bboxBits, grid.bboxInit, sizeof(int32_t) * 6, cudaMemcpyDeviceToDevice, stream);
+    // bbox init: (+1e36, -1e36) like the reference (src/hashgrid.hxx:50-51); for all-gathered
+    // blocks the bbox is already there (union of the block headers, launchGatherUnpackHeaders)
+    const bool bboxReady = set.singleCount == NULL;
+    if(!bboxReady) cudaMemcpyAsync(grid.bboxBits, grid.bboxInit, sizeof(int32_t) * 6, cudaMemcpyDeviceToDevice, stream);
     cudaMemsetAsync(grid.cellCount, 0, sizeof(uint32_t) * n, stream);
     int launches = 0;
     const uint32_t maxTotal = set.singleCount ? set.capacity : set.numSegs * set.segStride;
     if(maxTotal > 0)
     {
         const uint32_t gridN = gridFor(maxTotal, SVCM_BLOCK, 8);
-        k_gridBBox<<<gridN, SVCM_BLOCK, 0, stream>>>(set, grid.bboxBits);
+        if(!bboxReady) k_gridBBox<<<gridN, SVCM_BLOCK, 0, stream>>>(set, grid.bboxBits);
         k_gridKeys<<<gridN, SVCM_BLOCK, 0, stream>>>(set, grid.bboxBits, ic.invCellSize, ic.numCells,
                                                      grid.cellKey, grid.cellCount);
         launches += 2;

@@ -79,11 +79,21 @@ SVCM_D uint32_t mergeSetTotal(const MergeSet &set)
     if(set.singleCount) return uint32_t(min(*set.singleCount, (unsigned long long)set.capacity));
     return set.numSegs * set.segStride;
 }
-SVCM_D bool mergeSetValid(const MergeSet &set, uint32_t i)
+// virtual index -> (block, slot); one block in the single-rank case
+struct MergeSlot { uint32_t seg, j; };
+SVCM_D MergeSlot mergeSetSlot(const MergeSet &set, uint32_t i)
 {
-    if(set.singleCount) return true;
-    const uint32_t seg = i / set.segStride;
-    return (i - seg * set.segStride) < set.segCount[seg];
+    MergeSlot s; s.seg = 0u; s.j = i;
+    if(!set.singleCount) { s.seg = i / set.segStride; s.j = i - s.seg * set.segStride; }
+    return s;
+}
+SVCM_D bool mergeSetValid(const MergeSet &set, MergeSlot s)
+{
+    return set.singleCount ? true : s.j < set.segCountDev[s.seg];
+}
+template<typename T> SVCM_D const T *mergeSetStream(const MergeSet &set, const T *base, MergeSlot s)
+{
+    return reinterpret_cast<const T*>(reinterpret_cast<const unsigned char*>(base) + uint64_t(s.seg) * set.segBytes) + s.j;
 }
 
 // HashGrid::GetCellIndex(Vec3i), reference src/hashgrid.hxx:179-187
