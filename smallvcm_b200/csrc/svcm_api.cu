@@ -145,6 +145,7 @@ struct svcm_renderer
 
     int  iterationsDone;
     int  mergeGroup;
+    uint32_t queriesSizedFor, pairsSizedFor;   // maxPathLength the camera-vertex / pair stores were last sized for
     bool cellLayout;                // SVCM_OPT_GRID_LAYOUT
     int  mergeVariant;              // SVCM_OPT_MERGE_VARIANT
     bool refCandidates;             // SVCM_OPT_REF_CANDIDATES
@@ -332,7 +333,7 @@ void freeQueries(svcm_renderer *r)
     devFree(r->queries.q0); devFree(r->queries.q1); devFree(r->queries.q2); devFree(r->queries.q3);
     devFree(r->queries.q4); devFree(r->pairs.pairs);
     devFree(r->qsort.key); devFree(r->qsort.order);
-    r->queries.capacity = 0; r->pairs.capacity = 0;
+    r->queries.capacity = 0; r->pairs.capacity = 0; r->pairsSizedFor = 0;
 }
 void freeGridSorted(svcm_renderer *r)
 {
@@ -476,8 +477,11 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
     if(!r->lightTraceOnly && !r->pathTrace && !r->eyeLight)
     {
         const uint64_t worst = uint64_t(r->localPaths) * (r->ppm ? 1u : std::max(1u, camBounces - 1u));
-        if(r->queries.capacity < worst && r->queries.capacity < 0xFFFFFF00u)
+        // (a store bounded by free memory stays smaller than the worst case for good: only a longer
+        // path limit is a reason to size it again, not every call)
+        if(r->queries.capacity < worst && r->queries.capacity < 0xFFFFFF00u && maxLen > r->queriesSizedFor)
         {
+            r->queriesSizedFor = maxLen;
             const uint32_t old = r->queries.capacity;
             freeQueries(r);
             cudaMemGetInfo(&freeB, &totalB);
@@ -505,8 +509,9 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
         uint64_t perPath = 0;
         for(uint32_t c = 1; c + 1u < maxLen; c++) perPath += std::min<uint64_t>(lightBounces, maxLen - 1u - c);
         const uint64_t worst = std::max<uint64_t>(1, uint64_t(r->localPaths) * perPath);
-        if(r->pairs.capacity < worst && r->pairs.capacity < 0xFFFFFF00u)
+        if(r->pairs.capacity < worst && r->pairs.capacity < 0xFFFFFF00u && maxLen > r->pairsSizedFor)
         {
+            r->pairsSizedFor = maxLen;
             const uint32_t old = r->pairs.capacity;
             devFree(r->pairs.pairs);
             cudaMemGetInfo(&freeB, &totalB);
@@ -907,6 +912,7 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     r->accumReduced = NULL; r->reducedValid = false;
     r->gridStream = NULL; r->evLightDone = NULL; r->evGridDone = NULL;
     r->iterationsDone = 0; r->mergeGroup = 1; r->profile = false;
+    r->queriesSizedFor = 0; r->pairsSizedFor = 0;
     {
         // defaults; SVCM_GRID_LAYOUT / SVCM_MERGE_VARIANT override them for A/B measurements
         const char *layout = getenv("SVCM_GRID_LAYOUT");
@@ -1076,7 +1082,14 @@ int svcm_run_iterations(svcm_renderer *r, int32_t firstIteration, int32_t count,
     for(int i = 0; i < count; i++)
     {
         // per-iteration counters of the previous iteration are overwritten: check overflow first
-        if(r->statsPending && i > 0) { /* stats of intermediate iterations are not retained */ }
+        // the per-iteration counters live in a ring of SVCM_PROFILE_RING slots: before it wraps,
+        // wait and look at them, so that no iteration's overflow report is ever overwritten unseen
+        if(r->ringHead - r->ringTail >= SVCM_PROFILE_RING - 1)
+        {
+            SVCM_CUDA(r, cudaStreamSynchronize(r->stream));
+            if((rc = finishStats(r))) return rc;
+            r->ringTail = r->ringHead - 1;       // keep the last iteration's record for svcm_get_profile
+        }
         if((rc = runOneIteration(r, firstIteration + i, minPathLength, maxPathLength))) return rc;
     }
     return SVCM_OK;

@@ -366,10 +366,13 @@ k_cellRefKeys(const __grid_constant__ IterConst ic, const __grid_constant__ Grid
     }
 }
 
-// bbox of the particles (reference src/hashgrid.hxx:50-61)
+// bbox of the particles (reference src/hashgrid.hxx:50-61): per-thread min/max, shuffle reduction
+// per warp, shared-memory reduction per block, then six ordered-int atomics per BLOCK (atomics on
+// six addresses from every warp were most of this kernel's time)
 __global__ void __launch_bounds__(SVCM_BLOCK)
 k_cellBBox(const __grid_constant__ MergeSet set, int32_t *bboxBits)
 {
+    __shared__ float sMin[3][SVCM_BLOCK / 32], sMax[3][SVCM_BLOCK / 32];
     f3 mn = mk3(1e36f), mx = mk3(-1e36f);
     const uint32_t total = mergeSetTotal(set);
     for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
@@ -390,14 +393,23 @@ k_cellBBox(const __grid_constant__ MergeSet set, int32_t *bboxBits)
         mx.y = fmaxf(mx.y, __shfl_xor_sync(FULL_MASK, mx.y, o));
         mx.z = fmaxf(mx.z, __shfl_xor_sync(FULL_MASK, mx.z, o));
     }
-    if(laneId() == 0u && mn.x <= mx.x)
+    const uint32_t lane = laneId(), warp = threadIdx.x >> 5;
+    if(lane == 0u)
     {
-        atomicMin(bboxBits + 0, floatToOrdered(mn.x));
-        atomicMin(bboxBits + 1, floatToOrdered(mn.y));
-        atomicMin(bboxBits + 2, floatToOrdered(mn.z));
-        atomicMax(bboxBits + 3, floatToOrdered(mx.x));
-        atomicMax(bboxBits + 4, floatToOrdered(mx.y));
-        atomicMax(bboxBits + 5, floatToOrdered(mx.z));
+        sMin[0][warp] = mn.x; sMin[1][warp] = mn.y; sMin[2][warp] = mn.z;
+        sMax[0][warp] = mx.x; sMax[1][warp] = mx.y; sMax[2][warp] = mx.z;
+    }
+    __syncthreads();
+    if(warp == 0u && lane < 6u)
+    {
+        const bool isMax = lane >= 3u;
+        const float (*src)[SVCM_BLOCK / 32] = isMax ? sMax : sMin;
+        const uint32_t c = isMax ? lane - 3u : lane;
+        float v = src[c][0];
+        for(uint32_t k = 1; k < blockDim.x / 32u; k++) v = isMax ? fmaxf(v, src[c][k]) : fminf(v, src[c][k]);
+        // an empty block holds (+1e36, -1e36): the atomics leave the box as it is
+        if(isMax) atomicMax(bboxBits + lane, floatToOrdered(v));
+        else      atomicMin(bboxBits + lane, floatToOrdered(v));
     }
 }
 

@@ -518,8 +518,15 @@ k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ Iter
         }
 
         const uint32_t qidx = warpAppend64(a.counters + CNT_CAM_VERTS, record);
+        if(record && qidx >= a.queries.capacity)
+        {
+            // store full: the vertex is dropped (reported as an error at the next synchronisation);
+            // it must not reserve pairs either, k_connect would read slots nobody wrote
+            atomicAdd(a.counters + CNT_OVERFLOW, 1ull);
+            record = false; nv = 0u;
+        }
         // pairs (this vertex, k-th vertex of its own light sub-path): contiguous block per lane
-        uint32_t pairBase = 0u;
+        unsigned long long pairBase = 0ull;
         {
             uint32_t inc = record ? nv : 0u;
 #pragma unroll
@@ -532,25 +539,21 @@ k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ Iter
             unsigned long long base = 0ull;
             if(total && laneId() == 31u) base = atomicAdd(a.counters + CNT_PAIRS, (unsigned long long)total);
             base = __shfl_sync(FULL_MASK, base, 31);
-            pairBase = uint32_t(base) + inc - (record ? nv : 0u);
+            pairBase = base + inc - (record ? nv : 0u);
         }
         if(record)
         {
-            if(qidx < a.queries.capacity)
+            a.queries.q0[qidx] = mk4(hitPoint, __uint_as_float(s.extra));
+            a.queries.q1[qidx] = mk4(hit.normal, __uint_as_float(s.length | (uint32_t(hit.matID) << 16) |
+                                                                 (mergeable ? CAMV_MERGEABLE : 0u)));
+            a.queries.q2[qidx] = mk4(bsdf.localDirFix, s.dVCM);
+            a.queries.q3[qidx] = mk4(s.throughput, s.dVM);
+            if(ic.useVC) a.queries.q4[qidx] = make_float4(s.dVC, __uint_as_float(lpath), 0.f, 0.f);
+            for(uint32_t k = 0; k < nv; k++)
             {
-                a.queries.q0[qidx] = mk4(hitPoint, __uint_as_float(s.extra));
-                a.queries.q1[qidx] = mk4(hit.normal, __uint_as_float(s.length | (uint32_t(hit.matID) << 16) |
-                                                                     (mergeable ? CAMV_MERGEABLE : 0u)));
-                a.queries.q2[qidx] = mk4(bsdf.localDirFix, s.dVCM);
-                a.queries.q3[qidx] = mk4(s.throughput, s.dVM);
-                if(ic.useVC) a.queries.q4[qidx] = make_float4(s.dVC, __uint_as_float(lpath), 0.f, 0.f);
-                for(uint32_t k = 0; k < nv; k++)
-                {
-                    if(pairBase + k < a.pairs.capacity) a.pairs.pairs[pairBase + k] = make_uint2(qidx, k);
-                    else atomicAdd(a.counters + CNT_OVERFLOW, 1ull);
-                }
+                if(pairBase + k < (unsigned long long)a.pairs.capacity) a.pairs.pairs[pairBase + k] = make_uint2(qidx, k);
+                else atomicAdd(a.counters + CNT_OVERFLOW, 1ull);
             }
-            else atomicAdd(a.counters + CNT_OVERFLOW, 1ull);
         }
 
         if(alive)

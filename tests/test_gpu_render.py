@@ -69,8 +69,9 @@ def test_t2_same_stream_parity(scene_id, alg):
     ref, _ = orc.accum()
     cnt = orc.counters()
     assert n == iters
-    assert rel_l2(img, ref) <= 6e-2
     pix = np.abs(img - ref).max(2) / (np.abs(ref).max(2) + 1e-3)
+    _log_measured("t2_128", scene=scene_id, alg=alg, rel_l2=rel_l2(img, ref), pixels_off=float((pix > 1e-3).mean()))
+    assert rel_l2(img, ref) <= 6e-2
     assert (pix > 1e-3).mean() <= 1e-2
     assert abs(img.mean() - ref.mean()) <= 5e-3 * ref.mean()
     # workload counters of the last iteration: vertices exact, the rest to within branch flips
@@ -196,6 +197,52 @@ def test_t3_statistical_parity_with_unmodified_reference(scene_id, alg):
     lum = lambda x: float((x.astype(np.float64) @ LUM).mean())
     ref_lum = 0.5 * (lum(a) + lum(b))
     assert abs(lum(img) - ref_lum) <= (0.10 if scene_id == 3 else 0.02) * ref_lum
+
+
+def _log_measured(name, **values):
+    """Measured parity figures, kept next to the run (gpurun_out/ travels back from the GPU box)."""
+    try:
+        import json
+        d = os.path.join(os.path.dirname(GOLD), "..", "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_measured.jsonl"), "a") as f:
+            f.write(json.dumps(dict(test=name, **values)) + "\n")
+    except Exception:
+        pass
+
+
+# (scene, algorithm, width, maxLen, iterations, bound on relative L2): BASELINE.json configs #2, the
+# metric configuration, #3 and #4 at FULL size against the oracle on the same per-path random
+# streams. The oracle runs its path-parallel iteration (tests/test_oracle.py pins it to the serial
+# loop, which is pinned bit-exact to the reference). The L2 bound per configuration is ~3x what was
+# measured (gpurun_out/parity_measured.jsonl); it is carried by the few paths an epsilon branch
+# sends elsewhere — the pixel criterion below is the sharper one.
+FULL_SIZE = [(1, "vcm", 512, 10, 2, 3e-2), (1, "vcm", 1024, 10, 1, 3e-2), (0, "bpt", 1024, 10, 1, 6e-2),
+             (3, "bpm", 2048, 10, 1, 6e-2)]
+
+
+@pytest.mark.parametrize("scene_id,alg,w,max_len,iters,l2_bound", FULL_SIZE,
+                         ids=["config2_s1_vcm_512", "metric_s1_vcm_1024", "config3_s0_bpt_1024", "config4_s3_bpm_2048"])
+def test_t2_full_size_same_stream(scene_id, alg, w, max_len, iters, l2_bound):
+    scene = sv.Scene.cornell_box(scene_id, w, w)
+    img, n, st = render(scene, alg, iters, max_len=max_len)
+    orc = oa.Oracle(scene, abi.ALGORITHMS[alg], seed=1234, rng_mode=1, max_path_length=max_len)
+    for it in range(iters):
+        orc.run_iteration(it, threads=0)
+    ref, _ = orc.accum()
+    cnt = orc.counters()
+    l2 = rel_l2(img, ref)
+    pix = np.abs(img - ref).max(2) / (np.abs(ref).max(2) + 1e-3)
+    off = float((pix > 1e-3).mean())
+    _log_measured("t2_full_size", scene=scene_id, alg=alg, w=w, rel_l2=l2, pixels_off=off,
+                  mean_rel=float(abs(img.mean() - ref.mean()) / ref.mean()))
+    assert n == iters
+    assert l2 <= l2_bound
+    assert off <= 1e-2                                             # pixels off by more than 0.1 %
+    assert abs(img.mean() - ref.mean()) <= 2e-3 * ref.mean()
+    assert abs(st["lightVertices"] - orc.num_light_vertices()) <= 1e-4 * orc.num_light_vertices() + 2
+    for key in ("lightRays", "cameraRays", "shadowRays", "mergeQueries", "mergeCandidates", "mergeAccepted"):
+        assert abs(st[key] - cnt[key]) <= 1e-3 * cnt[key] + 8, (key, st[key], cnt[key])
 
 
 def test_full_size_properties_scene1_vcm_1024():
