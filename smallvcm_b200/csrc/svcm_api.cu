@@ -103,7 +103,7 @@ struct svcm_renderer
     float baseRadius;
 
     // device buffers
-    PathQueue queue[2];
+    PathQueue queue[4];             // [0], [1]: light pass (and the unidirectional walks); [2], [3]: camera pass
     uint32_t *queueCountsLight, *queueCountsCamera;   // [countsAlloc]
     uint32_t  countsAlloc;
     VertexStore verts;
@@ -142,6 +142,11 @@ struct svcm_renderer
     // the grid is built on its own stream, concurrently with the camera pass
     cudaStream_t gridStream;
     cudaEvent_t  evLightDone, evGridDone;
+    // ... and the camera sub-paths on a third one, concurrently with the light pass (they meet at
+    // the vertex connection)
+    cudaStream_t cameraStream;
+    cudaEvent_t  evIterStart, evCameraDone;
+    bool overlapPasses;             // SVCM_NO_PASS_OVERLAP=1 serialises them again (A/B)
 
     int  iterationsDone;
     int  mergeGroup;
@@ -629,6 +634,43 @@ int gatherLightVertices(svcm_renderer *r, MergeSet &set, cudaStream_t st, int sl
     return SVCM_OK;
 }
 
+// The visibility queue is one allocation; the light pass (one segment per splatted light vertex)
+// and the camera pass (direct illumination + vertex connections) fill disjoint parts of it, so the
+// two passes can run concurrently. counts[0] / counts[1] are their fill levels.
+ShadowQueue lightShadow(const svcm_renderer *r)
+{
+    ShadowQueue q = r->shadow;
+    if(!r->lightTraceOnly && !r->pathTrace) q.capacity = r->shadow.capacity / 4u;
+    return q;
+}
+ShadowQueue cameraShadow(const svcm_renderer *r)
+{
+    ShadowQueue q = r->shadow;
+    if(r->lightTraceOnly || r->pathTrace) return q;
+    const uint32_t skip = r->shadow.capacity / 4u;
+    q.r0 += skip; q.r1 += skip; q.r2 += skip;
+    q.capacity = r->shadow.capacity - skip;
+    return q;
+}
+
+// the camera walk (src/vertexcm.hxx:415-545 without connection and merging): maxLen bounce kernels
+int enqueueCameraBounces(svcm_renderer *r, const IterConst &ic, const TraceArgs &base, uint32_t maxLen, cudaStream_t cs,
+                         cudaEvent_t *ev)
+{
+    TraceArgs c = base;
+    c.queueCounts = r->queueCountsCamera;
+    c.shadow = cameraShadow(r);
+    const uint32_t camBounces = std::max(1u, maxLen);
+    if(ev) cudaEventRecord(ev[2], cs);
+    for(uint32_t b = 1; b <= camBounces; b++)
+    {
+        c.in = r->queue[2 + ((b + 1) & 1)]; c.out = r->queue[2 + (b & 1)];
+        launchCameraBounce(r->scene, ic, c, b, r->localPaths, cs);
+    }
+    if(ev) cudaEventRecord(ev[3], cs);
+    return int(camBounces);
+}
+
 // One iteration: the kernel schedule that replaces the two serial per-pixel loops
 static double hostNowMs()
 {
@@ -703,9 +745,19 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
         return SVCM_OK;
     }
 
+    // ---- fork: the camera walk runs on its own stream, concurrently with the light pass ---------
+    if(!r->lightTraceOnly && r->overlapPasses)
+    {
+        SVCM_CUDA(r, cudaEventRecord(r->evIterStart, st));
+        SVCM_CUDA(r, cudaStreamWaitEvent(r->cameraStream, r->evIterStart, 0));
+        launches += enqueueCameraBounces(r, ic, a, maxLen, r->cameraStream, timed ? ev : NULL);
+        SVCM_CUDA(r, cudaEventRecord(r->evCameraDone, r->cameraStream));
+    }
+
     // ---- light sub-paths (reference src/vertexcm.hxx:321-396) -----------------------------
     const uint32_t lightBounces = std::max(1u, maxLen > 0 ? maxLen - 1u : 0u);
     a.queueCounts = r->queueCountsLight;
+    a.shadow = lightShadow(r);
     for(uint32_t b = 1; b <= lightBounces; b++)
     {
         a.in = r->queue[(b + 1) & 1]; a.out = r->queue[b & 1];
@@ -756,21 +808,21 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     th[3] = hostNowMs();
 
     // ---- camera sub-paths (src/vertexcm.hxx:415-545) ---------------------------------------
+    // The walk itself needs nothing from the light pass: its bounces were enqueued on the camera
+    // stream before the light pass (below `forkCamera`); here the two passes meet for the vertex
+    // connection of every (camera vertex, stored light vertex of the same path) pair.
     if(!r->lightTraceOnly)
     {
-        const uint32_t camBounces = std::max(1u, maxLen);
-        a.queueCounts = r->queueCountsCamera;
-        for(uint32_t b = 1; b <= camBounces; b++)
-        {
-            a.in = r->queue[(b + 1) & 1]; a.out = r->queue[b & 1];
-            launchCameraBounce(r->scene, ic, a, b, r->localPaths, st);
-            launches++;
-        }
+        if(r->overlapPasses) SVCM_CUDA(r, cudaStreamWaitEvent(st, r->evCameraDone, 0));
+        else launches += enqueueCameraBounces(r, ic, a, maxLen, st, timed ? ev : NULL);
         if(r->useVC)
         {
-            launchConnect(r->scene, ic, a, st);       // every (camera vertex, light vertex) pair
-            launchShadow(r->scene, ic, a, 1, st);     // direct-illumination + connection visibility
-            launches += 2;
+            TraceArgs c = a;
+            c.queueCounts = r->queueCountsCamera;
+            c.shadow = cameraShadow(r);
+            launchConnect(r->scene, ic, c, st);       // pair list, then every (camera vertex, light vertex) pair
+            launchShadow(r->scene, ic, c, 1, st);     // direct-illumination + connection visibility
+            launches += 3;
         }
     }
     if(timed) cudaEventRecord(ev[4], st);
@@ -911,6 +963,8 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     r->devCounts64 = NULL; r->hostCounts64 = NULL;
     r->accumReduced = NULL; r->reducedValid = false;
     r->gridStream = NULL; r->evLightDone = NULL; r->evGridDone = NULL;
+    r->cameraStream = NULL; r->evIterStart = NULL; r->evCameraDone = NULL;
+    r->overlapPasses = !(getenv("SVCM_NO_PASS_OVERLAP") && atoi(getenv("SVCM_NO_PASS_OVERLAP")) != 0);
     r->iterationsDone = 0; r->mergeGroup = 1; r->profile = false;
     r->queriesSizedFor = 0; r->pairsSizedFor = 0;
     {
@@ -973,7 +1027,9 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     if((rc = uploadGeometry(r, scene, r->scene, r->geometry))) SVCM_CREATE_FAIL(rc);
     SVCM_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
     for(int i = 0; i < SVCM_NUM_USER_EVENTS; i++) SVCM_TRY(cudaEventCreate(&r->userEv[i]));
-    for(int i = 0; i < 2; i++) if((rc = allocQueue(r, r->queue[i], r->localPaths))) SVCM_CREATE_FAIL(rc);
+    const bool bidirectional = params->algorithm != SVCM_ALG_PATH_TRACE && params->algorithm != SVCM_ALG_EYE_LIGHT &&
+                               params->algorithm != SVCM_ALG_LIGHT_TRACE;
+    for(int i = 0; i < (bidirectional ? 4 : 2); i++) if((rc = allocQueue(r, r->queue[i], r->localPaths))) SVCM_CREATE_FAIL(rc);
     if((rc = devAlloc(r, &r->pathVertCount, r->localPaths))) SVCM_CREATE_FAIL(rc);
     if((rc = devAlloc(r, &r->counters, CNT_WORDS))) SVCM_CREATE_FAIL(rc);
     if((rc = devAlloc(r, &r->accum, size_t(r->paths) * 3))) SVCM_CREATE_FAIL(rc);
@@ -984,6 +1040,9 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     SVCM_TRY(cudaStreamCreateWithFlags(&r->gridStream, cudaStreamNonBlocking));
     SVCM_TRY(cudaEventCreateWithFlags(&r->evLightDone, cudaEventDisableTiming));
     SVCM_TRY(cudaEventCreateWithFlags(&r->evGridDone, cudaEventDisableTiming));
+    SVCM_TRY(cudaStreamCreateWithFlags(&r->cameraStream, cudaStreamNonBlocking));
+    SVCM_TRY(cudaEventCreateWithFlags(&r->evIterStart, cudaEventDisableTiming));
+    SVCM_TRY(cudaEventCreateWithFlags(&r->evCameraDone, cudaEventDisableTiming));
     SVCM_TRY(cudaMallocHost((void**)&r->hostCounters, sizeof(unsigned long long) * CNT_WORDS * SVCM_PROFILE_RING));
     SVCM_TRY(cudaMallocHost((void**)&r->hostCounts64, sizeof(unsigned long long) * 8 * SVCM_PROFILE_RING));
     memset(r->hostCounters, 0, sizeof(unsigned long long) * CNT_WORDS * SVCM_PROFILE_RING);
@@ -1008,7 +1067,10 @@ void svcm_destroy(svcm_renderer *r)
     cudaSetDevice(r->device);
     if(r->stream) cudaStreamSynchronize(r->stream);
     if(r->comm && ncclApi()->lib) ncclApi()->CommDestroy(r->comm);
-    freeQueue(r->queue[0]); freeQueue(r->queue[1]);
+    for(int i = 0; i < 4; i++) freeQueue(r->queue[i]);
+    if(r->cameraStream) { cudaStreamSynchronize(r->cameraStream); cudaStreamDestroy(r->cameraStream); }
+    if(r->evIterStart) cudaEventDestroy(r->evIterStart);
+    if(r->evCameraDone) cudaEventDestroy(r->evCameraDone);
     devFree(r->queueCountsLight); devFree(r->queueCountsCamera);
     devFree(r->shadow.r0); devFree(r->shadow.r1); devFree(r->shadow.r2); devFree(r->shadow.counts);
     freeVerts(r); freeQueries(r); freeGridSorted(r);

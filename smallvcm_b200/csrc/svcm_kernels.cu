@@ -491,7 +491,7 @@ k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ Iter
         // consume the record later (k_connect, k_merge*) — neither draws random numbers nor
         // steers the walk, so deferring them changes nothing but the order of summation
         bool record = false, mergeable = false;
-        uint32_t nv = 0u, lpath = 0u;
+        uint32_t lpath = 0u;
         if(alive && !bsdf.isDelta())
         {
             if(ic.useVC)
@@ -504,56 +504,31 @@ k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ Iter
                     if(!iszero(c)) emitShadowRay<kBvh>(sc, a.shadow, 1u, a.accum, hitPoint, dir, dist, s.extra, c);
                 }
                 lpath = globalToLocalPath(ic, s.path);
-                // the k-th stored light vertex has path length >= k+1, so only the first
-                // maxLen-1-length of them can pass the window of src/vertexcm.hxx:519-521
-                nv = a.pathVertCount[lpath];
-                nv = min(nv, ic.maxLen - 1u - s.length);
             }
             // Every non-delta vertex is a merge candidate; HashGrid::Process' early-out for queries
             // outside the particle bbox (src/hashgrid.hxx:116-122) is applied when the queries are
             // keyed for the merge — the camera pass then needs nothing from the grid build (nor
             // from the all-gather before it) and runs concurrently with both.
             mergeable = ic.useVM != 0;
-            record = mergeable || nv > 0u;
+            // vertex connection pairs this vertex with the stored vertices of its own light sub-path
+            // (k_makePairs, once both passes are through): possible while a connected path of
+            // length + 1 + (>= 1) still fits the limit
+            record = mergeable || (ic.useVC && s.length + 2u <= ic.maxLen);
         }
 
         const uint32_t qidx = warpAppend64(a.counters + CNT_CAM_VERTS, record);
-        if(record && qidx >= a.queries.capacity)
-        {
-            // store full: the vertex is dropped (reported as an error at the next synchronisation);
-            // it must not reserve pairs either, k_connect would read slots nobody wrote
-            atomicAdd(a.counters + CNT_OVERFLOW, 1ull);
-            record = false; nv = 0u;
-        }
-        // pairs (this vertex, k-th vertex of its own light sub-path): contiguous block per lane
-        unsigned long long pairBase = 0ull;
-        {
-            uint32_t inc = record ? nv : 0u;
-#pragma unroll
-            for(int o = 1; o < 32; o <<= 1)
-            {
-                const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o);
-                if(laneId() >= uint32_t(o)) inc += t;
-            }
-            const uint32_t total = __shfl_sync(FULL_MASK, inc, 31);
-            unsigned long long base = 0ull;
-            if(total && laneId() == 31u) base = atomicAdd(a.counters + CNT_PAIRS, (unsigned long long)total);
-            base = __shfl_sync(FULL_MASK, base, 31);
-            pairBase = base + inc - (record ? nv : 0u);
-        }
         if(record)
         {
-            a.queries.q0[qidx] = mk4(hitPoint, __uint_as_float(s.extra));
-            a.queries.q1[qidx] = mk4(hit.normal, __uint_as_float(s.length | (uint32_t(hit.matID) << 16) |
-                                                                 (mergeable ? CAMV_MERGEABLE : 0u)));
-            a.queries.q2[qidx] = mk4(bsdf.localDirFix, s.dVCM);
-            a.queries.q3[qidx] = mk4(s.throughput, s.dVM);
-            if(ic.useVC) a.queries.q4[qidx] = make_float4(s.dVC, __uint_as_float(lpath), 0.f, 0.f);
-            for(uint32_t k = 0; k < nv; k++)
+            if(qidx < a.queries.capacity)
             {
-                if(pairBase + k < (unsigned long long)a.pairs.capacity) a.pairs.pairs[pairBase + k] = make_uint2(qidx, k);
-                else atomicAdd(a.counters + CNT_OVERFLOW, 1ull);
+                a.queries.q0[qidx] = mk4(hitPoint, __uint_as_float(s.extra));
+                a.queries.q1[qidx] = mk4(hit.normal, __uint_as_float(s.length | (uint32_t(hit.matID) << 16) |
+                                                                     (mergeable ? CAMV_MERGEABLE : 0u)));
+                a.queries.q2[qidx] = mk4(bsdf.localDirFix, s.dVCM);
+                a.queries.q3[qidx] = mk4(s.throughput, s.dVM);
+                if(ic.useVC) a.queries.q4[qidx] = make_float4(s.dVC, __uint_as_float(lpath), 0.f, 0.f);
             }
+            else atomicAdd(a.counters + CNT_OVERFLOW, 1ull);   // dropped: an error at the next synchronisation
         }
 
         if(alive)
@@ -571,6 +546,45 @@ k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ Iter
     }
 
     warpCount(a.counters + CNT_CAMERA_RAYS, nRays);
+}
+
+// The pair list of vertex connection (reference src/vertexcm.hxx:498-526: every camera vertex
+// against the stored vertices of ITS light sub-path): one lane per recorded camera vertex reserves
+// a contiguous block of (vertex, k) pairs. Runs once both passes are through — the camera pass no
+// longer reads anything the light pass writes and the two run concurrently.
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_makePairs(const __grid_constant__ IterConst ic, const __grid_constant__ TraceArgs a)
+{
+    const uint32_t count = uint32_t(min(a.counters[CNT_CAM_VERTS], (unsigned long long)a.queries.capacity));
+    for(uint32_t i0 = blockIdx.x * blockDim.x; i0 < count; i0 += gridDim.x * blockDim.x)
+    {
+        const uint32_t i = i0 + threadIdx.x;
+        uint32_t nv = 0u;
+        if(i < count)
+        {
+            const uint32_t camLen = __float_as_uint(a.queries.q1[i].w) & 0xFFFFu;
+            const uint32_t lpath = __float_as_uint(a.queries.q4[i].y);
+            // the k-th stored light vertex has path length >= k+1, so only the first
+            // maxLen-1-length of them can pass the window of src/vertexcm.hxx:519-521
+            nv = (camLen + 1u < ic.maxLen) ? min(uint32_t(a.pathVertCount[lpath]), ic.maxLen - 1u - camLen) : 0u;
+        }
+        uint32_t inc = nv;
+#pragma unroll
+        for(int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o);
+            if(laneId() >= uint32_t(o)) inc += t;
+        }
+        const uint32_t total = __shfl_sync(FULL_MASK, inc, 31);
+        unsigned long long base = 0ull;
+        if(total && laneId() == 31u) base = atomicAdd(a.counters + CNT_PAIRS, (unsigned long long)total);
+        base = __shfl_sync(FULL_MASK, base, 31) + inc - nv;
+        for(uint32_t k = 0; k < nv; k++)
+        {
+            if(base + k < (unsigned long long)a.pairs.capacity) a.pairs.pairs[base + k] = make_uint2(i, k);
+            else atomicAdd(a.counters + CNT_OVERFLOW, 1ull);
+        }
+    }
 }
 
 // Vertex connection (reference src/vertexcm.hxx:498-526 + ConnectVertices :743-809), one lane
@@ -1671,6 +1685,7 @@ int launchQuerySort(const IterConst &ic, const QueryStore &queries, const unsign
 
 void launchConnect(const DevScene &sc, const IterConst &ic, const TraceArgs &args, cudaStream_t stream)
 {
+    k_makePairs<<<gridFor(args.queries.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(ic, args);
     if(sc.bvh) k_connect<true><<<gridFor(args.pairs.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args);
     else       k_connect<false><<<gridFor(args.pairs.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args);
 }

@@ -33,21 +33,31 @@ def _worker(rank, world, port, cfg, out):
     r.max_path_length = 10
     uid = sv.comm_unique_id() if rank == 0 else None
     r.comm_init(D.broadcast_bytes(uid, abi.COMM_ID_BYTES, 0))
-    r.run_iterations(0, iters)
-    st = r.stats()
+    if os.environ.get("SVCM_TEST_LAYOUT"):
+        r.set_option(abi.OPT_GRID_LAYOUT, int(os.environ["SVCM_TEST_LAYOUT"]))
+    # two calls with a synchronisation in between: the second sizes its all-gather blocks from the
+    # counts the first one saw (a different block stride, hence a different buffer layout)
+    r.run_iterations(0, 1)
+    st0 = r.stats()
     r.reduce_accum(0)
+    first, n1 = r.accum()
+    r.run_iterations(1, iters - 1)
+    st = r.stats()
+    r.reduce_accum(0)                    # reducing again must not count the first iteration twice
     img, n = r.accum()
     out[rank] = (img if rank == 0 else None, n, st["lightVertices"], st["localLightVertices"], st["localPaths"],
-                 st["mergeQueries"])
+                 st["mergeQueries"], first if rank == 0 else None, n1)
     r.close()
     D.barrier()
 
 
-@pytest.mark.parametrize("cfg", [(1, "vcm", 128, 96, 2), (3, "bpm", 96, 96, 2), (0, "bpt", 96, 64, 2)])
-def test_two_rank_render_equals_single_gpu(cfg):
+@pytest.mark.parametrize("layout", ["0", "1"])
+@pytest.mark.parametrize("cfg", [(1, "vcm", 128, 96, 3), (3, "bpm", 96, 96, 2), (0, "bpt", 96, 64, 2)])
+def test_two_rank_render_equals_single_gpu(cfg, layout, monkeypatch):
     lib = sv.load_library()
     if lib.svcm_device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("SVCM_TEST_LAYOUT", layout)
     import torch.multiprocessing as mp
     world = 2
     with mp.Manager() as m:
@@ -58,7 +68,10 @@ def test_two_rank_render_equals_single_gpu(cfg):
     scene = sv.Scene.cornell_box(scene_id, w, h)
     r = sv.VertexCM(scene, alg, seed=1234)
     r.max_path_length = 10
-    r.run_iterations(0, iters)
+    r.set_option(abi.OPT_GRID_LAYOUT, int(layout))
+    r.run_iterations(0, 1)
+    ref_first, _ = r.accum()
+    r.run_iterations(1, iters - 1)
     ref, n = r.accum()
     st = r.stats()
     r.close()
@@ -71,3 +84,6 @@ def test_two_rank_render_equals_single_gpu(cfg):
         assert abs(res[0][5] + res[1][5] - st["mergeQueries"]) <= 2
     rel = np.linalg.norm(img.astype(np.float64) - ref) / np.linalg.norm(ref.astype(np.float64))
     assert rel < 1e-5, rel
+    first = res[0][6]
+    assert res[0][7] == 1
+    assert np.linalg.norm(first.astype(np.float64) - ref_first) / np.linalg.norm(ref_first.astype(np.float64)) < 1e-5
