@@ -107,7 +107,7 @@ struct svcm_renderer
     uint32_t *queueCountsLight, *queueCountsCamera;   // [countsAlloc]
     uint32_t  countsAlloc;
     VertexStore verts;
-    uint32_t  vertSlots;            // rows of verts.pathVerts
+    uint32_t  vertSlots;            // connection slots per path the store was sized for (maxPathLength - 1)
     uint8_t  *pathVertCount;
     QueryStore queries;             // camera vertices (connection + merge consumers)
     PairStore pairs;
@@ -315,8 +315,8 @@ void freeVerts(svcm_renderer *r)
         freeGather(r);
     }
     devFree(r->verts.posLen); devFree(r->verts.thrVcm); devFree(r->verts.dirVm); devFree(r->verts.contProb);
-    devFree(r->verts.nrmVc); devFree(r->verts.ldfMat); devFree(r->verts.pathVerts);
-    r->verts.capacity = 0; r->vertSlots = 0;
+    devFree(r->verts.conn);
+    r->verts.capacity = 0; r->vertSlots = 0; r->verts.connSlots = 0;
 }
 
 // bytes of one all-gather block holding `slots` records, and the stream offsets inside it
@@ -434,9 +434,16 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
         cudaMemGetInfo(&freeB, &totalB);
         const uint64_t worst = uint64_t(r->localPaths) * lightBounces;
         const uint32_t ws = uint32_t(r->params.worldSize);
-        // bytes per local vertex: merge record 52 + connection extras 32, plus per rank the gathered
-        // copy (sharded runs) and the cell-sorted copy with its key
-        const uint64_t perVertex = 84u + (r->useVM ? (ws > 1u ? 112u * ws : 60u) : 0u) + 6u;
+        // the path-major connection records have a slot for every possible vertex, whatever is stored
+        if(r->useVC)
+        {
+            if((rc = devAlloc(r, &r->verts.conn, size_t(r->localPaths) * lightBounces * 4u))) return rc;
+            r->verts.connSlots = lightBounces;
+            cudaMemGetInfo(&freeB, &totalB);
+        }
+        // bytes per stored vertex: merge record 52, plus per rank the gathered copy (sharded runs)
+        // and the cell-sorted copy with its key
+        const uint64_t perVertex = 52u + (r->useVM ? (ws > 1u ? 112u * ws : 60u) : 0u) + 6u;
         const uint64_t budget = uint64_t(double(freeB) * 0.45);
         uint64_t cap = std::min<uint64_t>(worst, budget / perVertex);
         cap = std::min<uint64_t>(cap, 0xFFFFFF00u / ws);
@@ -458,9 +465,6 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
             if((rc = devAlloc(r, &r->verts.dirVm, cap))) return rc;
             if((rc = devAlloc(r, &r->verts.contProb, cap))) return rc;
         }
-        if((rc = devAlloc(r, &r->verts.nrmVc, cap))) return rc;
-        if((rc = devAlloc(r, &r->verts.ldfMat, cap))) return rc;
-        if((rc = devAlloc(r, &r->verts.pathVerts, size_t(lightBounces) * r->localPaths))) return rc;
         r->verts.capacity = uint32_t(cap);
         r->vertSlots = lightBounces;
         if(r->useVM)

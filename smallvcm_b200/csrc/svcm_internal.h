@@ -44,19 +44,24 @@ struct PathQueue
 };
 enum { PATH_FLAG_FINITE = 1u << 30, PATH_FLAG_SPECULAR = 1u << 31, PATH_LEN_MASK = (1u << 30) - 1u };
 
-// Light vertices of the LOCAL light sub-paths (PathVertex<true>, src/vertexcm.hxx:79-98),
-// split by consumer:
-//   merge record (52 B, all-gathered and cell-sorted): posLen, thrVcm, dirVm, contProb
-//   connection extras (local only)                   : nrmVc, ldfMat
+// Light vertices of the LOCAL light sub-paths (PathVertex<true>, src/vertexcm.hxx:79-98), stored
+// twice, once per consumer:
+//   merge record (52 B, all-gathered and cell-sorted; only when merging): posLen, thrVcm, dirVm,
+//     contProb, in the order the vertices were created
+//   connection record (64 B, local; only when connecting): `conn`, PATH-MAJOR — the k-th stored
+//     vertex of local path l lies at conn[(l * connSlots + k) * 4 .. +3], so the vertices one
+//     camera vertex connects to (its own light sub-path, src/vertexcm.hxx:504-506) are contiguous:
+//       [0] hitpoint.xyz | pathLength   [1] throughput.xyz | dVCM
+//       [2] shading normal.xyz | dVC    [3] local fixed direction.xyz | matID
+//     pathVertCount[l] says how many there are (replaces mPathEnds)
 struct VertexStore
 {
     float4  *posLen;    // hitpoint.xyz | pathLength (bits)
     float4  *thrVcm;    // throughput.xyz | dVCM
     float4  *dirVm;     // WorldDirFix().xyz | dVM
     float   *contProb;  // light BSDF continuation probability
-    float4  *nrmVc;     // shading normal.xyz | dVC
-    float4  *ldfMat;    // local fixed direction.xyz | matID (bits)
-    int32_t *pathVerts; // [slot k][local path] -> vertex index   (replaces mPathEnds)
+    float4  *conn;      // connection records, 4 x float4 per slot
+    uint32_t connSlots; // slots per path (maxPathLength - 1)
     uint32_t capacity;
 };
 

@@ -263,16 +263,27 @@ k_lightBounce(const __grid_constant__ DevScene sc, const __grid_constant__ IterC
         {
             if(vidx < a.verts.capacity)
             {
-                a.verts.posLen[vidx]   = mk4(hitPoint, __uint_as_float(s.length));
-                a.verts.thrVcm[vidx]   = mk4(s.throughput, s.dVCM);
-                a.verts.dirVm[vidx]    = mk4(bsdf.worldDirFix(), s.dVM);
-                a.verts.contProb[vidx] = bsdf.contProb;
-                a.verts.nrmVc[vidx]    = mk4(bsdf.frame.z, s.dVC);
-                a.verts.ldfMat[vidx]   = mk4(bsdf.localDirFix, __int_as_float(bsdf.matID));
-                const uint32_t l = globalToLocalPath(ic, s.path);
-                a.verts.pathVerts[size_t(s.extra) * ic.localPaths + l] = int32_t(vidx);
-                s.extra++;
-                a.pathVertCount[l] = uint8_t(s.extra);
+                const float4 posLen = mk4(hitPoint, __uint_as_float(s.length));
+                const float4 thrVcm = mk4(s.throughput, s.dVCM);
+                if(ic.useVM)
+                {
+                    a.verts.posLen[vidx]   = posLen;
+                    a.verts.thrVcm[vidx]   = thrVcm;
+                    a.verts.dirVm[vidx]    = mk4(bsdf.worldDirFix(), s.dVM);
+                    a.verts.contProb[vidx] = bsdf.contProb;
+                }
+                if(ic.useVC)
+                {
+                    // path-major connection record: 64 contiguous bytes, two full sectors
+                    const uint32_t l = globalToLocalPath(ic, s.path);
+                    float4 *rec = a.verts.conn + (size_t(l) * a.verts.connSlots + s.extra) * 4u;
+                    rec[0] = posLen;
+                    rec[1] = thrVcm;
+                    rec[2] = mk4(bsdf.frame.z, s.dVC);
+                    rec[3] = mk4(bsdf.localDirFix, __int_as_float(bsdf.matID));
+                    s.extra++;
+                    a.pathVertCount[l] = uint8_t(s.extra);
+                }
             }
             else atomicAdd(a.counters + CNT_OVERFLOW, 1ull);
         }
@@ -606,14 +617,16 @@ k_connect(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst
         const uint32_t camLen = bits & 0xFFFFu;
         const uint32_t lpath = __float_as_uint(q4.y);
 
-        const int32_t vi = a.verts.pathVerts[size_t(pr.y) * ic.localPaths + lpath];
-        const float4 pl = a.verts.posLen[vi];
+        // the k-th stored vertex of the camera vertex's own light sub-path: the lanes of one camera
+        // vertex read consecutive 64-byte records
+        const float4 *rec = a.verts.conn + (size_t(lpath) * a.verts.connSlots + pr.y) * 4u;
+        const float4 pl = rec[0];
         const uint32_t lvLen = __float_as_uint(pl.w);
         // path-length window, src/vertexcm.hxx:512-521
         if(lvLen + 1u + camLen < ic.minLen || lvLen + 1u + camLen > ic.maxLen) continue;
-        const float4 tv = a.verts.thrVcm[vi];
-        const float4 nv4 = a.verts.nrmVc[vi];
-        const float4 lm = a.verts.ldfMat[vi];
+        const float4 tv = rec[1];
+        const float4 nv4 = rec[2];
+        const float4 lm = rec[3];
 
         Bsdf camBsdf;                      // BSDF<false>::Setup at the camera vertex
         camBsdf.frame.setFromZ(xyz(q1));
