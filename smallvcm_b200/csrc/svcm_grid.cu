@@ -500,9 +500,9 @@ SVCM_D void parkQuery(float (*q)[32], uint32_t lane, const Bsdf &bsdf, float len
 // RangeQuery::Process (reference src/vertexcm.hxx:130-169) for the particle at sorted slot `idx`
 // and the query parked by lane `owner`; the result is added to the owner's sums
 SVCM_D void evaluatePair(const DevScene &sc, const IterConst &ic, const GridBuffers &g, float (*q)[32],
-                         float (*acc)[32], uint32_t idx, uint32_t owner)
+                         float (*acc)[32], uint32_t idx, uint32_t owner, float lenBits, float weight)
 {
-    const uint32_t lvLen = __float_as_uint(reinterpret_cast<const float*>(g.sPosLen + idx)[3]);
+    const uint32_t lvLen = __float_as_uint(lenBits);
     const uint32_t lenMat = __float_as_uint(q[12][owner]);
     const uint32_t camLen = lenMat & 0xFFFFu;
     const uint32_t camMat = (lenMat >> 16) & 0xFFu;
@@ -525,7 +525,7 @@ SVCM_D void evaluatePair(const DevScene &sc, const IterConst &ic, const GridBuff
     const float wLight  = tv.w * ic.misVcWeightFactor + dv.w * camDirPdfW;                 // (38)
     const float wCamera = q[16][owner] * ic.misVcWeightFactor + q[17][owner] * camRevPdfW; // (39)
     const float misWeight = ic.ppm ? 1.f : 1.f / (wLight + 1.f + wCamera);
-    const f3 c = (misWeight * f) * xyz(tv);
+    const f3 c = ((misWeight * weight) * f) * xyz(tv);   // `weight` visits of the reference add `weight` times this
     atomicAdd(&acc[0][owner], c.x);
     atomicAdd(&acc[1][owner], c.y);
     atomicAdd(&acc[2][owner], c.z);
@@ -657,8 +657,11 @@ k_mergeCellLane(const __grid_constant__ DevScene sc, const __grid_constant__ Ite
                 __syncwarp();
                 if(tail - head >= 32u)
                 {
-                    if(head + lane < head + 32u)
-                        evaluatePair(sc, ic, g, w.q, w.acc, w.queue[(head + lane) & 63u], w.queueOwner[(head + lane) & 63u]);
+                    {
+                        const uint32_t pi = w.queue[(head + lane) & 63u];
+                        evaluatePair(sc, ic, g, w.q, w.acc, pi, w.queueOwner[(head + lane) & 63u],
+                                     reinterpret_cast<const float*>(g.sPosLen + pi)[3], 1.f);
+                    }
                     __syncwarp();
                     head += 32u;
                 }
@@ -667,7 +670,11 @@ k_mergeCellLane(const __grid_constant__ DevScene sc, const __grid_constant__ Ite
         if(tail != head)
         {
             if(head + lane < tail)
-                evaluatePair(sc, ic, g, w.q, w.acc, w.queue[(head + lane) & 63u], w.queueOwner[(head + lane) & 63u]);
+            {
+                const uint32_t pi = w.queue[(head + lane) & 63u];
+                evaluatePair(sc, ic, g, w.q, w.acc, pi, w.queueOwner[(head + lane) & 63u],
+                             reinterpret_cast<const float*>(g.sPosLen + pi)[3], 1.f);
+            }
         }
         __syncwarp();
 
@@ -729,21 +736,29 @@ SVCM_D void bulkLoad(void *dstSmem, const void *srcGlobal, uint32_t bytes, unsig
 #define ST_XSPAN 6          // storage cells along x one sub-chunk may span
 #define ST_RUNS 9           // 3 x 3 rows around the sub-chunk's row
 
+// the staged kernel parks five more words per query: its cell (px, py, pz), the side of the second
+// cell on every axis, and the bucket multiplicities — the accept weight of a pair is worked out when
+// the pair is evaluated (all lanes busy), not inside the candidate walk
+#define SQ_WORDS (CQ_WORDS + 5)
+
 template<int PCAP, int LCAP>
 struct alignas(128) StagedWarpSmem
 {
     float4   stage[2][PCAP];            // staged positions | path length
-    uint32_t list[LCAP][32];            // accepted sorted slots, [entry][lane]
-    float    q[CQ_WORDS][32];
+    uint32_t list[LCAP][32];            // in-range sorted slots, [entry][lane]
+    float    q[SQ_WORDS][32];
     float    acc[3][32];
+    uint32_t nacc[32];                  // accepted pairs per owner, counted like the reference does
     uint32_t pref[32];
     unsigned long long bar[2];
 };
 
-// evaluates every listed pair of the warp, 32 per step; empties the lists
+// evaluates every listed pair of the warp, 32 per step; empties the lists. A listed pair is in
+// range; how often the reference counts it (the bucket multiplicity of the particle's own cell, 0 if
+// that cell is not one of the query's 8) is worked out here from the parked cell words.
 template<int PCAP, int LCAP>
 SVCM_D void flushLists(const DevScene &sc, const IterConst &ic, const GridBuffers &g, StagedWarpSmem<PCAP, LCAP> &w,
-                       uint32_t &cnt)
+                       f3 bbMin, uint32_t &cnt)
 {
     const uint32_t lane = laneId();
     uint32_t inc = cnt;
@@ -765,7 +780,20 @@ SVCM_D void flushLists(const DevScene &sc, const IterConst &ic, const GridBuffer
             uint32_t o = 0u;                      // the lane whose list holds pair p: pref[o] <= p < pref[o + 1]
 #pragma unroll
             for(int s = 16; s > 0; s >>= 1) if(w.pref[o + uint32_t(s)] <= p) o += uint32_t(s);
-            evaluatePair(sc, ic, g, w.q, w.acc, w.list[p - w.pref[o]][o], o);
+            const uint32_t idx = w.list[p - w.pref[o]][o];
+            const float4 pl = g.sPosLen[idx];
+            QueryCells c;
+            c.px = __float_as_int(w.q[CQ_WORDS + 0][o]); c.py = __float_as_int(w.q[CQ_WORDS + 1][o]);
+            c.pz = __float_as_int(w.q[CQ_WORDS + 2][o]);
+            const uint32_t side = __float_as_uint(w.q[CQ_WORDS + 3][o]);
+            c.pxo = c.px + ((side & 4u) ? 1 : -1); c.pyo = c.py + ((side & 2u) ? 1 : -1); c.pzo = c.pz + ((side & 1u) ? 1 : -1);
+            c.mults = __float_as_uint(w.q[CQ_WORDS + 4][o]);
+            const uint32_t weight = acceptWeight(c, ic, bbMin, pl);
+            if(weight)
+            {
+                atomicAdd(&w.nacc[o], weight);
+                evaluatePair(sc, ic, g, w.q, w.acc, idx, o, pl.w, float(weight));
+            }
         }
     }
     cnt = 0u;
@@ -804,8 +832,8 @@ k_mergeStaged(const __grid_constant__ DevScene sc, const __grid_constant__ IterC
         bool valid = q0i + lane < nq;
         const uint32_t q = valid ? (qs.order ? qs.order[q0i + lane] : q0i + lane) : 0u;
         f3 qpos = mk3(0.f), scale = mk3(0.f);
-        uint32_t pixel = 0u, cand = 0u, accepted = 0u, refCand = 0u;
-        w.acc[0][lane] = 0.f; w.acc[1][lane] = 0.f; w.acc[2][lane] = 0.f;
+        uint32_t pixel = 0u, cand = 0u, refCand = 0u;
+        w.acc[0][lane] = 0.f; w.acc[1][lane] = 0.f; w.acc[2][lane] = 0.f; w.nacc[lane] = 0u;
         QueryCells qc; qc.px = qc.py = qc.pz = qc.pxo = qc.pyo = qc.pzo = 0; qc.mults = 0x11111111u;
         // own storage cell: x, folded row; the x interval and the second row of each axis
         int32_t sxq = 0, sxlo = 0, sxhi = 0, ry0 = 0, ry1 = 0, rz0 = 0, rz1 = 0;
@@ -841,6 +869,11 @@ k_mergeStaged(const __grid_constant__ DevScene sc, const __grid_constant__ IterC
                 ry0 = foldCoord(qc.py, d.fy); ry1 = foldCoord(qc.pyo, d.fy);
                 rz0 = foldCoord(qc.pz, d.fz); rz1 = foldCoord(qc.pzo, d.fz);
                 dyo = qc.pyo - qc.py; dzo = qc.pzo - qc.pz;
+                w.q[CQ_WORDS + 0][lane] = __int_as_float(qc.px); w.q[CQ_WORDS + 1][lane] = __int_as_float(qc.py);
+                w.q[CQ_WORDS + 2][lane] = __int_as_float(qc.pz);
+                w.q[CQ_WORDS + 3][lane] = __uint_as_float((qc.pxo > qc.px ? 4u : 0u) | (qc.pyo > qc.py ? 2u : 0u) |
+                                                          (qc.pzo > qc.pz ? 1u : 0u));
+                w.q[CQ_WORDS + 4][lane] = __uint_as_float(qc.mults);
                 pending = true;
             }
         }
@@ -947,53 +980,42 @@ k_mergeStaged(const __grid_constant__ DevScene sc, const __grid_constant__ IterC
                 const uint32_t w0 = k * uint32_t(PCAP), w1 = min(L, w0 + uint32_t(PCAP));
                 const float4 *stage = w.stage[b];
 
-                // walk this lane's ranges inside the window; accepted slots go to the private list,
-                // a full list anywhere in the warp flushes all of them
+                // walk this lane's ranges inside the window: the loop body is the distance test and
+                // nothing else — an in-range slot goes to the private list, a full list anywhere in
+                // the warp flushes all of them (evaluation with every lane busy)
                 uint32_t r = 0u, v = max(vs[0], w0), vend = min(ve[0], w1), delta = dl[0];
-                uint32_t rep = 0u, repSlot = 0u;
                 for(;;)
                 {
                     bool exhausted = false;                            // else: stopped at a full list
                     for(;;)
                     {
-                        if(rep == 0u)
+                        while(v >= vend && r < 3u)
                         {
-                            while(v >= vend && r < 3u)
-                            {
-                                r++;
-                                const uint32_t s = r == 1u ? vs[1] : r == 2u ? vs[2] : vs[3];
-                                const uint32_t e = r == 1u ? ve[1] : r == 2u ? ve[2] : ve[3];
-                                delta = r == 1u ? dl[1] : r == 2u ? dl[2] : dl[3];
-                                v = max(s, w0); vend = min(e, w1);
-                            }
-                            if(v >= vend) { exhausted = true; break; }  // nothing left in this window
-                            const float4 pl = stage[v - w0];
-                            if(inRange(qpos, pl, ic.radiusSqr))
-                            {
-                                rep = acceptWeight(qc, ic, bbMin, pl);
-                                accepted += rep;
-                                repSlot = v + delta;
-                            }
-                            v++;
-                            if(rep == 0u) continue;
+                            r++;
+                            const uint32_t s = r == 1u ? vs[1] : r == 2u ? vs[2] : vs[3];
+                            const uint32_t e = r == 1u ? ve[1] : r == 2u ? ve[2] : ve[3];
+                            delta = r == 1u ? dl[1] : r == 2u ? dl[2] : dl[3];
+                            v = max(s, w0); vend = min(e, w1);
                         }
+                        if(v >= vend) { exhausted = true; break; }      // nothing left in this window
                         if(cnt == uint32_t(LCAP)) break;
-                        w.list[cnt++][lane] = repSlot;
-                        rep--;
+                        if(inRange(qpos, stage[v - w0], ic.radiusSqr)) w.list[cnt++][lane] = v + delta;
+                        v++;
                     }
                     if(!__any_sync(FULL_MASK, !exhausted)) break;
-                    flushLists<PCAP, LCAP>(sc, ic, g, w, cnt);
+                    flushLists<PCAP, LCAP>(sc, ic, g, w, bbMin, cnt);
                 }
                 __syncwarp();
             }
             pending = pending && !inSub;
         }
 
-        flushLists<PCAP, LCAP>(sc, ic, g, w, cnt);
+        flushLists<PCAP, LCAP>(sc, ic, g, w, bbMin, cnt);
 
         if(valid)
         {
             const f3 contrib = mk3(w.acc[0][lane], w.acc[1][lane], w.acc[2][lane]);
+            const uint32_t accepted = w.nacc[lane];
             if(g.refCount) cand = refCand;
             nCand += cand; nAcc += accepted;
             if(contribOut)
