@@ -192,6 +192,14 @@ __global__ void k_gatherUnpackHeaders(const unsigned char *blocks, uint64_t bloc
 // single-pass exclusive scan with decoupled look-back (reference src/hashgrid.hxx:75-81)
 // state word: generation << 34 | flag << 32 | value;  flag 1 = tile aggregate, 2 = inclusive prefix
 // ------------------------------------------------------------------------------------------
+SVCM_D unsigned long long globalTimerNs()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// a wait that cannot hang the device: two seconds without progress is a bug, trap and report it
+#define SVCM_SPIN_LIMIT_NS 2000000000ull
 #define LB_ITEMS 16
 #define LB_TILE (SVCM_BLOCK * LB_ITEMS)
 
@@ -271,11 +279,16 @@ k_scanLookback(uint32_t *data, const GridDims *dims, uint32_t nHost, volatile un
                 unsigned long long s;
                 uint32_t flag;
                 uint32_t spins = 0u;
+                unsigned long long t0 = 0ull;
                 do
                 {
                     s = (t >= 0) ? state[t] : lbPack(gen, 2u, 0u);
                     flag = (uint32_t(s >> 34) == gen) ? (uint32_t(s >> 32) & 3u) : 0u;
-                    if(++spins > (1u << 26)) __trap();               // never hang the device
+                    if((++spins & 1023u) == 0u)                      // never hang the device
+                    {
+                        if(t0 == 0ull) t0 = globalTimerNs();
+                        else if(globalTimerNs() - t0 > SVCM_SPIN_LIMIT_NS) __trap();
+                    }
                 } while(__any_sync(FULL_MASK, flag == 0u));
                 const uint32_t inclMask = __ballot_sync(FULL_MASK, flag == 2u);
                 const int first = __ffs(inclMask) - 1;               // nearest predecessor with an inclusive prefix
@@ -722,8 +735,9 @@ SVCM_D bool mbarTryWait(unsigned long long *bar, uint32_t parity)
 }
 SVCM_D void mbarWait(unsigned long long *bar, uint32_t parity)
 {
-    uint32_t spins = 0u;
-    while(!mbarTryWait(bar, parity)) if(++spins > (1u << 24)) __trap();   // a lost copy must not hang the device
+    if(mbarTryWait(bar, parity)) return;
+    const unsigned long long t0 = globalTimerNs();
+    while(!mbarTryWait(bar, parity)) if(globalTimerNs() - t0 > SVCM_SPIN_LIMIT_NS) __trap();
 }
 // global -> shared bulk asynchronous copy (TMA engine, 1-D), completion counted on `bar`
 SVCM_D void bulkLoad(void *dstSmem, const void *srcGlobal, uint32_t bytes, unsigned long long *bar)
