@@ -854,8 +854,12 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
             launches += launchQuerySort(ic, r->queries, r->counters + CNT_CAM_VERTS, r->grid.bboxBits, r->qsort,
                                         r->counters, st);
             qs.order = r->qsort.order;
-            launchMerge(r->scene, ic, qs, count, 0, r->grid, r->accum, NULL, NULL,
-                        r->counters, r->mergeGroup, st);
+            if(r->mergeGroup >= 2 && r->mergeGroup <= 4)
+                launchBucketStagedMerge(r->scene, ic, qs, count, 0, r->grid, r->accum, NULL, NULL, r->counters,
+                                        r->mergeGroup, st);
+            else
+                launchMerge(r->scene, ic, qs, count, 0, r->grid, r->accum, NULL, NULL,
+                            r->counters, r->mergeGroup, st);
         }
         launches++;
     }
@@ -969,7 +973,8 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     r->gridStream = NULL; r->evLightDone = NULL; r->evGridDone = NULL;
     r->cameraStream = NULL; r->evIterStart = NULL; r->evCameraDone = NULL;
     r->overlapPasses = !(getenv("SVCM_NO_PASS_OVERLAP") && atoi(getenv("SVCM_NO_PASS_OVERLAP")) != 0);
-    r->iterationsDone = 0; r->mergeGroup = 1; r->profile = false;
+    r->iterationsDone = 0; r->profile = false;
+    r->mergeGroup = getenv("SVCM_MERGE_KERNEL") ? atoi(getenv("SVCM_MERGE_KERNEL")) : 1;
     r->queriesSizedFor = 0; r->pairsSizedFor = 0;
     {
         // defaults; SVCM_GRID_LAYOUT / SVCM_MERGE_VARIANT override them for A/B measurements
@@ -1117,8 +1122,8 @@ int svcm_set_option(svcm_renderer *r, int32_t option, int64_t value)
         r->profile = value != 0;
         return SVCM_OK;
     case SVCM_OPT_MERGE_GROUP:
-        if(value != 1 && value != 8 && value != 16 && value != 32)
-            return fail(r, SVCM_E_INVALID, "merge group must be 1 (lane per query), 8, 16 or 32");
+        if(value != 1 && value != 2 && value != 3 && value != 4 && value != 8 && value != 16 && value != 32)
+            return fail(r, SVCM_E_INVALID, "merge kernel must be 1 (lane per query), 2..4 (staged buckets), 8, 16 or 32");
         r->mergeGroup = int(value); return SVCM_OK;
     case SVCM_OPT_COUNTERS: return SVCM_OK;   // counters are always maintained
     case SVCM_OPT_GRID_LAYOUT:
@@ -1669,11 +1674,14 @@ int svcm_hashgrid_query(svcm_hashgrid *g, const SvcmSceneDesc *scene, const Svcm
         }
         else
         {
-        // the parity tests exercise both merge kernels: the environment picks the variant
+        // the parity tests exercise every merge kernel: the environment picks the variant
         const char *variant = getenv("SVCM_MERGE_GROUP");
         const int group = variant ? atoi(variant) : 1;
-        launchMerge(sc, ic, qs, NULL, uint32_t(count), g->grid, NULL, dContrib, dCounts, NULL,
-                    (group == 8 || group == 16 || group == 32) ? group : 1, 0);
+        if(group >= 2 && group <= 4)
+            launchBucketStagedMerge(sc, ic, qs, NULL, uint32_t(count), g->grid, NULL, dContrib, dCounts, NULL, group, 0);
+        else
+            launchMerge(sc, ic, qs, NULL, uint32_t(count), g->grid, NULL, dContrib, dCounts, NULL,
+                        (group == 8 || group == 16 || group == 32) ? group : 1, 0);
         }
         e = cudaMemcpy(contrib, dContrib, sizeof(float) * 3 * size_t(count), cudaMemcpyDeviceToHost);
         if(e == cudaSuccess && counts) e = cudaMemcpy(counts, dCounts, sizeof(int32_t) * 2 * size_t(count), cudaMemcpyDeviceToHost);

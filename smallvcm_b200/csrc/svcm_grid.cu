@@ -1052,6 +1052,317 @@ k_mergeStaged(const __grid_constant__ DevScene sc, const __grid_constant__ IterC
 }
 
 // ------------------------------------------------------------------------------------------
+// merge over the reference's BUCKET layout with the buckets of a warp's 32 queries staged into shared
+// memory (HashGrid::Process src/hashgrid.hxx:110-169 + RangeQuery::Process src/vertexcm.hxx:130-169).
+//
+// A warp takes 32 consecutive queries of the bucket-sorted query order — queries of one or two
+// cells. Their 8 x 32 bucket ids are de-duplicated through a small per-warp hash set in shared
+// memory (neighbouring queries share most of their neighbour cells); the lane that inserts an id
+// fetches that bucket's range once and copies its positions into the warp's stage with ONE bulk
+// asynchronous copy (cp.async.bulk, completion on an mbarrier). Every lane then walks its 8 ranges
+// — in the reference's order, a bucket shared by two of its cells twice, exactly like the
+// reference — from shared memory; a bucket that does not fit the stage is walked from global
+// memory instead (dense grids: the stage is an accelerator, never a limit). In-range slots go to
+// per-lane lists and are evaluated flattened, 32 pairs per warp step.
+// ------------------------------------------------------------------------------------------
+#define BS_WARPS 8
+#define BS_GLOBAL 0xFFFFFFFFu
+
+template<int PCAP, int LCAP, int TSLOTS>
+struct alignas(128) BucketWarpSmem
+{
+    float4   stage[PCAP];               // staged positions | path length
+    uint32_t list[LCAP][32];            // in-range sorted slots, [entry][lane]
+    float    q[CQ_WORDS][32];
+    float    acc[3][32];
+    uint32_t pref[32];
+    uint32_t slotKey[TSLOTS];           // bucket id + 1 (0: empty)
+    uint32_t slotStart[TSLOTS];         // first sorted slot of the bucket
+    uint32_t slotCount[TSLOTS];         // particles in it
+    uint32_t slotOff[TSLOTS];           // offset in `stage`, or BS_GLOBAL: walk it from global memory
+    uint32_t stagedTotal;               // particles reserved in `stage` for this chunk
+    unsigned long long bar;
+};
+
+template<int PCAP, int LCAP, int TSLOTS>
+SVCM_D void flushBucketLists(const DevScene &sc, const IterConst &ic, const GridBuffers &g,
+                             BucketWarpSmem<PCAP, LCAP, TSLOTS> &w, uint32_t &cnt)
+{
+    const uint32_t lane = laneId();
+    uint32_t inc = cnt;
+#pragma unroll
+    for(int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o);
+        if(lane >= uint32_t(o)) inc += t;
+    }
+    const uint32_t total = __shfl_sync(FULL_MASK, inc, 31);
+    if(total == 0u) return;
+    w.pref[lane] = inc - cnt;
+    __syncwarp();
+    for(uint32_t base = 0u; base < total; base += 32u)
+    {
+        const uint32_t p = base + lane;
+        if(p < total)
+        {
+            uint32_t o = 0u;                      // the lane whose list holds pair p: pref[o] <= p < pref[o + 1]
+#pragma unroll
+            for(int s = 16; s > 0; s >>= 1) if(w.pref[o + uint32_t(s)] <= p) o += uint32_t(s);
+            const uint32_t idx = w.list[p - w.pref[o]][o];
+            evaluatePair(sc, ic, g, w.q, w.acc, idx, o, reinterpret_cast<const float*>(g.sPosLen + idx)[3], 1.f);
+        }
+    }
+    cnt = 0u;
+    __syncwarp();
+}
+
+template<int PCAP, int LCAP, int TSLOTS, bool kBulk>
+__global__ void __launch_bounds__(BS_WARPS * 32)
+k_mergeBucketStaged(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
+                    const __grid_constant__ QueryStore qs, const unsigned long long *queryCountPtr,
+                    const uint32_t hostQueryCount, const __grid_constant__ GridBuffers g, float *accum,
+                    float *contribOut, int32_t *countsOut, unsigned long long *counters)
+{
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    typedef BucketWarpSmem<PCAP, LCAP, TSLOTS> WarpSmem;
+    WarpSmem &w = reinterpret_cast<WarpSmem*>(smemRaw)[threadIdx.x >> 5];
+
+    uint32_t nq = hostQueryCount;
+    if(queryCountPtr) nq = uint32_t(min(*queryCountPtr, (unsigned long long)qs.capacity));
+    const uint32_t lane = laneId();
+    const f3 bbMin = mk3(orderedToFloat(g.bboxBits[0]), orderedToFloat(g.bboxBits[1]), orderedToFloat(g.bboxBits[2]));
+    const f3 bbMax = mk3(orderedToFloat(g.bboxBits[3]), orderedToFloat(g.bboxBits[4]), orderedToFloat(g.bboxBits[5]));
+    uint32_t nCand = 0u, nAcc = 0u;
+    uint32_t parity = 0u;
+    if(kBulk)
+    {
+        if(lane == 0u) { mbarInit(&w.bar, 1u); mbarInitFence(); }
+        __syncwarp();
+    }
+
+    const uint32_t warpGlobal = blockIdx.x * BS_WARPS + (threadIdx.x >> 5);
+    for(uint32_t q0i = warpGlobal * 32u; q0i < nq; q0i += gridDim.x * BS_WARPS * 32u)
+    {
+        bool valid = q0i + lane < nq;
+        const uint32_t q = valid ? (qs.order ? qs.order[q0i + lane] : q0i + lane) : 0u;
+        f3 qpos = mk3(0.f), scale = mk3(0.f);
+        uint32_t pixel = 0u, cand = 0u, accepted = 0u;
+        w.acc[0][lane] = 0.f; w.acc[1][lane] = 0.f; w.acc[2][lane] = 0.f;
+        // the table is emptied by everybody, the stage starts empty
+#pragma unroll
+        for(int k = 0; k < TSLOTS / 32; k++) w.slotKey[k * 32 + int(lane)] = 0u;
+        if(lane == 0u) w.stagedTotal = 0u;
+        bool inside = false;
+        uint32_t h[8];
+#pragma unroll
+        for(int j = 0; j < 8; j++) h[j] = 0u;
+
+        float4 q1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if(valid)
+        {
+            q1 = qs.q1[q];
+            valid = (__float_as_uint(q1.w) & CAMV_MERGEABLE) != 0u;   // else: vertex connection only
+        }
+        if(valid)
+        {
+            const float4 q0 = qs.q0[q], q2 = qs.q2[q], q3 = qs.q3[q];
+            qpos = xyz(q0); scale = xyz(q3) * ic.vmNormalization; pixel = __float_as_uint(q0.w);
+            const uint32_t lenMat = __float_as_uint(q1.w);
+            Bsdf bsdf;                             // BSDF<false>::Setup from normal / local direction / material
+            bsdf.frame.setFromZ(xyz(q1));
+            bsdf.localDirFix = xyz(q2);
+            bsdf.diffProb = bsdf.phongProb = bsdf.reflProb = bsdf.refrProb = 0.f;
+            bsdfFromLocal(sc, int32_t((lenMat >> 16) & 0xFFu), bsdf);
+            parkQuery(w.q, lane, bsdf, q1.w, q2.w, q3.w);
+            // HashGrid::Process: bbox early-out, then the 8 cells (src/hashgrid.hxx:116-155)
+            inside = !(qpos.x - bbMin.x < 0.f || bbMax.x - qpos.x < 0.f || qpos.y - bbMin.y < 0.f ||
+                       bbMax.y - qpos.y < 0.f || qpos.z - bbMin.z < 0.f || bbMax.z - qpos.z < 0.f);
+            if(inside)
+            {
+                const f3 cellPt = mk3(ic.invCellSize * (qpos.x - bbMin.x), ic.invCellSize * (qpos.y - bbMin.y),
+                                      ic.invCellSize * (qpos.z - bbMin.z));
+                const f3 coordF = mk3(floorf(cellPt.x), floorf(cellPt.y), floorf(cellPt.z));
+                const int px = int(coordF.x), py = int(coordF.y), pz = int(coordF.z);
+                const int pxo = px + ((cellPt.x - coordF.x) < 0.5f ? -1 : +1);
+                const int pyo = py + ((cellPt.y - coordF.y) < 0.5f ? -1 : +1);
+                const int pzo = pz + ((cellPt.z - coordF.z) < 0.5f ? -1 : +1);
+#pragma unroll
+                for(int j = 0; j < 8; j++)
+                    h[j] = refHash((j & 4) ? pxo : px, (j & 2) ? pyo : py, (j & 1) ? pzo : pz, ic);
+            }
+        }
+        __syncwarp();
+
+        // ---- de-duplicate the warp's bucket ids; the inserting lane owns the bucket ----------------
+        uint32_t slots = 0u, slotsHi = 0u;        // 8 x 8-bit table positions of this lane's buckets
+        uint32_t owned = 0u;                      // bit j: this lane inserted bucket j (fetches and stages it)
+        if(inside)
+        {
+#pragma unroll
+            for(int j = 0; j < 8; j++)
+            {
+                const uint32_t key = h[j] + 1u;
+                uint32_t s = (h[j] * 2654435761u) >> (32 - 8);        // TSLOTS == 256
+                s &= uint32_t(TSLOTS - 1);
+                for(;;)
+                {
+                    const uint32_t old = atomicCAS(&w.slotKey[s], 0u, key);
+                    if(old == 0u) { owned |= 1u << j; break; }
+                    if(old == key) break;
+                    s = (s + 1u) & uint32_t(TSLOTS - 1);
+                }
+                if(j < 4) slots |= s << (8 * j); else slotsHi |= s << (8 * (j - 4));
+            }
+            // the owner fetches the range (GetCellRange, src/hashgrid.hxx:173-177) and reserves stage room
+#pragma unroll
+            for(int j = 0; j < 8; j++)
+            {
+                if(!(owned & (1u << j))) continue;
+                const uint32_t s = ((j < 4 ? slots >> (8 * j) : slotsHi >> (8 * (j - 4))) & 0xFFu);
+                const uint32_t start = (h[j] == 0u) ? 0u : g.cellCount[h[j] - 1u];
+                const uint32_t count = g.cellCount[h[j]] - start;
+                uint32_t off = BS_GLOBAL;
+                if(count > 0u && count <= uint32_t(PCAP))
+                {
+                    off = atomicAdd(&w.stagedTotal, count);
+                    if(off + count > uint32_t(PCAP)) { atomicSub(&w.stagedTotal, count); off = BS_GLOBAL; }
+                }
+                w.slotStart[s] = start; w.slotCount[s] = count; w.slotOff[s] = off;
+            }
+        }
+        __syncwarp();
+        // (a reservation that was taken back may have pushed a later one over the limit spuriously;
+        // that bucket is then walked from global memory — slower, never wrong)
+
+        // ---- stage: one bulk copy per owned bucket that fits -------------------------------------
+        const uint32_t stagedTotal = w.stagedTotal;
+        if(kBulk)
+        {
+            if(stagedTotal > 0u)
+            {
+                if(lane == 0u) mbarArriveExpectTx(&w.bar, stagedTotal * 16u);
+                __syncwarp();
+#pragma unroll
+                for(int j = 0; j < 8; j++)
+                {
+                    if(!(owned & (1u << j))) continue;
+                    const uint32_t s = ((j < 4 ? slots >> (8 * j) : slotsHi >> (8 * (j - 4))) & 0xFFu);
+                    const uint32_t off = w.slotOff[s];
+                    if(off != BS_GLOBAL) bulkLoad(&w.stage[off], g.sPosLen + w.slotStart[s], w.slotCount[s] * 16u, &w.bar);
+                }
+                mbarWait(&w.bar, parity);
+                parity ^= 1u;
+            }
+        }
+        else
+        {
+#pragma unroll
+            for(int j = 0; j < 8; j++)
+            {
+                // plain-load variant: every lane copies the buckets it owns itself
+                if(!(owned & (1u << j))) continue;
+                const uint32_t s = ((j < 4 ? slots >> (8 * j) : slotsHi >> (8 * (j - 4))) & 0xFFu);
+                const uint32_t off = w.slotOff[s];
+                if(off != BS_GLOBAL)
+                    for(uint32_t i = 0u; i < w.slotCount[s]; i++) w.stage[off + i] = g.sPosLen[w.slotStart[s] + i];
+            }
+            __syncwarp();
+        }
+
+        // ---- walk the 8 ranges in the reference's order ------------------------------------------
+        uint32_t cnt = 0u;                        // entries in this lane's list
+        uint32_t j = 0u, i = 0u, n = 0u, start = 0u;
+        const float4 *base = g.sPosLen;
+        bool begun = false;
+        for(;;)
+        {
+            bool exhausted = false;
+            for(;;)
+            {
+                while(i >= n)
+                {
+                    if(begun) j++;
+                    begun = true;
+                    if(!inside || j >= 8u) { exhausted = true; break; }
+                    const uint32_t s = ((j < 4u ? slots >> (8u * j) : slotsHi >> (8u * (j - 4u))) & 0xFFu);
+                    n = w.slotCount[s]; start = w.slotStart[s]; i = 0u;
+                    const uint32_t off = w.slotOff[s];
+                    base = (off != BS_GLOBAL) ? &w.stage[off] : g.sPosLen + start;    // generic pointer: either space
+                    cand += n;
+                }
+                if(exhausted) break;
+                if(cnt == uint32_t(LCAP)) break;
+                if(inRange(qpos, base[i], ic.radiusSqr)) { w.list[cnt++][lane] = start + i; accepted++; }
+                i++;
+            }
+            if(!__any_sync(FULL_MASK, !exhausted)) break;
+            flushBucketLists<PCAP, LCAP, TSLOTS>(sc, ic, g, w, cnt);
+        }
+        flushBucketLists<PCAP, LCAP, TSLOTS>(sc, ic, g, w, cnt);
+
+        if(valid)
+        {
+            const f3 contrib = mk3(w.acc[0][lane], w.acc[1][lane], w.acc[2][lane]);
+            nCand += cand; nAcc += accepted;
+            if(contribOut)
+            {
+                contribOut[3ull * q + 0] = contrib.x; contribOut[3ull * q + 1] = contrib.y;
+                contribOut[3ull * q + 2] = contrib.z;
+            }
+            if(countsOut) { countsOut[2ull * q] = int32_t(cand); countsOut[2ull * q + 1] = int32_t(accepted); }
+            // color += cameraState.mThroughput * mVmNormalization * query.GetContrib()  (src/vertexcm.hxx:534)
+            if(accum) addPixel(accum, pixel, scale * contrib);
+        }
+        __syncwarp();
+    }
+
+    if(counters)
+    {
+        warpCount(counters + CNT_CANDIDATES, nCand);
+        warpCount(counters + CNT_ACCEPTED, nAcc);
+    }
+}
+
+template<int PCAP, int LCAP, bool kBulk>
+static void launchBucketStagedT(const DevScene &sc, const IterConst &ic, const QueryStore &queries,
+                                const unsigned long long *queryCount, uint32_t hostQueryCount, const GridBuffers &grid,
+                                float *accum, float *contribOut, int32_t *countsOut, unsigned long long *counters,
+                                uint64_t maxQueries, cudaStream_t stream)
+{
+    typedef BucketWarpSmem<PCAP, LCAP, 256> WarpSmem;
+    const size_t smem = sizeof(WarpSmem) * BS_WARPS;
+    static bool configured = false;
+    if(!configured)
+    {
+        cudaFuncSetAttribute(k_mergeBucketStaged<PCAP, LCAP, 256, kBulk>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        configured = true;
+    }
+    int perSM = int((227u * 1024u) / (smem + 1024u));
+    if(perSM < 1) perSM = 1;
+    if(perSM > 8) perSM = 8;
+    k_mergeBucketStaged<PCAP, LCAP, 256, kBulk><<<gridFor(maxQueries, BS_WARPS * 32, perSM), BS_WARPS * 32, smem, stream>>>(
+        sc, ic, queries, queryCount, hostQueryCount, grid, accum, contribOut, countsOut, counters);
+}
+
+void launchBucketStagedMerge(const DevScene &sc, const IterConst &ic, const QueryStore &queries,
+                             const unsigned long long *queryCount, uint32_t hostQueryCount, const GridBuffers &grid,
+                             float *accum, float *contribOut, int32_t *countsOut, unsigned long long *counters,
+                             int variant, cudaStream_t stream)
+{
+    const uint64_t maxQueries = queryCount ? queries.capacity : hostQueryCount;
+    if(maxQueries == 0) return;
+    if(variant == 3)
+        launchBucketStagedT<256, 16, false>(sc, ic, queries, queryCount, hostQueryCount, grid, accum, contribOut, countsOut,
+                                            counters, maxQueries, stream);
+    else if(variant == 4)
+        launchBucketStagedT<128, 8, true>(sc, ic, queries, queryCount, hostQueryCount, grid, accum, contribOut, countsOut,
+                                          counters, maxQueries, stream);
+    else
+        launchBucketStagedT<256, 16, true>(sc, ic, queries, queryCount, hostQueryCount, grid, accum, contribOut, countsOut,
+                                           counters, maxQueries, stream);
+}
+
+// ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
 uint64_t hashMagicFor(uint32_t numCells)

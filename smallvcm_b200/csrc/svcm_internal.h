@@ -274,6 +274,12 @@ void launchCellMerge(const DevScene &sc, const IterConst &ic, const QueryStore &
                      const unsigned long long *queryCount, uint32_t hostQueryCount,
                      const GridBuffers &grid, float *accum, float *contribOut, int32_t *countsOut,
                      unsigned long long *counters, int variant, cudaStream_t stream);
+// merge over the BUCKET layout with a warp's buckets staged into shared memory. variant: 2 = bulk
+// async copies (default), 3 = plain loads, 4 = bulk with smaller stages
+void launchBucketStagedMerge(const DevScene &sc, const IterConst &ic, const QueryStore &queries,
+                             const unsigned long long *queryCount, uint32_t hostQueryCount,
+                             const GridBuffers &grid, float *accum, float *contribOut, int32_t *countsOut,
+                             unsigned long long *counters, int variant, cudaStream_t stream);
 // per sorted slot: the reference hash bucket of that particle (T1 export of the cell layout)
 void launchCellRefKeys(const IterConst &ic, const GridBuffers &grid, uint32_t count, uint32_t *out, cudaStream_t stream);
 uint64_t hashMagicFor(uint32_t numCells);

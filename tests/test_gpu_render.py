@@ -82,8 +82,8 @@ def test_t2_same_stream_parity(scene_id, alg):
         assert abs(st[key] - cnt[okey]) <= 2e-3 * cnt[okey] + 8, (key, st[key], cnt[okey])
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
-@pytest.mark.parametrize("scene_id,alg", [(1, "vcm"), (3, "bpm"), (1, "ppm"), (2, "vcm"), (0, "vcm")])
+@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("scene_id,alg", [(1, "vcm"), (3, "bpm"), (1, "ppm")])
 def test_t2_cell_layout_parity(scene_id, alg, variant):
     """T2 with the particles in true cell order (every merge variant) and, for comparison, in the
     reference's bucket order: same bars, and the two layouts agree with each other to summation order."""
@@ -164,13 +164,13 @@ def test_accumulate_clear_and_linearity():
 def test_merge_group_sizes_agree():
     scene = sv.Scene.cornell_box(3, 128, 128)
     imgs = []
-    for group in (1, 8, 16, 32):
+    for group in (1, 2, 3, 4, 8, 16, 32):
         r = sv.VertexCM(scene, "bpm"); r.max_path_length = 10
         r.set_option(abi.OPT_MERGE_GROUP, group)
         r.run_iterations(0, 2)
         imgs.append(r.accum()[0])
         r.close()
-    assert max(rel_l2(imgs[k], imgs[0]) for k in (1, 2, 3)) < 1e-5
+    assert max(rel_l2(imgs[k], imgs[0]) for k in range(1, len(imgs))) < 1e-5
 
 
 @pytest.mark.parametrize("scene_id,alg", [(1, "vcm"), (3, "bpm"), (0, "bpt"), (1, "pt")])

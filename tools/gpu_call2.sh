@@ -1,26 +1,25 @@
 #!/bin/bash
-# single-GPU check of the cell layout, the stream overlap and the bench line; every step bounded
+# single-GPU check: staged bucket merge, stream overlap, cell layout, bench line; every step bounded
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-PYT="python -m pytest -q -m gpu --timeout 120 --timeout-method=thread -p no:cacheprovider"
-echo "== T1 cell"; timeout 420 $PYT tests/test_gpu_kernels.py -k "hashgrid or lights" > gpurun_out/c2_t1.log 2>&1; tail -6 gpurun_out/c2_t1.log
-echo "== T2 cell"; timeout 420 $PYT tests/test_gpu_render.py -k "cell_layout or t2_same_stream" > gpurun_out/c2_t2.log 2>&1; tail -6 gpurun_out/c2_t2.log
+PYT="python -m pytest -q -m gpu --timeout 90 --timeout-method=thread -p no:cacheprovider"
+echo "== T1 merge kernels"; timeout 300 $PYT tests/test_gpu_kernels.py -k "hashgrid and not cell" > gpurun_out/c2_t1.log 2>&1; tail -4 gpurun_out/c2_t1.log
 echo "== variants"
 rm -f gpurun_out/variants.jsonl
-timeout 600 python tools/gpu_variants.py \
-  r1=build/variants/libsvcm_r1.so: \
-  camocc=build/variants/libsvcm_camera-occupancy.so: \
-  bucket=:SVCM_GRID_LAYOUT=bucket \
-  bucket_serial=:SVCM_GRID_LAYOUT=bucket,SVCM_NO_PASS_OVERLAP=1 \
-  cell0=:SVCM_GRID_LAYOUT=cell,SVCM_MERGE_VARIANT=0 \
-  cell1=:SVCM_GRID_LAYOUT=cell,SVCM_MERGE_VARIANT=1 \
-  cell2=:SVCM_GRID_LAYOUT=cell,SVCM_MERGE_VARIANT=2 \
-  cell3=:SVCM_GRID_LAYOUT=cell,SVCM_MERGE_VARIANT=3 \
-  cell1_serial=:SVCM_GRID_LAYOUT=cell,SVCM_MERGE_VARIANT=1,SVCM_NO_PASS_OVERLAP=1 \
-  c4_bucket=:SVCM_GRID_LAYOUT=bucket,SCENE=3,ALG=bpm,W=2048,ITERS=4 \
-  c4_cell1=:SVCM_GRID_LAYOUT=cell,SVCM_MERGE_VARIANT=1,SCENE=3,ALG=bpm,W=2048,ITERS=4 \
-  c5_bucket=:SVCM_GRID_LAYOUT=bucket,W=4096,MAXLEN=20,ITERS=2,FIRST=1 \
-  c5_cell1=:SVCM_GRID_LAYOUT=cell,SVCM_MERGE_VARIANT=1,W=4096,MAXLEN=20,ITERS=2,FIRST=1 \
+timeout 500 python tools/gpu_variants.py \
+  lane=:SVCM_MERGE_KERNEL=1 \
+  lane_serial=:SVCM_MERGE_KERNEL=1,SVCM_NO_PASS_OVERLAP=1 \
+  staged=:SVCM_MERGE_KERNEL=2 \
+  staged_plain=:SVCM_MERGE_KERNEL=3 \
+  staged_small=:SVCM_MERGE_KERNEL=4 \
+  c4_lane=:SVCM_MERGE_KERNEL=1,SCENE=3,ALG=bpm,W=2048,ITERS=4 \
+  c4_staged=:SVCM_MERGE_KERNEL=2,SCENE=3,ALG=bpm,W=2048,ITERS=4 \
+  c5_lane=:SVCM_MERGE_KERNEL=1,W=4096,MAXLEN=20,ITERS=2,FIRST=1 \
+  c5_staged=:SVCM_MERGE_KERNEL=2,W=4096,MAXLEN=20,ITERS=2,FIRST=1 \
+  c3_bpt=:SCENE=0,ALG=bpt,ITERS=10 \
+  c3_bpt_serial=:SCENE=0,ALG=bpt,ITERS=10,SVCM_NO_PASS_OVERLAP=1 \
   > gpurun_out/c2_variants.log 2>&1; cat gpurun_out/c2_variants.log
-echo "== full suite, cell layout"; SVCM_GRID_LAYOUT=cell timeout 600 $PYT tests > gpurun_out/c2_all_cell.log 2>&1; tail -8 gpurun_out/c2_all_cell.log
-echo "== full suite, defaults"; timeout 600 $PYT tests > gpurun_out/c2_all.log 2>&1; tail -8 gpurun_out/c2_all.log
+echo "== T1 rest + T2"; timeout 400 $PYT tests/test_gpu_kernels.py tests/test_gpu_render.py -k "not cell and not hashgrid and not full_size and not drop_in" > gpurun_out/c2_t2.log 2>&1; tail -6 gpurun_out/c2_t2.log
+echo "== full size"; timeout 400 $PYT tests/test_gpu_render.py -k "full_size or drop_in" > gpurun_out/c2_full.log 2>&1; tail -6 gpurun_out/c2_full.log
+echo "== other files"; timeout 300 $PYT tests/test_bvh.py tests/test_image.py tests/test_abi.py > gpurun_out/c2_other.log 2>&1; tail -4 gpurun_out/c2_other.log
+echo "== cell layout"; timeout 300 $PYT tests/test_gpu_kernels.py tests/test_gpu_render.py -k "cell" > gpurun_out/c2_cell.log 2>&1; tail -4 gpurun_out/c2_cell.log
