@@ -238,8 +238,8 @@ enum {
                                    arithmetically, results identical)                   */
     SVCM_OPT_MERGE_VARIANT = 5, /* cell layout only: 0 = lane per query from global
                                    memory, 1 = neighbourhood staged through shared
-                                   memory by bulk async copies (default), 2 = staged
-                                   with plain loads, 3 = like 1 with smaller stages     */
+                                   memory by bulk async copies (default), 3 = like 1
+                                   with smaller stages                                  */
     SVCM_OPT_REF_CANDIDATES = 6 /* 0/1, cell layout: also histogram the reference's
                                    buckets so that mergeCandidates counts what the
                                    reference's walk would visit (statistics; off: the

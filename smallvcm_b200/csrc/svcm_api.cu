@@ -147,6 +147,7 @@ struct svcm_renderer
     cudaStream_t cameraStream;
     cudaEvent_t  evIterStart, evCameraDone;
     bool overlapPasses;             // SVCM_NO_PASS_OVERLAP=1 serialises them again (A/B)
+    bool legacyBuild;               // SVCM_LEGACY_BUILD=1: round 1's three-kernel scan + direct record scatter (A/B)
 
     int  iterationsDone;
     int  mergeGroup;
@@ -364,7 +365,6 @@ int ensureGridSorted(svcm_renderer *r, uint32_t capacity)
 // key space of the cell layout: 2^21 storage cells (8 MB per table), independent of the resolution
 // because the cell edge follows the radius, not the pixel count
 static const uint32_t kCellTableCapacity = 1u << 21;
-static const size_t   kScanStateWords = 4096;
 
 int allocCellTables(svcm_renderer *r, GridBuffers &grid, QuerySortBuffers *qs, uint32_t numCells)
 {
@@ -804,7 +804,7 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
         }
         if(timed) cudaEventRecord(ev[7], sg);
         if(r->cellLayout) launches += launchCellGridBuild(ic, set, r->grid, r->scanGenGrid, r->refCandidates, sg);
-        else launches += launchGridBuild(ic, set, r->grid, sg);
+        else launches += launchGridBuild(ic, set, r->grid, r->legacyBuild ? NULL : &r->scanGenGrid, sg);
         if(timed) cudaEventRecord(ev[8], sg);
         SVCM_CUDA(r, cudaEventRecord(r->evGridDone, sg));
     }
@@ -852,7 +852,7 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
         else
         {
             launches += launchQuerySort(ic, r->queries, r->counters + CNT_CAM_VERTS, r->grid.bboxBits, r->qsort,
-                                        r->counters, st);
+                                        r->counters, r->legacyBuild ? NULL : &r->scanGenQuery, st);
             qs.order = r->qsort.order;
             if(r->mergeGroup >= 2 && r->mergeGroup <= 4)
                 launchBucketStagedMerge(r->scene, ic, qs, count, 0, r->grid, r->accum, NULL, NULL, r->counters,
@@ -973,6 +973,7 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     r->gridStream = NULL; r->evLightDone = NULL; r->evGridDone = NULL;
     r->cameraStream = NULL; r->evIterStart = NULL; r->evCameraDone = NULL;
     r->overlapPasses = !(getenv("SVCM_NO_PASS_OVERLAP") && atoi(getenv("SVCM_NO_PASS_OVERLAP")) != 0);
+    r->legacyBuild = getenv("SVCM_LEGACY_BUILD") && atoi(getenv("SVCM_LEGACY_BUILD")) != 0;
     r->iterationsDone = 0; r->profile = false;
     r->mergeGroup = getenv("SVCM_MERGE_KERNEL") ? atoi(getenv("SVCM_MERGE_KERNEL")) : 1;
     r->queriesSizedFor = 0; r->pairsSizedFor = 0;
@@ -1130,7 +1131,7 @@ int svcm_set_option(svcm_renderer *r, int32_t option, int64_t value)
         if(value != 0 && value != 1) return fail(r, SVCM_E_INVALID, "grid layout must be 0 (hash buckets) or 1 (cell order)");
         r->cellLayout = value != 0; return SVCM_OK;
     case SVCM_OPT_MERGE_VARIANT:
-        if(value < 0 || value > 3) return fail(r, SVCM_E_INVALID, "merge variant must be 0..3");
+        if(value != 0 && value != 1 && value != 3) return fail(r, SVCM_E_INVALID, "merge variant must be 0, 1 or 3");
         r->mergeVariant = int(value); return SVCM_OK;
     case SVCM_OPT_REF_CANDIDATES:
         r->refCandidates = value != 0; return SVCM_OK;
@@ -1541,7 +1542,19 @@ int svcm_hashgrid_build(const SvcmMergeVertex *vertices, int64_t count, float ra
             if(allocCellTables(NULL, g->grid, NULL, uint32_t(numCells)) != SVCM_OK) e = cudaErrorMemoryAllocation;
             else launchCellGridBuild(ic, set, g->grid, g->scanGen, true, 0);
         }
-        else launchGridBuild(ic, set, g->grid, 0);
+        else
+        {
+            // scan state for the single-pass scan (the product's build); SVCM_LEGACY_BUILD=1: round 1's
+            const bool legacy = getenv("SVCM_LEGACY_BUILD") && atoi(getenv("SVCM_LEGACY_BUILD")) != 0;
+            if(!legacy)
+            {
+                if(e == cudaSuccess) e = cudaMalloc((void**)&g->grid.scanState, sizeof(unsigned long long) * kScanStateWords);
+                if(e == cudaSuccess) e = cudaMalloc((void**)&g->grid.scanCounter, sizeof(uint32_t));
+                if(e == cudaSuccess) e = cudaMemset(g->grid.scanState, 0, sizeof(unsigned long long) * kScanStateWords);
+                if(e == cudaSuccess) e = cudaMemset(g->grid.scanCounter, 0, sizeof(uint32_t));
+            }
+            if(e == cudaSuccess) launchGridBuild(ic, set, g->grid, legacy ? NULL : &g->scanGen, 0);
+        }
     }
     rc = cudaDone(e, "svcm_hashgrid_build");
     if(staging) cudaFree(staging);

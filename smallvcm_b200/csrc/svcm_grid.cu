@@ -353,9 +353,10 @@ k_cellScatterIndex(const uint32_t *key, const unsigned long long *countPtr, uint
 
 // slot-ordered gather of the records: dense 16-byte stores, random 16-byte loads
 __global__ void __launch_bounds__(SVCM_BLOCK)
-k_cellGather(const __grid_constant__ MergeSet set, const __grid_constant__ GridBuffers g)
+k_cellGather(const __grid_constant__ MergeSet set, const __grid_constant__ GridBuffers g, const uint32_t *totalPtr)
 {
-    const uint32_t total = g.cellEnd[g.dims->numKeys];      // end of the last key = number of particles
+    // cell layout: the end of the last key; bucket layout: the scan's last entry (never a cursor)
+    const uint32_t total = totalPtr ? *totalPtr : g.cellEnd[g.dims->numKeys];
     for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += gridDim.x * blockDim.x)
     {
         const MergeSlot ms = mergeSetSlot(set, uint32_t(g.sIndex[slot]));
@@ -1371,8 +1372,8 @@ uint64_t hashMagicFor(uint32_t numCells)
     return 0xFFFFFFFFFFFFFFFFull / uint64_t(numCells) + 1ull;
 }
 
-static void launchLookbackScan(uint32_t *data, const GridDims *dims, uint32_t n, unsigned long long *state,
-                               uint32_t *counter, ScanGen &gen, cudaStream_t stream)
+void launchLookbackScan(uint32_t *data, const GridDims *dims, uint32_t n, unsigned long long *state,
+                        uint32_t *counter, ScanGen &gen, cudaStream_t stream)
 {
     const uint32_t tiles = (n + LB_TILE - 1) / LB_TILE;
     gen.value = (gen.value + 1u) & 0x3FFFFFFFu;
@@ -1407,7 +1408,7 @@ int launchCellGridBuild(const IterConst &ic, const MergeSet &set, const GridBuff
     {
         k_cellScatterIndex<<<gridFor((maxTotal + 3u) / 4u, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(
             grid.cellKey, set.singleCount, maxTotal, maxTotal, grid.cellEnd, reinterpret_cast<uint32_t*>(grid.sIndex));
-        k_cellGather<<<gridN, SVCM_BLOCK, 0, stream>>>(set, grid);
+        k_cellGather<<<gridN, SVCM_BLOCK, 0, stream>>>(set, grid, NULL);
         launches += 2;
     }
     return launches;
@@ -1463,10 +1464,6 @@ void launchCellMerge(const DevScene &sc, const IterConst &ic, const QueryStore &
         k_mergeCellLane<<<gridFor(maxQueries, SVCM_BLOCK, 4), SVCM_BLOCK, 0, stream>>>(
             sc, ic, queries, queryCount, hostQueryCount, grid, accum, contribOut, countsOut, counters);
         break;
-    case 2:
-        launchStaged<256, 16, false>(sc, ic, queries, queryCount, hostQueryCount, grid, accum, contribOut, countsOut,
-                                     counters, maxQueries, stream);
-        break;
     case 3:
         launchStaged<128, 8, true>(sc, ic, queries, queryCount, hostQueryCount, grid, accum, contribOut, countsOut,
                                    counters, maxQueries, stream);
@@ -1490,6 +1487,18 @@ void launchGatherUnpackHeaders(const unsigned char *blocks, uint64_t blockBytes,
                                uint32_t *segCountDev, int32_t *bboxBits, unsigned long long *totals, cudaStream_t stream)
 {
     k_gatherUnpackHeaders<<<1, 32, 0, stream>>>(blocks, blockBytes, numSegs, segStride, segCountDev, bboxBits, totals);
+}
+
+// second half of HashGrid::Build in the BUCKET layout (after keys + histogram + scan): 4-byte index
+// scatter through the cursor, then the slot-ordered record gather
+int launchBucketReorder(const MergeSet &set, const GridBuffers &grid, uint32_t numCells, cudaStream_t stream)
+{
+    const uint32_t maxTotal = set.singleCount ? set.capacity : set.numSegs * set.segStride;
+    if(maxTotal == 0u) return 0;
+    k_cellScatterIndex<<<gridFor((maxTotal + 3u) / 4u, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(
+        grid.cellKey, set.singleCount, maxTotal, maxTotal, grid.cellCount, reinterpret_cast<uint32_t*>(grid.sIndex));
+    k_cellGather<<<gridFor(maxTotal, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(set, grid, grid.cellCount + numCells);
+    return 2;
 }
 
 void launchCellRefKeys(const IterConst &ic, const GridBuffers &grid, uint32_t count, uint32_t *out, cudaStream_t stream)

@@ -216,6 +216,9 @@ SVCM_HD float orderedToFloat(int32_t i)
 #endif
 }
 
+// Generation counter of the look-back scan state words; bump once per scan launch.
+struct ScanGen { uint32_t value; };
+
 // ---- launchers implemented in svcm_kernels.cu (all asynchronous on `stream`) -------------
 void launchLightBounce(const DevScene &sc, const IterConst &ic, const TraceArgs &args,
                        uint32_t bounce, uint32_t maxItems, cudaStream_t stream);
@@ -224,7 +227,8 @@ void launchCameraBounce(const DevScene &sc, const IterConst &ic, const TraceArgs
 // groups the mergeable camera vertices by cell (counting sort of indices): neighbouring lanes of
 // the merge kernel then walk the same cell ranges. Returns the number of kernels launched.
 int launchQuerySort(const IterConst &ic, const QueryStore &queries, const unsigned long long *vertexCount,
-                    const int32_t *bboxBits, const QuerySortBuffers &qs, unsigned long long *counters, cudaStream_t stream);
+                    const int32_t *bboxBits, const QuerySortBuffers &qs, unsigned long long *counters, ScanGen *gen,
+                    cudaStream_t stream);
 // vertex connection of every queued (camera vertex, light vertex) pair
 void launchConnect(const DevScene &sc, const IterConst &ic, const TraceArgs &args, cudaStream_t stream);
 // any-hit tests + splats for the rays queued by pass `which` (0 light, 1 camera; count read on
@@ -238,7 +242,7 @@ void launchEyeLight(const DevScene &sc, const IterConst &ic, const TraceArgs &ar
                     cudaStream_t stream);
 // HashGrid::Build: bbox -> keys + histogram -> exclusive scan -> scatter. Returns the
 // number of kernels launched.
-int  launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers &grid,
+int  launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers &grid, ScanGen *gen,
                      cudaStream_t stream);
 // HashGrid::Process + RangeQuery::Process over the queued camera vertices flagged
 // CAMV_MERGEABLE (their number is read from *queryCount on the device when queryCount != NULL,
@@ -249,8 +253,6 @@ void launchMerge(const DevScene &sc, const IterConst &ic, const QueryStore &quer
                  unsigned long long *counters, int groupSize, cudaStream_t stream);
 
 // ---- cell layout (svcm_grid.cu) ------------------------------------------------------------
-// Generation counter of the look-back scan state words; bump once per scan launch.
-struct ScanGen { uint32_t value; };
 // HashGrid::Build in the cell layout: bbox -> grid dims -> keys + histogram -> single-pass
 // look-back scan -> index scatter -> record gather. `withRefCount`: also histogram the
 // reference's hash buckets into grid.refCount (numCells entries). Returns kernels launched.
@@ -269,11 +271,17 @@ void launchGatherPackHeader(const MergeSet &localSet, const int32_t *bboxInit, G
 void launchGatherUnpackHeaders(const unsigned char *blocks, uint64_t blockBytes, uint32_t numSegs, uint32_t segStride,
                                uint32_t *segCountDev, int32_t *bboxBits, unsigned long long *totals, cudaStream_t stream);
 // merge over the cell layout. variant: 0 = lane per query straight from global memory, 1 = staged
-// through shared memory with bulk async copies, 2 = staged with plain loads
+// through shared memory with bulk async copies, 3 = the same with smaller stages
 void launchCellMerge(const DevScene &sc, const IterConst &ic, const QueryStore &queries,
                      const unsigned long long *queryCount, uint32_t hostQueryCount,
                      const GridBuffers &grid, float *accum, float *contribOut, int32_t *countsOut,
                      unsigned long long *counters, int variant, cudaStream_t stream);
+// single-pass decoupled look-back exclusive scan of data[0..n) (dims: optional cap on n, cell layout);
+// needs (n + 4095) / 4096 state words and a zeroed counter
+void launchLookbackScan(uint32_t *data, const GridDims *dims, uint32_t n, unsigned long long *state,
+                        uint32_t *counter, ScanGen &gen, cudaStream_t stream);
+static const uint32_t kScanStateWords = 8192;      // scans of up to 2^25 entries
+int launchBucketReorder(const MergeSet &set, const GridBuffers &grid, uint32_t numCells, cudaStream_t stream);
 // merge over the BUCKET layout with a warp's buckets staged into shared memory. variant: 2 = bulk
 // async copies (default), 3 = plain loads, 4 = bulk with smaller stages
 void launchBucketStagedMerge(const DevScene &sc, const IterConst &ic, const QueryStore &queries,

@@ -1681,19 +1681,27 @@ void launchCameraBounce(const DevScene &sc, const IterConst &ic, const TraceArgs
 }
 
 int launchQuerySort(const IterConst &ic, const QueryStore &queries, const unsigned long long *vertexCount,
-                    const int32_t *bboxBits, const QuerySortBuffers &qs, unsigned long long *counters, cudaStream_t stream)
+                    const int32_t *bboxBits, const QuerySortBuffers &qs, unsigned long long *counters, ScanGen *gen,
+                    cudaStream_t stream)
 {
     const uint32_t n = ic.numCells + 1u;
     cudaMemsetAsync(qs.cellCount, 0, sizeof(uint32_t) * n, stream);
     const uint32_t gridN = gridFor(queries.capacity, SVCM_BLOCK, 8);
     k_queryKeys<<<gridN, SVCM_BLOCK, 0, stream>>>(queries, vertexCount, bboxBits, ic.invCellSize, ic.numCells,
                                                   qs.key, qs.cellCount, counters);
-    const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    k_scanTiles<<<tiles, SVCM_BLOCK, 0, stream>>>(qs.cellCount, n, qs.blockSums);
-    k_scanSums<<<1, SVCM_BLOCK, 0, stream>>>(qs.blockSums, tiles);
-    k_scanAdd<<<tiles, SVCM_BLOCK, 0, stream>>>(qs.cellCount, n, qs.blockSums);
+    int launches = 3;
+    if(gen && qs.scanState && (n + 4095u) / 4096u <= kScanStateWords)
+        launchLookbackScan(qs.cellCount, NULL, n, qs.scanState, qs.scanCounter, *gen, stream);   // single pass
+    else
+    {
+        const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+        k_scanTiles<<<tiles, SVCM_BLOCK, 0, stream>>>(qs.cellCount, n, qs.blockSums);
+        k_scanSums<<<1, SVCM_BLOCK, 0, stream>>>(qs.blockSums, tiles);
+        k_scanAdd<<<tiles, SVCM_BLOCK, 0, stream>>>(qs.cellCount, n, qs.blockSums);
+        launches += 2;
+    }
     k_queryScatter<<<gridN, SVCM_BLOCK, 0, stream>>>(vertexCount, queries.capacity, qs.key, qs.cellCount, qs.order);
-    return 5;
+    return launches;
 }
 
 void launchConnect(const DevScene &sc, const IterConst &ic, const TraceArgs &args, cudaStream_t stream)
@@ -1711,7 +1719,10 @@ void launchShadow(const DevScene &sc, const IterConst &ic, const TraceArgs &args
     else       k_shadow<false><<<gridFor(args.shadow.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, args, which);
 }
 
-int launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers &grid, cudaStream_t stream)
+// HashGrid::Build in the reference's bucket order: bbox -> keys + histogram -> exclusive scan -> reorder.
+// With `gen` (scan state allocated): single-pass look-back scan and the two-step reorder (4-byte
+// index scatter + dense record gather); without: the three-kernel scan and the direct record scatter.
+int launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers &grid, ScanGen *gen, cudaStream_t stream)
 {
     const uint32_t n = ic.numCells + 1u;
     // bbox init: (+1e36, -1e36) like the reference (src/hashgrid.hxx:50-51); for all-gathered
@@ -1728,6 +1739,12 @@ int launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers 
         k_gridKeys<<<gridN, SVCM_BLOCK, 0, stream>>>(set, grid.bboxBits, ic.invCellSize, ic.numCells,
                                                      grid.cellKey, grid.cellCount);
         launches += 2;
+    }
+    if(gen && grid.scanState && (n + 4095u) / 4096u <= kScanStateWords)
+    {
+        launchLookbackScan(grid.cellCount, NULL, n, grid.scanState, grid.scanCounter, *gen, stream);
+        launches += 1 + launchBucketReorder(set, grid, ic.numCells, stream);
+        return launches;
     }
     const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     k_scanTiles<<<tiles, SVCM_BLOCK, 0, stream>>>(grid.cellCount, n, grid.blockSums);
