@@ -214,11 +214,14 @@ def _log_measured(name, **values):
 # (scene, algorithm, width, maxLen, iterations, bound on relative L2): BASELINE.json configs #2, the
 # metric configuration, #3 and #4 at FULL size against the oracle on the same per-path random
 # streams. The oracle runs its path-parallel iteration (tests/test_oracle.py pins it to the serial
-# loop, which is pinned bit-exact to the reference). The L2 bound per configuration is ~3x what was
-# measured (gpurun_out/parity_measured.jsonl); it is carried by the few paths an epsilon branch
-# sends elsewhere — the pixel criterion below is the sharper one.
-FULL_SIZE = [(1, "vcm", 512, 10, 2, 3e-2), (1, "vcm", 1024, 10, 1, 3e-2), (0, "bpt", 1024, 10, 1, 6e-2),
-             (3, "bpm", 2048, 10, 1, 6e-2)]
+# loop, which is pinned bit-exact to the reference). Bounds are ~3x what was measured on B200
+# (profiles/r2_parity_measured.jsonl: rel. L2 3.4e-4 / 3.1e-4 / 1.6e-2 / 1.7e-2, mean radiance equal
+# to 1e-5 .. 1e-6). The L2 norm is carried by the few paths an epsilon branch sends elsewhere; a
+# flipped LIGHT path moves every pixel whose query merges with it by a little, so the share of
+# pixels off by more than 0.1 % grows with the resolution (0.9 % .. 2.1 % measured) while the share
+# off by more than 1 % stays small.
+FULL_SIZE = [(1, "vcm", 512, 10, 2, 1e-3), (1, "vcm", 1024, 10, 1, 1e-3), (0, "bpt", 1024, 10, 1, 5e-2),
+             (3, "bpm", 2048, 10, 1, 5e-2)]
 
 
 @pytest.mark.parametrize("scene_id,alg,w,max_len,iters,l2_bound", FULL_SIZE,
@@ -234,12 +237,14 @@ def test_t2_full_size_same_stream(scene_id, alg, w, max_len, iters, l2_bound):
     l2 = rel_l2(img, ref)
     pix = np.abs(img - ref).max(2) / (np.abs(ref).max(2) + 1e-3)
     off = float((pix > 1e-3).mean())
-    _log_measured("t2_full_size", scene=scene_id, alg=alg, w=w, rel_l2=l2, pixels_off=off,
+    off1 = float((pix > 1e-2).mean())
+    _log_measured("t2_full_size", scene=scene_id, alg=alg, w=w, rel_l2=l2, pixels_off=off, pixels_off_1pct=off1,
                   mean_rel=float(abs(img.mean() - ref.mean()) / ref.mean()))
     assert n == iters
     assert l2 <= l2_bound
-    assert off <= 1e-2                                             # pixels off by more than 0.1 %
-    assert abs(img.mean() - ref.mean()) <= 2e-3 * ref.mean()
+    assert off <= 5e-2                                             # pixels off by more than 0.1 %
+    assert off1 <= 1e-2                                            # pixels off by more than 1 %
+    assert abs(img.mean() - ref.mean()) <= 1e-4 * ref.mean()
     assert abs(st["lightVertices"] - orc.num_light_vertices()) <= 1e-4 * orc.num_light_vertices() + 2
     for key in ("lightRays", "cameraRays", "shadowRays", "mergeQueries", "mergeCandidates", "mergeAccepted"):
         assert abs(st[key] - cnt[key]) <= 1e-3 * cnt[key] + 8, (key, st[key], cnt[key])
