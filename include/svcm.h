@@ -227,8 +227,8 @@ enum {
                                    query straight from global memory; 2 = one lane per
                                    query, the buckets of a warp's 32 queries de-duplicated
                                    and staged into shared memory by bulk async copies;
-                                   3 = like 2 with plain loads; 4 = like 2 with a smaller
-                                   stage; 8, 16, 32 = that many lanes cooperating on one
+                                   3 = like 2 with plain loads; 4, 5 = like 2 with smaller
+                                   stages; 8, 16, 32 = that many lanes cooperating on one
                                    query                                               */
     SVCM_OPT_COUNTERS      = 3, /* 0/1: maintain N_cand/N_acc counters (small cost)    */
     SVCM_OPT_GRID_LAYOUT   = 4, /* particle order of the hash grid: 0 = the reference's

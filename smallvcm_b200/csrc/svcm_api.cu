@@ -147,6 +147,7 @@ struct svcm_renderer
     cudaStream_t cameraStream;
     cudaEvent_t  evIterStart, evCameraDone;
     bool overlapPasses;             // SVCM_NO_PASS_OVERLAP=1 serialises them again (A/B)
+    bool spatialQueries;            // SVCM_QUERY_ORDER=bucket restores round 1's order (A/B)
     bool legacyBuild;               // SVCM_LEGACY_BUILD=1: round 1's three-kernel scan + direct record scatter (A/B)
 
     int  iterationsDone;
@@ -852,9 +853,9 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
         else
         {
             launches += launchQuerySort(ic, r->queries, r->counters + CNT_CAM_VERTS, r->grid.bboxBits, r->qsort,
-                                        r->counters, r->legacyBuild ? NULL : &r->scanGenQuery, st);
+                                        r->counters, r->legacyBuild ? NULL : &r->scanGenQuery, r->spatialQueries, st);
             qs.order = r->qsort.order;
-            if(r->mergeGroup >= 2 && r->mergeGroup <= 4)
+            if(r->mergeGroup >= 2 && r->mergeGroup <= 5)
                 launchBucketStagedMerge(r->scene, ic, qs, count, 0, r->grid, r->accum, NULL, NULL, r->counters,
                                         r->mergeGroup, st);
             else
@@ -974,6 +975,7 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     r->cameraStream = NULL; r->evIterStart = NULL; r->evCameraDone = NULL;
     r->overlapPasses = !(getenv("SVCM_NO_PASS_OVERLAP") && atoi(getenv("SVCM_NO_PASS_OVERLAP")) != 0);
     r->legacyBuild = getenv("SVCM_LEGACY_BUILD") && atoi(getenv("SVCM_LEGACY_BUILD")) != 0;
+    r->spatialQueries = !(getenv("SVCM_QUERY_ORDER") && strcmp(getenv("SVCM_QUERY_ORDER"), "bucket") == 0);
     r->iterationsDone = 0; r->profile = false;
     r->mergeGroup = getenv("SVCM_MERGE_KERNEL") ? atoi(getenv("SVCM_MERGE_KERNEL")) : 1;
     r->queriesSizedFor = 0; r->pairsSizedFor = 0;
@@ -1123,8 +1125,8 @@ int svcm_set_option(svcm_renderer *r, int32_t option, int64_t value)
         r->profile = value != 0;
         return SVCM_OK;
     case SVCM_OPT_MERGE_GROUP:
-        if(value != 1 && value != 2 && value != 3 && value != 4 && value != 8 && value != 16 && value != 32)
-            return fail(r, SVCM_E_INVALID, "merge kernel must be 1 (lane per query), 2..4 (staged buckets), 8, 16 or 32");
+        if(value != 1 && value != 2 && value != 3 && value != 4 && value != 5 && value != 8 && value != 16 && value != 32)
+            return fail(r, SVCM_E_INVALID, "merge kernel must be 1 (lane per query), 2..5 (staged buckets), 8, 16 or 32");
         r->mergeGroup = int(value); return SVCM_OK;
     case SVCM_OPT_COUNTERS: return SVCM_OK;   // counters are always maintained
     case SVCM_OPT_GRID_LAYOUT:
@@ -1690,7 +1692,7 @@ int svcm_hashgrid_query(svcm_hashgrid *g, const SvcmSceneDesc *scene, const Svcm
         // the parity tests exercise every merge kernel: the environment picks the variant
         const char *variant = getenv("SVCM_MERGE_GROUP");
         const int group = variant ? atoi(variant) : 1;
-        if(group >= 2 && group <= 4)
+        if(group >= 2 && group <= 5)
             launchBucketStagedMerge(sc, ic, qs, NULL, uint32_t(count), g->grid, NULL, dContrib, dCounts, NULL, group, 0);
         else
             launchMerge(sc, ic, qs, NULL, uint32_t(count), g->grid, NULL, dContrib, dCounts, NULL,

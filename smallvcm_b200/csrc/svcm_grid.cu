@@ -513,6 +513,65 @@ SVCM_D void parkQuery(float (*q)[32], uint32_t lane, const Bsdf &bsdf, float len
 
 // RangeQuery::Process (reference src/vertexcm.hxx:130-169) for the particle at sorted slot `idx`
 // and the query parked by lane `owner`; the result is added to the owner's sums
+// (the particle's payload is loaded by the caller, all four words at once: one memory round trip
+// per evaluation step instead of three dependent ones)
+SVCM_D f3 pairContribution(const DevScene &sc, const IterConst &ic, float (*q)[32], uint32_t owner,
+                           float lenBits, float4 dv, float4 tv, float lightContProb)
+{
+    const uint32_t lvLen = __float_as_uint(lenBits);
+    const uint32_t lenMat = __float_as_uint(q[12][owner]);
+    const uint32_t camLen = lenMat & 0xFFFFu;
+    const uint32_t camMat = (lenMat >> 16) & 0xFFu;
+    if((lvLen + camLen > ic.maxLen) || (lvLen + camLen < ic.minLen)) return mk3(0.f);
+    Bsdf b;
+    b.frame.x = mk3(q[0][owner], q[1][owner], q[2][owner]);
+    b.frame.y = mk3(q[3][owner], q[4][owner], q[5][owner]);
+    b.frame.z = mk3(q[6][owner], q[7][owner], q[8][owner]);
+    b.localDirFix = mk3(q[9][owner], q[10][owner], q[11][owner]);
+    const f3 localDirGen = b.frame.toLocal(xyz(dv));
+    if(localDirGen.z * b.localDirFix.z < 0.f) return mk3(0.f);
+    b.diffProb = q[13][owner]; b.phongProb = q[14][owner]; b.contProb = q[15][owner];
+    float camDirPdfW, camRevPdfW;
+    const f3 f = bsdfEvaluateLocal(sc.mats[camMat], b, localDirGen, camDirPdfW, camRevPdfW);
+    if(iszero(f)) return mk3(0.f);
+    camDirPdfW *= b.contProb;
+    camRevPdfW *= lightContProb;                                 // the LIGHT vertex's RR probability
+    const float wLight  = tv.w * ic.misVcWeightFactor + dv.w * camDirPdfW;                 // (38)
+    const float wCamera = q[16][owner] * ic.misVcWeightFactor + q[17][owner] * camRevPdfW; // (39)
+    const float misWeight = ic.ppm ? 1.f : 1.f / (wLight + 1.f + wCamera);
+    return (misWeight * f) * xyz(tv);
+}
+
+SVCM_D void evaluatePairLoaded(const DevScene &sc, const IterConst &ic, float (*q)[32], float (*acc)[32], uint32_t owner,
+                               float lenBits, float4 dv, float4 tv, float lightContProb, float weight)
+{
+    const uint32_t lvLen = __float_as_uint(lenBits);
+    const uint32_t lenMat = __float_as_uint(q[12][owner]);
+    const uint32_t camLen = lenMat & 0xFFFFu;
+    const uint32_t camMat = (lenMat >> 16) & 0xFFu;
+    if((lvLen + camLen > ic.maxLen) || (lvLen + camLen < ic.minLen)) return;
+    Bsdf b;
+    b.frame.x = mk3(q[0][owner], q[1][owner], q[2][owner]);
+    b.frame.y = mk3(q[3][owner], q[4][owner], q[5][owner]);
+    b.frame.z = mk3(q[6][owner], q[7][owner], q[8][owner]);
+    b.localDirFix = mk3(q[9][owner], q[10][owner], q[11][owner]);
+    const f3 localDirGen = b.frame.toLocal(xyz(dv));
+    if(localDirGen.z * b.localDirFix.z < 0.f) return;
+    b.diffProb = q[13][owner]; b.phongProb = q[14][owner]; b.contProb = q[15][owner];
+    float camDirPdfW, camRevPdfW;
+    const f3 f = bsdfEvaluateLocal(sc.mats[camMat], b, localDirGen, camDirPdfW, camRevPdfW);
+    if(iszero(f)) return;
+    camDirPdfW *= b.contProb;
+    camRevPdfW *= lightContProb;                                 // the LIGHT vertex's RR probability
+    const float wLight  = tv.w * ic.misVcWeightFactor + dv.w * camDirPdfW;                 // (38)
+    const float wCamera = q[16][owner] * ic.misVcWeightFactor + q[17][owner] * camRevPdfW; // (39)
+    const float misWeight = ic.ppm ? 1.f : 1.f / (wLight + 1.f + wCamera);
+    const f3 c = ((misWeight * weight) * f) * xyz(tv);
+    atomicAdd(&acc[0][owner], c.x);
+    atomicAdd(&acc[1][owner], c.y);
+    atomicAdd(&acc[2][owner], c.z);
+}
+
 SVCM_D void evaluatePair(const DevScene &sc, const IterConst &ic, const GridBuffers &g, float (*q)[32],
                          float (*acc)[32], uint32_t idx, uint32_t owner, float lenBits, float weight)
 {
@@ -1066,7 +1125,7 @@ k_mergeStaged(const __grid_constant__ DevScene sc, const __grid_constant__ IterC
 // memory instead (dense grids: the stage is an accelerator, never a limit). In-range slots go to
 // per-lane lists and are evaluated flattened, 32 pairs per warp step.
 // ------------------------------------------------------------------------------------------
-#define BS_WARPS 8
+#define BS_WARPS 4          // warps per block: small blocks pack the shared memory of an SM better
 #define BS_GLOBAL 0xFFFFFFFFu
 
 template<int PCAP, int LCAP, int TSLOTS>
@@ -1085,6 +1144,11 @@ struct alignas(128) BucketWarpSmem
     unsigned long long bar;
 };
 
+// Evaluates every listed pair of the warp, 32 per step, and empties the lists. Pairs are taken in
+// owner-major order, so the lanes of one step hold runs of equal owners: their contributions are
+// summed with a segmented shuffle scan and the last lane of a run adds the run's sum to its owner
+// (shared-memory float atomics compile to compare-and-swap loops and were 11 % of this kernel's
+// instructions).
 template<int PCAP, int LCAP, int TSLOTS>
 SVCM_D void flushBucketLists(const DevScene &sc, const IterConst &ic, const GridBuffers &g,
                              BucketWarpSmem<PCAP, LCAP, TSLOTS> &w, uint32_t &cnt)
@@ -1104,14 +1168,33 @@ SVCM_D void flushBucketLists(const DevScene &sc, const IterConst &ic, const Grid
     for(uint32_t base = 0u; base < total; base += 32u)
     {
         const uint32_t p = base + lane;
+        uint32_t o = 0xFFFFFFFFu;                 // owner; lanes past the end form a run of their own
+        f3 c = mk3(0.f);
         if(p < total)
         {
-            uint32_t o = 0u;                      // the lane whose list holds pair p: pref[o] <= p < pref[o + 1]
+            o = 0u;                               // the lane whose list holds pair p: pref[o] <= p < pref[o + 1]
 #pragma unroll
             for(int s = 16; s > 0; s >>= 1) if(w.pref[o + uint32_t(s)] <= p) o += uint32_t(s);
             const uint32_t idx = w.list[p - w.pref[o]][o];
-            evaluatePair(sc, ic, g, w.q, w.acc, idx, o, reinterpret_cast<const float*>(g.sPosLen + idx)[3], 1.f);
+            const float lenBits = reinterpret_cast<const float*>(g.sPosLen + idx)[3];
+            const float4 dv = g.sDirVm[idx], tv = g.sThrVcm[idx];
+            const float cp = g.sContProb[idx];
+            c = pairContribution(sc, ic, w.q, o, lenBits, dv, tv, cp);
         }
+#pragma unroll
+        for(int d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t ou = __shfl_up_sync(FULL_MASK, o, d);
+            const float cx = __shfl_up_sync(FULL_MASK, c.x, d), cy = __shfl_up_sync(FULL_MASK, c.y, d),
+                        cz = __shfl_up_sync(FULL_MASK, c.z, d);
+            if(lane >= uint32_t(d) && ou == o) { c.x += cx; c.y += cy; c.z += cz; }
+        }
+        const uint32_t on = __shfl_down_sync(FULL_MASK, o, 1);
+        if(p < total && (lane == 31u || on != o))
+        {
+            w.acc[0][o] += c.x; w.acc[1][o] += c.y; w.acc[2][o] += c.z;
+        }
+        __syncwarp();
     }
     cnt = 0u;
     __syncwarp();
@@ -1158,15 +1241,15 @@ k_mergeBucketStaged(const __grid_constant__ DevScene sc, const __grid_constant__
 #pragma unroll
         for(int j = 0; j < 8; j++) h[j] = 0u;
 
-        float4 q1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
         if(valid)
         {
-            q1 = qs.q1[q];
-            valid = (__float_as_uint(q1.w) & CAMV_MERGEABLE) != 0u;   // else: vertex connection only
+            // all four words at once (one memory round trip); a vertex recorded for connection only is skipped
+            q0 = qs.q0[q]; q1 = qs.q1[q]; q2 = qs.q2[q]; q3 = qs.q3[q];
+            valid = (__float_as_uint(q1.w) & CAMV_MERGEABLE) != 0u;
         }
         if(valid)
         {
-            const float4 q0 = qs.q0[q], q2 = qs.q2[q], q3 = qs.q3[q];
             qpos = xyz(q0); scale = xyz(q3) * ic.vmNormalization; pixel = __float_as_uint(q0.w);
             const uint32_t lenMat = __float_as_uint(q1.w);
             Bsdf bsdf;                             // BSDF<false>::Setup from normal / local direction / material
@@ -1270,34 +1353,30 @@ k_mergeBucketStaged(const __grid_constant__ DevScene sc, const __grid_constant__
             __syncwarp();
         }
 
-        // ---- walk the 8 ranges in the reference's order ------------------------------------------
+        // ---- walk the 8 ranges in the reference's order, the whole warp in step ------------------
+        // Range j of every lane together, then candidate i of every lane together: the loop
+        // bookkeeping runs once per step for 32 lanes (a lane-private walk spent 40 % of the kernel's
+        // instructions hopping between its short ranges with 4 of 32 lanes active).
         uint32_t cnt = 0u;                        // entries in this lane's list
-        uint32_t j = 0u, i = 0u, n = 0u, start = 0u;
-        const float4 *base = g.sPosLen;
-        bool begun = false;
-        for(;;)
+#pragma unroll 1
+        for(uint32_t j = 0u; j < 8u; j++)
         {
-            bool exhausted = false;
-            for(;;)
+            uint32_t n = 0u, start = 0u;
+            const float4 *base = g.sPosLen;
+            if(inside)
             {
-                while(i >= n)
-                {
-                    if(begun) j++;
-                    begun = true;
-                    if(!inside || j >= 8u) { exhausted = true; break; }
-                    const uint32_t s = ((j < 4u ? slots >> (8u * j) : slotsHi >> (8u * (j - 4u))) & 0xFFu);
-                    n = w.slotCount[s]; start = w.slotStart[s]; i = 0u;
-                    const uint32_t off = w.slotOff[s];
-                    base = (off != BS_GLOBAL) ? &w.stage[off] : g.sPosLen + start;    // generic pointer: either space
-                    cand += n;
-                }
-                if(exhausted) break;
-                if(cnt == uint32_t(LCAP)) break;
-                if(inRange(qpos, base[i], ic.radiusSqr)) { w.list[cnt++][lane] = start + i; accepted++; }
-                i++;
+                const uint32_t s = ((j < 4u ? slots >> (8u * j) : slotsHi >> (8u * (j - 4u))) & 0xFFu);
+                n = w.slotCount[s]; start = w.slotStart[s];
+                const uint32_t off = w.slotOff[s];
+                base = (off != BS_GLOBAL) ? &w.stage[off] : g.sPosLen + start;    // generic pointer: either space
+                cand += n;
             }
-            if(!__any_sync(FULL_MASK, !exhausted)) break;
-            flushBucketLists<PCAP, LCAP, TSLOTS>(sc, ic, g, w, cnt);
+            const uint32_t nmax = __reduce_max_sync(FULL_MASK, n);
+            for(uint32_t i = 0u; i < nmax; i++)
+            {
+                if(i < n && inRange(qpos, base[i], ic.radiusSqr)) { w.list[cnt++][lane] = start + i; accepted++; }
+                if(__any_sync(FULL_MASK, cnt == uint32_t(LCAP))) flushBucketLists<PCAP, LCAP, TSLOTS>(sc, ic, g, w, cnt);
+            }
         }
         flushBucketLists<PCAP, LCAP, TSLOTS>(sc, ic, g, w, cnt);
 
@@ -1353,13 +1432,16 @@ void launchBucketStagedMerge(const DevScene &sc, const IterConst &ic, const Quer
     const uint64_t maxQueries = queryCount ? queries.capacity : hostQueryCount;
     if(maxQueries == 0) return;
     if(variant == 3)
-        launchBucketStagedT<256, 16, false>(sc, ic, queries, queryCount, hostQueryCount, grid, accum, contribOut, countsOut,
+        launchBucketStagedT<512, 16, false>(sc, ic, queries, queryCount, hostQueryCount, grid, accum, contribOut, countsOut,
                                             counters, maxQueries, stream);
     else if(variant == 4)
         launchBucketStagedT<128, 8, true>(sc, ic, queries, queryCount, hostQueryCount, grid, accum, contribOut, countsOut,
                                           counters, maxQueries, stream);
-    else
+    else if(variant == 5)
         launchBucketStagedT<256, 16, true>(sc, ic, queries, queryCount, hostQueryCount, grid, accum, contribOut, countsOut,
+                                           counters, maxQueries, stream);
+    else
+        launchBucketStagedT<512, 16, true>(sc, ic, queries, queryCount, hostQueryCount, grid, accum, contribOut, countsOut,
                                            counters, maxQueries, stream);
 }
 

@@ -228,7 +228,7 @@ void launchCameraBounce(const DevScene &sc, const IterConst &ic, const TraceArgs
 // the merge kernel then walk the same cell ranges. Returns the number of kernels launched.
 int launchQuerySort(const IterConst &ic, const QueryStore &queries, const unsigned long long *vertexCount,
                     const int32_t *bboxBits, const QuerySortBuffers &qs, unsigned long long *counters, ScanGen *gen,
-                    cudaStream_t stream);
+                    int spatial, cudaStream_t stream);
 // vertex connection of every queued (camera vertex, light vertex) pair
 void launchConnect(const DevScene &sc, const IterConst &ic, const TraceArgs &args, cudaStream_t stream);
 // any-hit tests + splats for the rays queued by pass `which` (0 light, 1 camera; count read on

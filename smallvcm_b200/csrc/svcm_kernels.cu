@@ -1048,6 +1048,16 @@ k_gridScatter(const __grid_constant__ MergeSet set, const __grid_constant__ Grid
     }
 }
 
+// 7 bits -> every third bit of 21
+SVCM_D uint32_t morton7(uint32_t v)
+{
+    v &= 0x7Fu;
+    v = (v | (v << 8)) & 0x0000700Fu;     // ---- ---- ---- ---- -654 ---- ---- 3210
+    v = (v | (v << 4)) & 0x000430C3u;     // ---- ---- ---- -6-- --54 ---- 32-- --10
+    v = (v | (v << 2)) & 0x00049249u;     // ---- ---- ---- -6-- 5--4 --3- -2-- 1--0
+    return v;
+}
+
 // ------------------------------------------------------------------------------------------
 // query grouping: the merge is a join between cell-sorted particles and range queries; sorting
 // the QUERIES by the bucket of their own cell as well makes neighbouring lanes of the merge
@@ -1056,11 +1066,21 @@ k_gridScatter(const __grid_constant__ MergeSet set, const __grid_constant__ Grid
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SVCM_BLOCK)
 k_queryKeys(const __grid_constant__ QueryStore qs, const unsigned long long *vertexCount, const int32_t *bboxBits,
-            float invCellSize, uint32_t numCells, uint32_t *key, uint32_t *cellCount, unsigned long long *counters)
+            float invCellSize, uint32_t numCells, uint32_t *key, uint32_t *cellCount, unsigned long long *counters,
+            int spatial)
 {
     const uint32_t n = uint32_t(min(*vertexCount, (unsigned long long)qs.capacity));
     const f3 bbMin = mk3(orderedToFloat(bboxBits[0]), orderedToFloat(bboxBits[1]), orderedToFloat(bboxBits[2]));
     const f3 bbMax = mk3(orderedToFloat(bboxBits[3]), orderedToFloat(bboxBits[4]), orderedToFloat(bboxBits[5]));
+    // spatial order: 21-bit Morton code of the own cell, coarsened until 7 bits per axis suffice
+    int shift = 0;
+    if(spatial)
+    {
+        const float ext = fmaxf(fmaxf(bbMax.x - bbMin.x, bbMax.y - bbMin.y), bbMax.z - bbMin.z);
+        const float cells = fminf(fmaxf(floorf(invCellSize * ext), 0.f), 1073741824.f);
+        uint32_t top = uint32_t(cells) >> 7;
+        while(top) { shift++; top >>= 1; }
+    }
     uint32_t nInside = 0u;
     for(uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x)
     {
@@ -1074,8 +1094,10 @@ k_queryKeys(const __grid_constant__ QueryStore qs, const unsigned long long *ver
                                   bbMax.y - p.y < 0.f || p.z - bbMin.z < 0.f || bbMax.z - p.z < 0.f);
             if(inside)
             {
-                k = cellHash(int32_t(floorf(invCellSize * (p.x - bbMin.x))), int32_t(floorf(invCellSize * (p.y - bbMin.y))),
-                             int32_t(floorf(invCellSize * (p.z - bbMin.z))), numCells);
+                const int32_t cx = int32_t(floorf(invCellSize * (p.x - bbMin.x))), cy = int32_t(floorf(invCellSize * (p.y - bbMin.y))),
+                              cz = int32_t(floorf(invCellSize * (p.z - bbMin.z)));
+                if(spatial) k = morton7(uint32_t(cx) >> shift) | (morton7(uint32_t(cy) >> shift) << 1) | (morton7(uint32_t(cz) >> shift) << 2);
+                else        k = cellHash(cx, cy, cz, numCells);
                 atomicAdd(cellCount + k, 1u);
                 nInside++;
             }
@@ -1682,25 +1704,30 @@ void launchCameraBounce(const DevScene &sc, const IterConst &ic, const TraceArgs
 
 int launchQuerySort(const IterConst &ic, const QueryStore &queries, const unsigned long long *vertexCount,
                     const int32_t *bboxBits, const QuerySortBuffers &qs, unsigned long long *counters, ScanGen *gen,
-                    cudaStream_t stream)
+                    int spatial, cudaStream_t stream)
 {
-    const uint32_t n = ic.numCells + 1u;
-    cudaMemsetAsync(qs.cellCount, 0, sizeof(uint32_t) * n, stream);
+    // order of the queries: by the hash bucket of their own cell (round 1), or — spatial — by a
+    // Morton code of the cell, so that consecutive warps of the merge work on neighbouring cells and
+    // find the buckets they share still in the L2
+    spatial = spatial && qs.cellEnd != NULL;
+    const uint32_t n = spatial ? (1u << 21) + 1u : ic.numCells + 1u;
+    uint32_t *table = spatial ? qs.cellEnd : qs.cellCount;
+    cudaMemsetAsync(table, 0, sizeof(uint32_t) * n, stream);
     const uint32_t gridN = gridFor(queries.capacity, SVCM_BLOCK, 8);
     k_queryKeys<<<gridN, SVCM_BLOCK, 0, stream>>>(queries, vertexCount, bboxBits, ic.invCellSize, ic.numCells,
-                                                  qs.key, qs.cellCount, counters);
+                                                  qs.key, table, counters, spatial);
     int launches = 3;
     if(gen && qs.scanState && (n + 4095u) / 4096u <= kScanStateWords)
-        launchLookbackScan(qs.cellCount, NULL, n, qs.scanState, qs.scanCounter, *gen, stream);   // single pass
+        launchLookbackScan(table, NULL, n, qs.scanState, qs.scanCounter, *gen, stream);   // single pass
     else
     {
         const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-        k_scanTiles<<<tiles, SVCM_BLOCK, 0, stream>>>(qs.cellCount, n, qs.blockSums);
+        k_scanTiles<<<tiles, SVCM_BLOCK, 0, stream>>>(table, n, qs.blockSums);
         k_scanSums<<<1, SVCM_BLOCK, 0, stream>>>(qs.blockSums, tiles);
-        k_scanAdd<<<tiles, SVCM_BLOCK, 0, stream>>>(qs.cellCount, n, qs.blockSums);
+        k_scanAdd<<<tiles, SVCM_BLOCK, 0, stream>>>(table, n, qs.blockSums);
         launches += 2;
     }
-    k_queryScatter<<<gridN, SVCM_BLOCK, 0, stream>>>(vertexCount, queries.capacity, qs.key, qs.cellCount, qs.order);
+    k_queryScatter<<<gridN, SVCM_BLOCK, 0, stream>>>(vertexCount, queries.capacity, qs.key, table, qs.order);
     return launches;
 }
 

@@ -188,7 +188,7 @@ def test_hashgrid_edge_cases(layout, variant, monkeypatch):
     assert close(gc, oc).all()
 
 
-@pytest.mark.parametrize("merge_kernel", ["1", "2", "3", "4", "8", "32", "cell0", "cell1", "cell3"])
+@pytest.mark.parametrize("merge_kernel", ["1", "2", "3", "4", "5", "8", "32", "cell0", "cell1", "cell3"])
 @pytest.mark.parametrize("scene_id,alg,w,ppm", [(1, "vcm", 128, False), (3, "bpm", 128, False), (1, "ppm", 96, True),
                                                 (0, "vcm", 96, False)])
 def test_hashgrid_query_against_oracle(scene_id, alg, w, ppm, merge_kernel, monkeypatch):
