@@ -431,7 +431,9 @@ SVCM_D f3 connectVertices(const DevScene &sc, const IterConst &ic, f3 lvPos, con
 // record that k_merge resolves after the whole camera pass (merging draws no random
 // numbers and does not steer the walk, so the split changes nothing but summation order).
 template<bool kBvh>
-__global__ void __launch_bounds__(SVCM_BLOCK)
+// (three resident blocks per SM: 80 registers with a few spill stores beat 86 registers and two
+// blocks — measured 1.73 -> 1.63 ms for the camera pass at 1024^2)
+__global__ void __launch_bounds__(SVCM_BLOCK, 3)
 k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
                const __grid_constant__ TraceArgs a, const uint32_t bounce)
 {
@@ -1313,14 +1315,17 @@ SVCM_D void mergeEvaluatePairs(const DevScene &sc, const IterConst &ic, const Gr
     if(head + lane < tail)
     {
         const uint32_t idx = w.queue[(head + lane) & 63u], owner = w.queueOwner[(head + lane) & 63u];
-        const uint32_t lvLen = __float_as_uint(g.sPosLen[idx].w);
+        // the particle's whole payload at once: one memory round trip per step instead of three
+        // dependent ones (length -> direction -> throughput)
+        const uint32_t lvLen = __float_as_uint(reinterpret_cast<const float*>(g.sPosLen + idx)[3]);
+        const float4 dv = g.sDirVm[idx], tv = g.sThrVcm[idx];
+        const float lightContProb = g.sContProb[idx];
         const uint32_t lenMat = __float_as_uint(w.q[12][owner]);
         const uint32_t camLen = lenMat & 0xFFFFu;
         const uint32_t camMat = (lenMat >> 16) & 0xFFu;
         // RangeQuery::Process, reference src/vertexcm.hxx:130-169
         if(!((lvLen + camLen > ic.maxLen) || (lvLen + camLen < ic.minLen)))
         {
-            const float4 dv = g.sDirVm[idx];
             Bsdf b;
             b.frame.x = mk3(w.q[0][owner], w.q[1][owner], w.q[2][owner]);
             b.frame.y = mk3(w.q[3][owner], w.q[4][owner], w.q[5][owner]);
@@ -1334,9 +1339,8 @@ SVCM_D void mergeEvaluatePairs(const DevScene &sc, const IterConst &ic, const Gr
                 const f3 f = bsdfEvaluateLocal(sc.mats[camMat], b, localDirGen, camDirPdfW, camRevPdfW);
                 if(!iszero(f))
                 {
-                    const float4 tv = g.sThrVcm[idx];
                     camDirPdfW *= b.contProb;
-                    camRevPdfW *= g.sContProb[idx];                    // the LIGHT vertex's RR probability
+                    camRevPdfW *= lightContProb;                       // the LIGHT vertex's RR probability
                     const float wLight  = tv.w * ic.misVcWeightFactor + dv.w * camDirPdfW;                     // (38)
                     const float wCamera = w.q[16][owner] * ic.misVcWeightFactor + w.q[17][owner] * camRevPdfW; // (39)
                     const float misWeight = ic.ppm ? 1.f : 1.f / (wLight + 1.f + wCamera);
@@ -1380,15 +1384,15 @@ k_mergeLane(const __grid_constant__ DevScene sc, const __grid_constant__ IterCon
 #pragma unroll
         for(int j = 0; j < 8; j++) { w.rangeStart[j][lane] = 0u; w.rangeEnd[j][lane] = 0u; }
 
-        float4 q1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
         if(valid)
         {
-            q1 = qs.q1[q];
+            // the four words of the record at once (one memory round trip)
+            q0 = qs.q0[q]; q1 = qs.q1[q]; q2 = qs.q2[q]; q3 = qs.q3[q];
             valid = (__float_as_uint(q1.w) & CAMV_MERGEABLE) != 0u;   // else: vertex connection only
         }
         if(valid)
         {
-            const float4 q0 = qs.q0[q], q2 = qs.q2[q], q3 = qs.q3[q];
             qpos = xyz(q0); scale = xyz(q3) * ic.vmNormalization; pixel = __float_as_uint(q0.w);
             const uint32_t lenMat = __float_as_uint(q1.w);
             // camera BSDF: BSDF<false>::Setup from the stored normal / local direction / material
@@ -1421,7 +1425,7 @@ k_mergeLane(const __grid_constant__ DevScene sc, const __grid_constant__ IterCon
 #pragma unroll
                 for(int j = 0; j < 8; j++)
                 {
-                    const uint32_t h = cellHash((j & 4) ? pxo : px, (j & 2) ? pyo : py, (j & 1) ? pzo : pz, ic.numCells);
+                    const uint32_t h = refHash((j & 4) ? pxo : px, (j & 2) ? pyo : py, (j & 1) ? pzo : pz, ic);
                     const uint32_t start = (h == 0u) ? 0u : g.cellCount[h - 1u];   // GetCellRange
                     const uint32_t end = g.cellCount[h];
                     w.rangeStart[j][lane] = start; w.rangeEnd[j][lane] = end;
@@ -1434,17 +1438,28 @@ k_mergeLane(const __grid_constant__ DevScene sc, const __grid_constant__ IterCon
         // walk the ranges; compact accepted pairs through the warp queue
         uint32_t j = 0u, cur = w.rangeStart[0][lane], end = w.rangeEnd[0][lane];
         uint32_t head = 0u, tail = 0u;
+        // the position of the NEXT candidate is requested one step ahead: its latency overlaps the
+        // test, the compaction and the pair evaluations of the current step
+        while(cur == end && j < 7u) { j++; cur = w.rangeStart[j][lane]; end = w.rangeEnd[j][lane]; }
+        bool has = cur < end;
+        float4 plNext = make_float4(0.f, 0.f, 0.f, 0.f);
+        if(has) plNext = g.sPosLen[cur];
         for(;;)
         {
-            while(cur == end && j < 7u) { j++; cur = w.rangeStart[j][lane]; end = w.rangeEnd[j][lane]; }
-            const bool has = cur < end;
             if(!__any_sync(FULL_MASK, has)) break;
             bool hitIt = false;
             uint32_t idx = 0u;
+            const float4 pl = plNext;
+            const bool hasNow = has;
             if(has)
             {
                 idx = cur++;
-                const float4 pl = g.sPosLen[idx];
+                while(cur == end && j < 7u) { j++; cur = w.rangeStart[j][lane]; end = w.rangeEnd[j][lane]; }
+                has = cur < end;
+                if(has) plNext = g.sPosLen[cur];
+            }
+            if(hasNow)
+            {
                 // |q - p|^2 <= r^2 in the reference's exact (unfused) evaluation order
                 // (src/hashgrid.hxx:162-165): identical accept decisions for identical inputs
                 const float dx = qpos.x - pl.x, dy = qpos.y - pl.y, dz = qpos.z - pl.z;

@@ -103,6 +103,16 @@ SVCM_D uint32_t cellHash(int32_t cx, int32_t cy, int32_t cz, uint32_t numCells)
 }
 
 
+// x % numCells for the reference hash (src/hashgrid.hxx:179-187) without an integer division:
+// floor(a / n) = mulhi64(a, ceil(2^64 / n)) exactly for a < 2^32
+SVCM_D uint32_t refHash(int32_t cx, int32_t cy, int32_t cz, const IterConst &ic)
+{
+    const uint32_t a = (uint32_t(cx) * 73856093u) ^ (uint32_t(cy) * 19349663u) ^ (uint32_t(cz) * 83492791u);
+    if(ic.hashMagic == 0ull) return 0u;                       // numCells == 1
+    const uint32_t q = uint32_t(__umul64hi((unsigned long long)a, ic.hashMagic));
+    return a - q * ic.numCells;
+}
+
 // persistent-style grid: a multiple of the SM count, capped by the work available
 int numSMs();
 uint32_t gridFor(uint64_t items, int perBlock, int blocksPerSM);
