@@ -147,6 +147,7 @@ struct svcm_renderer
     cudaStream_t cameraStream;
     cudaEvent_t  evIterStart, evCameraDone;
     bool overlapPasses;             // SVCM_NO_PASS_OVERLAP=1 serialises them again (A/B)
+    bool overlapGrid;               // SVCM_NO_GRID_OVERLAP=1: grid build on the main stream (isolated stage times)
     bool spatialQueries;            // SVCM_QUERY_ORDER=bucket restores round 1's order (A/B)
     bool legacyBuild;               // SVCM_LEGACY_BUILD=1: round 1's three-kernel scan + direct record scatter (A/B)
 
@@ -783,7 +784,7 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     // concurrently with the camera sub-paths and only the merge waits for them.
     if(r->useVM)
     {
-        cudaStream_t sg = r->gridStream;
+        cudaStream_t sg = r->overlapGrid ? r->gridStream : st;      // same stream: strictly after the light pass, before the camera pass joins
         SVCM_CUDA(r, cudaEventRecord(r->evLightDone, st));
         SVCM_CUDA(r, cudaStreamWaitEvent(sg, r->evLightDone, 0));
         if(timed) cudaEventRecord(ev[6], sg);
@@ -855,7 +856,7 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
             launches += launchQuerySort(ic, r->queries, r->counters + CNT_CAM_VERTS, r->grid.bboxBits, r->qsort,
                                         r->counters, r->legacyBuild ? NULL : &r->scanGenQuery, r->spatialQueries, st);
             qs.order = r->qsort.order;
-            if(r->mergeGroup >= 2 && r->mergeGroup <= 5)
+            if(r->mergeGroup >= 2 && r->mergeGroup <= 6)
                 launchBucketStagedMerge(r->scene, ic, qs, count, 0, r->grid, r->accum, NULL, NULL, r->counters,
                                         r->mergeGroup, st);
             else
@@ -975,6 +976,7 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     r->cameraStream = NULL; r->evIterStart = NULL; r->evCameraDone = NULL;
     r->overlapPasses = !(getenv("SVCM_NO_PASS_OVERLAP") && atoi(getenv("SVCM_NO_PASS_OVERLAP")) != 0);
     r->legacyBuild = getenv("SVCM_LEGACY_BUILD") && atoi(getenv("SVCM_LEGACY_BUILD")) != 0;
+    r->overlapGrid = !(getenv("SVCM_NO_GRID_OVERLAP") && atoi(getenv("SVCM_NO_GRID_OVERLAP")) != 0);
     r->spatialQueries = !(getenv("SVCM_QUERY_ORDER") && strcmp(getenv("SVCM_QUERY_ORDER"), "bucket") == 0);
     r->iterationsDone = 0; r->profile = false;
     r->mergeGroup = getenv("SVCM_MERGE_KERNEL") ? atoi(getenv("SVCM_MERGE_KERNEL")) : 1;
@@ -1125,8 +1127,8 @@ int svcm_set_option(svcm_renderer *r, int32_t option, int64_t value)
         r->profile = value != 0;
         return SVCM_OK;
     case SVCM_OPT_MERGE_GROUP:
-        if(value != 1 && value != 2 && value != 3 && value != 4 && value != 5 && value != 8 && value != 16 && value != 32)
-            return fail(r, SVCM_E_INVALID, "merge kernel must be 1 (lane per query), 2..5 (staged buckets), 8, 16 or 32");
+        if(!((value >= 1 && value <= 6) || value == 8 || value == 16 || value == 32))
+            return fail(r, SVCM_E_INVALID, "merge kernel must be 1 (lane per query), 2..5 (staged buckets), 6 (lane per query, private lists), 8, 16 or 32");
         r->mergeGroup = int(value); return SVCM_OK;
     case SVCM_OPT_COUNTERS: return SVCM_OK;   // counters are always maintained
     case SVCM_OPT_GRID_LAYOUT:
@@ -1692,7 +1694,7 @@ int svcm_hashgrid_query(svcm_hashgrid *g, const SvcmSceneDesc *scene, const Svcm
         // the parity tests exercise every merge kernel: the environment picks the variant
         const char *variant = getenv("SVCM_MERGE_GROUP");
         const int group = variant ? atoi(variant) : 1;
-        if(group >= 2 && group <= 5)
+        if(group >= 2 && group <= 6)
             launchBucketStagedMerge(sc, ic, qs, NULL, uint32_t(count), g->grid, NULL, dContrib, dCounts, NULL, group, 0);
         else
             launchMerge(sc, ic, qs, NULL, uint32_t(count), g->grid, NULL, dContrib, dCounts, NULL,

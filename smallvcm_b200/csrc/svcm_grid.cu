@@ -1393,6 +1393,178 @@ k_mergeBucketStaged(const __grid_constant__ DevScene sc, const __grid_constant__
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// merge over the bucket layout, lane per query from global memory, second version: the walk of
+// round 1's k_mergeLane (every lane its own 8 ranges, one candidate per step) without a ballot and
+// a shared ring update in every step — an in-range slot goes to the lane's private list with one
+// predicated store, and the lists are evaluated flattened (owner-major, 32 pairs per step, segmented
+// shuffle reduction) whenever one of them is full.
+// ------------------------------------------------------------------------------------------
+#define L2_WARPS (SVCM_BLOCK / 32)
+#define L2_LCAP 8
+
+struct LaneV2Smem
+{
+    uint32_t list[L2_LCAP][32];
+    float    q[CQ_WORDS][32];
+    float    acc[3][32];
+    uint32_t pref[32];
+    uint32_t rangeStart[8][32];
+    uint32_t rangeEnd[8][32];
+};
+
+SVCM_D void flushLaneLists(const DevScene &sc, const IterConst &ic, const GridBuffers &g, LaneV2Smem &w, uint32_t &cnt)
+{
+    const uint32_t lane = laneId();
+    uint32_t inc = cnt;
+#pragma unroll
+    for(int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o);
+        if(lane >= uint32_t(o)) inc += t;
+    }
+    const uint32_t total = __shfl_sync(FULL_MASK, inc, 31);
+    if(total == 0u) return;
+    w.pref[lane] = inc - cnt;
+    __syncwarp();
+    for(uint32_t base = 0u; base < total; base += 32u)
+    {
+        const uint32_t p = base + lane;
+        uint32_t o = 0xFFFFFFFFu;
+        f3 c = mk3(0.f);
+        if(p < total)
+        {
+            o = 0u;
+#pragma unroll
+            for(int s = 16; s > 0; s >>= 1) if(w.pref[o + uint32_t(s)] <= p) o += uint32_t(s);
+            const uint32_t idx = w.list[p - w.pref[o]][o];
+            const float lenBits = reinterpret_cast<const float*>(g.sPosLen + idx)[3];
+            const float4 dv = g.sDirVm[idx], tv = g.sThrVcm[idx];
+            const float cp = g.sContProb[idx];
+            c = pairContribution(sc, ic, w.q, o, lenBits, dv, tv, cp);
+        }
+#pragma unroll
+        for(int d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t ou = __shfl_up_sync(FULL_MASK, o, d);
+            const float cx = __shfl_up_sync(FULL_MASK, c.x, d), cy = __shfl_up_sync(FULL_MASK, c.y, d),
+                        cz = __shfl_up_sync(FULL_MASK, c.z, d);
+            if(lane >= uint32_t(d) && ou == o) { c.x += cx; c.y += cy; c.z += cz; }
+        }
+        const uint32_t on = __shfl_down_sync(FULL_MASK, o, 1);
+        if(p < total && (lane == 31u || on != o)) { w.acc[0][o] += c.x; w.acc[1][o] += c.y; w.acc[2][o] += c.z; }
+        __syncwarp();
+    }
+    cnt = 0u;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(SVCM_BLOCK, 4)
+k_mergeLaneV2(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
+              const __grid_constant__ QueryStore qs, const unsigned long long *queryCountPtr,
+              const uint32_t hostQueryCount, const __grid_constant__ GridBuffers g, float *accum,
+              float *contribOut, int32_t *countsOut, unsigned long long *counters)
+{
+    __shared__ LaneV2Smem smem[L2_WARPS];
+    LaneV2Smem &w = smem[threadIdx.x >> 5];
+    uint32_t nq = hostQueryCount;
+    if(queryCountPtr) nq = uint32_t(min(*queryCountPtr, (unsigned long long)qs.capacity));
+    const uint32_t lane = laneId();
+    const f3 bbMin = mk3(orderedToFloat(g.bboxBits[0]), orderedToFloat(g.bboxBits[1]), orderedToFloat(g.bboxBits[2]));
+    const f3 bbMax = mk3(orderedToFloat(g.bboxBits[3]), orderedToFloat(g.bboxBits[4]), orderedToFloat(g.bboxBits[5]));
+    uint32_t nCand = 0u, nAcc = 0u;
+
+    for(uint32_t q0i = (blockIdx.x * L2_WARPS + (threadIdx.x >> 5)) * 32u; q0i < nq; q0i += gridDim.x * L2_WARPS * 32u)
+    {
+        bool valid = q0i + lane < nq;
+        const uint32_t q = valid ? (qs.order ? qs.order[q0i + lane] : q0i + lane) : 0u;
+        f3 qpos = mk3(0.f), scale = mk3(0.f);
+        uint32_t pixel = 0u, cand = 0u, accepted = 0u;
+        w.acc[0][lane] = 0.f; w.acc[1][lane] = 0.f; w.acc[2][lane] = 0.f;
+#pragma unroll
+        for(int j = 0; j < 8; j++) { w.rangeStart[j][lane] = 0u; w.rangeEnd[j][lane] = 0u; }
+
+        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
+        if(valid)
+        {
+            q0 = qs.q0[q]; q1 = qs.q1[q]; q2 = qs.q2[q]; q3 = qs.q3[q];
+            valid = (__float_as_uint(q1.w) & CAMV_MERGEABLE) != 0u;   // else: vertex connection only
+        }
+        if(valid)
+        {
+            qpos = xyz(q0); scale = xyz(q3) * ic.vmNormalization; pixel = __float_as_uint(q0.w);
+            const uint32_t lenMat = __float_as_uint(q1.w);
+            Bsdf bsdf;                             // BSDF<false>::Setup from normal / local direction / material
+            bsdf.frame.setFromZ(xyz(q1));
+            bsdf.localDirFix = xyz(q2);
+            bsdf.diffProb = bsdf.phongProb = bsdf.reflProb = bsdf.refrProb = 0.f;
+            bsdfFromLocal(sc, int32_t((lenMat >> 16) & 0xFFu), bsdf);
+            parkQuery(w.q, lane, bsdf, q1.w, q2.w, q3.w);
+            // HashGrid::Process: bbox early-out, then the 8 cells (src/hashgrid.hxx:116-155)
+            const bool inside = !(qpos.x - bbMin.x < 0.f || bbMax.x - qpos.x < 0.f || qpos.y - bbMin.y < 0.f ||
+                                  bbMax.y - qpos.y < 0.f || qpos.z - bbMin.z < 0.f || bbMax.z - qpos.z < 0.f);
+            if(inside)
+            {
+                const f3 cellPt = mk3(ic.invCellSize * (qpos.x - bbMin.x), ic.invCellSize * (qpos.y - bbMin.y),
+                                      ic.invCellSize * (qpos.z - bbMin.z));
+                const f3 coordF = mk3(floorf(cellPt.x), floorf(cellPt.y), floorf(cellPt.z));
+                const int px = int(coordF.x), py = int(coordF.y), pz = int(coordF.z);
+                const int pxo = px + ((cellPt.x - coordF.x) < 0.5f ? -1 : +1);
+                const int pyo = py + ((cellPt.y - coordF.y) < 0.5f ? -1 : +1);
+                const int pzo = pz + ((cellPt.z - coordF.z) < 0.5f ? -1 : +1);
+#pragma unroll
+                for(int j = 0; j < 8; j++)
+                {
+                    const uint32_t h = refHash((j & 4) ? pxo : px, (j & 2) ? pyo : py, (j & 1) ? pzo : pz, ic);
+                    const uint32_t start = (h == 0u) ? 0u : g.cellCount[h - 1u];   // GetCellRange
+                    const uint32_t end = g.cellCount[h];
+                    w.rangeStart[j][lane] = start; w.rangeEnd[j][lane] = end;
+                    cand += end - start;
+                }
+            }
+        }
+        __syncwarp();
+
+        uint32_t cnt = 0u;
+        uint32_t j = 0u, cur = w.rangeStart[0][lane], end = w.rangeEnd[0][lane];
+        for(;;)
+        {
+            bool exhausted = false;                // else: stopped at a full list
+            for(;;)
+            {
+                while(cur == end && j < 7u) { j++; cur = w.rangeStart[j][lane]; end = w.rangeEnd[j][lane]; }
+                if(cur == end) { exhausted = true; break; }
+                if(cnt == uint32_t(L2_LCAP)) break;
+                if(inRange(qpos, g.sPosLen[cur], ic.radiusSqr)) { w.list[cnt++][lane] = cur; accepted++; }
+                cur++;
+            }
+            if(!__any_sync(FULL_MASK, !exhausted)) break;
+            flushLaneLists(sc, ic, g, w, cnt);
+        }
+        flushLaneLists(sc, ic, g, w, cnt);
+
+        if(valid)
+        {
+            const f3 contrib = mk3(w.acc[0][lane], w.acc[1][lane], w.acc[2][lane]);
+            nCand += cand; nAcc += accepted;
+            if(contribOut)
+            {
+                contribOut[3ull * q + 0] = contrib.x; contribOut[3ull * q + 1] = contrib.y;
+                contribOut[3ull * q + 2] = contrib.z;
+            }
+            if(countsOut) { countsOut[2ull * q] = int32_t(cand); countsOut[2ull * q + 1] = int32_t(accepted); }
+            // color += cameraState.mThroughput * mVmNormalization * query.GetContrib()  (src/vertexcm.hxx:534)
+            if(accum) addPixel(accum, pixel, scale * contrib);
+        }
+        __syncwarp();
+    }
+    if(counters)
+    {
+        warpCount(counters + CNT_CANDIDATES, nCand);
+        warpCount(counters + CNT_ACCEPTED, nAcc);
+    }
+}
+
 template<int PCAP, int LCAP, bool kBulk>
 static void launchBucketStagedT(const DevScene &sc, const IterConst &ic, const QueryStore &queries,
                                 const unsigned long long *queryCount, uint32_t hostQueryCount, const GridBuffers &grid,
@@ -1421,7 +1593,10 @@ void launchBucketStagedMerge(const DevScene &sc, const IterConst &ic, const Quer
 {
     const uint64_t maxQueries = queryCount ? queries.capacity : hostQueryCount;
     if(maxQueries == 0) return;
-    if(variant == 3)
+    if(variant == 6)
+        k_mergeLaneV2<<<gridFor(maxQueries, SVCM_BLOCK, 4), SVCM_BLOCK, 0, stream>>>(
+            sc, ic, queries, queryCount, hostQueryCount, grid, accum, contribOut, countsOut, counters);
+    else if(variant == 3)
         launchBucketStagedT<512, 16, false>(sc, ic, queries, queryCount, hostQueryCount, grid, accum, contribOut, countsOut,
                                             counters, maxQueries, stream);
     else if(variant == 4)

