@@ -1050,16 +1050,6 @@ k_gridScatter(const __grid_constant__ MergeSet set, const __grid_constant__ Grid
     }
 }
 
-// 7 bits -> every third bit of 21
-SVCM_D uint32_t morton7(uint32_t v)
-{
-    v &= 0x7Fu;
-    v = (v | (v << 8)) & 0x0000700Fu;     // ---- ---- ---- ---- -654 ---- ---- 3210
-    v = (v | (v << 4)) & 0x000430C3u;     // ---- ---- ---- -6-- --54 ---- 32-- --10
-    v = (v | (v << 2)) & 0x00049249u;     // ---- ---- ---- -6-- 5--4 --3- -2-- 1--0
-    return v;
-}
-
 // ------------------------------------------------------------------------------------------
 // query grouping: the merge is a join between cell-sorted particles and range queries; sorting
 // the QUERIES by the bucket of their own cell as well makes neighbouring lanes of the merge
@@ -1075,14 +1065,7 @@ k_queryKeys(const __grid_constant__ QueryStore qs, const unsigned long long *ver
     const f3 bbMin = mk3(orderedToFloat(bboxBits[0]), orderedToFloat(bboxBits[1]), orderedToFloat(bboxBits[2]));
     const f3 bbMax = mk3(orderedToFloat(bboxBits[3]), orderedToFloat(bboxBits[4]), orderedToFloat(bboxBits[5]));
     // spatial order: 21-bit Morton code of the own cell, coarsened until 7 bits per axis suffice
-    int shift = 0;
-    if(spatial)
-    {
-        const float ext = fmaxf(fmaxf(bbMax.x - bbMin.x, bbMax.y - bbMin.y), bbMax.z - bbMin.z);
-        const float cells = fminf(fmaxf(floorf(invCellSize * ext), 0.f), 1073741824.f);
-        uint32_t top = uint32_t(cells) >> 7;
-        while(top) { shift++; top >>= 1; }
-    }
+    const int shift = spatial ? mortonShift(bbMin, bbMax, invCellSize) : 0;
     uint32_t nInside = 0u;
     for(uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x)
     {

@@ -113,6 +113,37 @@ SVCM_D uint32_t refHash(int32_t cx, int32_t cy, int32_t cz, const IterConst &ic)
     return a - q * ic.numCells;
 }
 
+// ---- spatial order of the merge queries: 21-bit Morton code of the query's own cell, coarsened by
+// `shift` bits per axis until 7 bits per axis suffice. All queries of one code form a GROUP: the
+// cells of a cube of 2^shift cells per axis.
+// 7 bits -> every third bit of 21
+SVCM_D uint32_t morton7(uint32_t v)
+{
+    v &= 0x7Fu;
+    v = (v | (v << 8)) & 0x0000700Fu;     // ---- ---- ---- ---- -654 ---- ---- 3210
+    v = (v | (v << 4)) & 0x000430C3u;     // ---- ---- ---- -6-- --54 ---- 32-- --10
+    v = (v | (v << 2)) & 0x00049249u;     // ---- ---- ---- -6-- 5--4 --3- -2-- 1--0
+    return v;
+}
+// every third bit of 21 -> 7 bits
+SVCM_D uint32_t unmorton7(uint32_t v)
+{
+    v &= 0x00049249u;
+    v = (v | (v >> 2)) & 0x000430C3u;
+    v = (v | (v >> 4)) & 0x0000700Fu;
+    v = (v | (v >> 8)) & 0x0000007Fu;
+    return v;
+}
+SVCM_D int mortonShift(f3 bbMin, f3 bbMax, float invCellSize)
+{
+    const float ext = fmaxf(fmaxf(bbMax.x - bbMin.x, bbMax.y - bbMin.y), bbMax.z - bbMin.z);
+    const float cells = fminf(fmaxf(floorf(invCellSize * ext), 0.f), 1073741824.f);
+    uint32_t top = uint32_t(cells) >> 7;
+    int shift = 0;
+    while(top) { shift++; top >>= 1; }
+    return shift;
+}
+
 // persistent-style grid: a multiple of the SM count, capped by the work available
 int numSMs();
 uint32_t gridFor(uint64_t items, int perBlock, int blocksPerSM);
