@@ -856,11 +856,7 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
             launches += launchQuerySort(ic, r->queries, r->counters + CNT_CAM_VERTS, r->grid.bboxBits, r->qsort,
                                         r->counters, r->legacyBuild ? NULL : &r->scanGenQuery, r->spatialQueries, st);
             qs.order = r->qsort.order;
-            if(r->mergeGroup == 7 && r->spatialQueries && groupMergeApplicable(r->scene.sphereRadius, ic.radius))
-                launchGroupMerge(r->scene, ic, qs, r->qsort.cellEnd, r->grid, r->accum, NULL, NULL, r->counters, st);
-            else if(r->mergeGroup == 7)
-                launchMerge(r->scene, ic, qs, count, 0, r->grid, r->accum, NULL, NULL, r->counters, 1, st);
-            else if(r->mergeGroup >= 2 && r->mergeGroup <= 6)
+            if(r->mergeGroup >= 2 && r->mergeGroup <= 5)
                 launchBucketStagedMerge(r->scene, ic, qs, count, 0, r->grid, r->accum, NULL, NULL, r->counters,
                                         r->mergeGroup, st);
             else
@@ -1131,8 +1127,8 @@ int svcm_set_option(svcm_renderer *r, int32_t option, int64_t value)
         r->profile = value != 0;
         return SVCM_OK;
     case SVCM_OPT_MERGE_GROUP:
-        if(!((value >= 1 && value <= 7) || value == 8 || value == 16 || value == 32))
-            return fail(r, SVCM_E_INVALID, "merge kernel must be 1 (lane per query), 2..5 (staged buckets), 6 (lane per query, private lists), 8, 16 or 32");
+        if(!((value >= 1 && value <= 5) || value == 8 || value == 16 || value == 32))
+            return fail(r, SVCM_E_INVALID, "merge kernel must be 1 (lane per query), 2..5 (staged buckets), 8, 16 or 32");
         r->mergeGroup = int(value); return SVCM_OK;
     case SVCM_OPT_COUNTERS: return SVCM_OK;   // counters are always maintained
     case SVCM_OPT_GRID_LAYOUT:
@@ -1698,32 +1694,7 @@ int svcm_hashgrid_query(svcm_hashgrid *g, const SvcmSceneDesc *scene, const Svcm
         // the parity tests exercise every merge kernel: the environment picks the variant
         const char *variant = getenv("SVCM_MERGE_GROUP");
         const int group = variant ? atoi(variant) : 1;
-        if(group == 7 && groupMergeApplicable(1.5f, g->radius))
-        {
-            // the group kernel works on the spatially sorted queries: sort them like the path does
-            // (queries outside the particle bbox are left out of the order: their results stay zero)
-            QuerySortBuffers sort; memset(&sort, 0, sizeof(sort));
-            sort.key = s.alloc<uint32_t>(size_t(count), e); sort.order = s.alloc<uint32_t>(size_t(count), e);
-            sort.cellEnd = s.alloc<uint32_t>(size_t(1u << 21) + 64, e);
-            sort.scanState = s.alloc<unsigned long long>(kScanStateWords, e);
-            sort.scanCounter = s.alloc<uint32_t>(1, e);
-            unsigned long long *dCounters = s.alloc<unsigned long long>(CNT_WORDS, e);
-            unsigned long long hostCounters[CNT_WORDS]; memset(hostCounters, 0, sizeof(hostCounters));
-            hostCounters[CNT_CAM_VERTS] = (unsigned long long)count;
-            if(e == cudaSuccess) e = cudaMemset(sort.scanState, 0, sizeof(unsigned long long) * kScanStateWords);
-            if(e == cudaSuccess) e = cudaMemset(sort.scanCounter, 0, sizeof(uint32_t));
-            if(e == cudaSuccess) e = cudaMemcpy(dCounters, hostCounters, sizeof(hostCounters), cudaMemcpyHostToDevice);
-            if(e == cudaSuccess) e = cudaMemset(dContrib, 0, sizeof(float) * 3 * size_t(count));
-            if(e == cudaSuccess) e = cudaMemset(dCounts, 0, sizeof(int32_t) * 2 * size_t(count));
-            if(e == cudaSuccess)
-            {
-                ScanGen gen; gen.value = 0;
-                launchQuerySort(ic, qs, dCounters + CNT_CAM_VERTS, g->grid.bboxBits, sort, dCounters, &gen, 1, 0);
-                qs.order = sort.order;
-                launchGroupMerge(sc, ic, qs, sort.cellEnd, g->grid, NULL, dContrib, dCounts, NULL, 0);
-            }
-        }
-        else if(group >= 2 && group <= 6)
+        if(group >= 2 && group <= 5)
             launchBucketStagedMerge(sc, ic, qs, NULL, uint32_t(count), g->grid, NULL, dContrib, dCounts, NULL, group, 0);
         else
             launchMerge(sc, ic, qs, NULL, uint32_t(count), g->grid, NULL, dContrib, dCounts, NULL,

@@ -1393,508 +1393,6 @@ k_mergeBucketStaged(const __grid_constant__ DevScene sc, const __grid_constant__
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// merge over the bucket layout, lane per query from global memory, second version: the walk of
-// round 1's k_mergeLane (every lane its own 8 ranges, one candidate per step) without a ballot and
-// a shared ring update in every step — an in-range slot goes to the lane's private list with one
-// predicated store, and the lists are evaluated flattened (owner-major, 32 pairs per step, segmented
-// shuffle reduction) whenever one of them is full.
-// ------------------------------------------------------------------------------------------
-#define L2_WARPS (SVCM_BLOCK / 32)
-#define L2_LCAP 8
-
-struct LaneV2Smem
-{
-    uint32_t list[L2_LCAP][32];
-    float    q[CQ_WORDS][32];
-    float    acc[3][32];
-    uint32_t pref[32];
-    uint32_t rangeStart[8][32];
-    uint32_t rangeEnd[8][32];
-};
-
-SVCM_D void flushLaneLists(const DevScene &sc, const IterConst &ic, const GridBuffers &g, LaneV2Smem &w, uint32_t &cnt)
-{
-    const uint32_t lane = laneId();
-    uint32_t inc = cnt;
-#pragma unroll
-    for(int o = 1; o < 32; o <<= 1)
-    {
-        const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o);
-        if(lane >= uint32_t(o)) inc += t;
-    }
-    const uint32_t total = __shfl_sync(FULL_MASK, inc, 31);
-    if(total == 0u) return;
-    w.pref[lane] = inc - cnt;
-    __syncwarp();
-    for(uint32_t base = 0u; base < total; base += 32u)
-    {
-        const uint32_t p = base + lane;
-        uint32_t o = 0xFFFFFFFFu;
-        f3 c = mk3(0.f);
-        if(p < total)
-        {
-            o = 0u;
-#pragma unroll
-            for(int s = 16; s > 0; s >>= 1) if(w.pref[o + uint32_t(s)] <= p) o += uint32_t(s);
-            const uint32_t idx = w.list[p - w.pref[o]][o];
-            const float lenBits = reinterpret_cast<const float*>(g.sPosLen + idx)[3];
-            const float4 dv = g.sDirVm[idx], tv = g.sThrVcm[idx];
-            const float cp = g.sContProb[idx];
-            c = pairContribution(sc, ic, w.q, o, lenBits, dv, tv, cp);
-        }
-#pragma unroll
-        for(int d = 1; d < 32; d <<= 1)
-        {
-            const uint32_t ou = __shfl_up_sync(FULL_MASK, o, d);
-            const float cx = __shfl_up_sync(FULL_MASK, c.x, d), cy = __shfl_up_sync(FULL_MASK, c.y, d),
-                        cz = __shfl_up_sync(FULL_MASK, c.z, d);
-            if(lane >= uint32_t(d) && ou == o) { c.x += cx; c.y += cy; c.z += cz; }
-        }
-        const uint32_t on = __shfl_down_sync(FULL_MASK, o, 1);
-        if(p < total && (lane == 31u || on != o)) { w.acc[0][o] += c.x; w.acc[1][o] += c.y; w.acc[2][o] += c.z; }
-        __syncwarp();
-    }
-    cnt = 0u;
-    __syncwarp();
-}
-
-__global__ void __launch_bounds__(SVCM_BLOCK, 4)
-k_mergeLaneV2(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
-              const __grid_constant__ QueryStore qs, const unsigned long long *queryCountPtr,
-              const uint32_t hostQueryCount, const __grid_constant__ GridBuffers g, float *accum,
-              float *contribOut, int32_t *countsOut, unsigned long long *counters)
-{
-    __shared__ LaneV2Smem smem[L2_WARPS];
-    LaneV2Smem &w = smem[threadIdx.x >> 5];
-    uint32_t nq = hostQueryCount;
-    if(queryCountPtr) nq = uint32_t(min(*queryCountPtr, (unsigned long long)qs.capacity));
-    const uint32_t lane = laneId();
-    const f3 bbMin = mk3(orderedToFloat(g.bboxBits[0]), orderedToFloat(g.bboxBits[1]), orderedToFloat(g.bboxBits[2]));
-    const f3 bbMax = mk3(orderedToFloat(g.bboxBits[3]), orderedToFloat(g.bboxBits[4]), orderedToFloat(g.bboxBits[5]));
-    uint32_t nCand = 0u, nAcc = 0u;
-
-    for(uint32_t q0i = (blockIdx.x * L2_WARPS + (threadIdx.x >> 5)) * 32u; q0i < nq; q0i += gridDim.x * L2_WARPS * 32u)
-    {
-        bool valid = q0i + lane < nq;
-        const uint32_t q = valid ? (qs.order ? qs.order[q0i + lane] : q0i + lane) : 0u;
-        f3 qpos = mk3(0.f), scale = mk3(0.f);
-        uint32_t pixel = 0u, cand = 0u, accepted = 0u;
-        w.acc[0][lane] = 0.f; w.acc[1][lane] = 0.f; w.acc[2][lane] = 0.f;
-#pragma unroll
-        for(int j = 0; j < 8; j++) { w.rangeStart[j][lane] = 0u; w.rangeEnd[j][lane] = 0u; }
-
-        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
-        if(valid)
-        {
-            q0 = qs.q0[q]; q1 = qs.q1[q]; q2 = qs.q2[q]; q3 = qs.q3[q];
-            valid = (__float_as_uint(q1.w) & CAMV_MERGEABLE) != 0u;   // else: vertex connection only
-        }
-        if(valid)
-        {
-            qpos = xyz(q0); scale = xyz(q3) * ic.vmNormalization; pixel = __float_as_uint(q0.w);
-            const uint32_t lenMat = __float_as_uint(q1.w);
-            Bsdf bsdf;                             // BSDF<false>::Setup from normal / local direction / material
-            bsdf.frame.setFromZ(xyz(q1));
-            bsdf.localDirFix = xyz(q2);
-            bsdf.diffProb = bsdf.phongProb = bsdf.reflProb = bsdf.refrProb = 0.f;
-            bsdfFromLocal(sc, int32_t((lenMat >> 16) & 0xFFu), bsdf);
-            parkQuery(w.q, lane, bsdf, q1.w, q2.w, q3.w);
-            // HashGrid::Process: bbox early-out, then the 8 cells (src/hashgrid.hxx:116-155)
-            const bool inside = !(qpos.x - bbMin.x < 0.f || bbMax.x - qpos.x < 0.f || qpos.y - bbMin.y < 0.f ||
-                                  bbMax.y - qpos.y < 0.f || qpos.z - bbMin.z < 0.f || bbMax.z - qpos.z < 0.f);
-            if(inside)
-            {
-                const f3 cellPt = mk3(ic.invCellSize * (qpos.x - bbMin.x), ic.invCellSize * (qpos.y - bbMin.y),
-                                      ic.invCellSize * (qpos.z - bbMin.z));
-                const f3 coordF = mk3(floorf(cellPt.x), floorf(cellPt.y), floorf(cellPt.z));
-                const int px = int(coordF.x), py = int(coordF.y), pz = int(coordF.z);
-                const int pxo = px + ((cellPt.x - coordF.x) < 0.5f ? -1 : +1);
-                const int pyo = py + ((cellPt.y - coordF.y) < 0.5f ? -1 : +1);
-                const int pzo = pz + ((cellPt.z - coordF.z) < 0.5f ? -1 : +1);
-#pragma unroll
-                for(int j = 0; j < 8; j++)
-                {
-                    const uint32_t h = refHash((j & 4) ? pxo : px, (j & 2) ? pyo : py, (j & 1) ? pzo : pz, ic);
-                    const uint32_t start = (h == 0u) ? 0u : g.cellCount[h - 1u];   // GetCellRange
-                    const uint32_t end = g.cellCount[h];
-                    w.rangeStart[j][lane] = start; w.rangeEnd[j][lane] = end;
-                    cand += end - start;
-                }
-            }
-        }
-        __syncwarp();
-
-        uint32_t cnt = 0u;
-        uint32_t j = 0u, cur = w.rangeStart[0][lane], end = w.rangeEnd[0][lane];
-        for(;;)
-        {
-            bool exhausted = false;                // else: stopped at a full list
-            for(;;)
-            {
-                while(cur == end && j < 7u) { j++; cur = w.rangeStart[j][lane]; end = w.rangeEnd[j][lane]; }
-                if(cur == end) { exhausted = true; break; }
-                if(cnt == uint32_t(L2_LCAP)) break;
-                if(inRange(qpos, g.sPosLen[cur], ic.radiusSqr)) { w.list[cnt++][lane] = cur; accepted++; }
-                cur++;
-            }
-            if(!__any_sync(FULL_MASK, !exhausted)) break;
-            flushLaneLists(sc, ic, g, w, cnt);
-        }
-        flushLaneLists(sc, ic, g, w, cnt);
-
-        if(valid)
-        {
-            const f3 contrib = mk3(w.acc[0][lane], w.acc[1][lane], w.acc[2][lane]);
-            nCand += cand; nAcc += accepted;
-            if(contribOut)
-            {
-                contribOut[3ull * q + 0] = contrib.x; contribOut[3ull * q + 1] = contrib.y;
-                contribOut[3ull * q + 2] = contrib.z;
-            }
-            if(countsOut) { countsOut[2ull * q] = int32_t(cand); countsOut[2ull * q + 1] = int32_t(accepted); }
-            // color += cameraState.mThroughput * mVmNormalization * query.GetContrib()  (src/vertexcm.hxx:534)
-            if(accum) addPixel(accum, pixel, scale * contrib);
-        }
-        __syncwarp();
-    }
-    if(counters)
-    {
-        warpCount(counters + CNT_CANDIDATES, nCand);
-        warpCount(counters + CNT_ACCEPTED, nAcc);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// merge, group-staged: the production kernel for sparse-to-moderate grids.
-//
-// The queries are sorted by the Morton code of their own cell (launchQuerySort, spatial order); all
-// queries of one code are the queries of a cube of B = 2^shift cells per axis. A warp takes one such
-// GROUP: every bucket its queries can visit belongs to a cell of the (B+2)^3 cube around it, so the
-// lanes hash those cells once (GetCellIndex, src/hashgrid.hxx:179-187), fetch their ranges once
-// (GetCellRange, :173-177) and bring the positions of every non-empty bucket into the warp's stage
-// with one bulk asynchronous copy each (cp.async.bulk, completion counted on an mbarrier). After
-// that a query finds the range of cell (x, y, z) by its position in the cube — no hashing, no
-// table lookups in global memory — and walks its 8 ranges, in the reference's order and a bucket
-// that two of its cells share twice like the reference, from shared memory. Buckets that do not
-// fit the stage are walked from global memory. In-range slots go to per-lane lists, evaluated
-// flattened with all lanes busy (flushLaneLists-style segmented reduction).
-//
-// Compared with one lane gathering its own candidates from global memory (k_mergeLane), which is
-// bound by the L1 request rate of scattered 16-byte loads (ncu: l1tex 67 % of peak, 10 sectors per
-// request), the candidates here cross the L1 once per group, as whole buckets.
-// ------------------------------------------------------------------------------------------
-#define GM_WARPS 4
-#define GM_LCAP 8
-#define GM_MAXB 4            // group cube edge up to 4 cells -> (4+2)^3 = 216 neighbourhood cells
-#define GM_CELLS ((GM_MAXB + 2) * (GM_MAXB + 2) * (GM_MAXB + 2))
-
-template<int PCAP>           // particles one warp stages: 256 for groups of up to 2^3 cells, 512 beyond
-struct alignas(128) GroupWarpSmem
-{
-    float4   stage[PCAP];
-    uint32_t list[GM_LCAP][32];
-    float    q[CQ_WORDS][32];
-    float    acc[3][32];
-    uint32_t pref[32];
-    uint32_t cellStart[GM_CELLS];       // first sorted slot of the cell's bucket
-    uint32_t cellCount[GM_CELLS];       // particles in it
-    uint32_t cellOff[GM_CELLS];         // offset in `stage`, or BS_GLOBAL
-    unsigned long long bar;
-};
-
-template<int PCAP>
-SVCM_D void flushGroupLists(const DevScene &sc, const IterConst &ic, const GridBuffers &g, GroupWarpSmem<PCAP> &w, uint32_t &cnt)
-{
-    const uint32_t lane = laneId();
-    uint32_t inc = cnt;
-#pragma unroll
-    for(int o = 1; o < 32; o <<= 1)
-    {
-        const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o);
-        if(lane >= uint32_t(o)) inc += t;
-    }
-    const uint32_t total = __shfl_sync(FULL_MASK, inc, 31);
-    if(total == 0u) return;
-    w.pref[lane] = inc - cnt;
-    __syncwarp();
-    for(uint32_t base = 0u; base < total; base += 32u)
-    {
-        const uint32_t p = base + lane;
-        uint32_t o = 0xFFFFFFFFu;
-        f3 c = mk3(0.f);
-        if(p < total)
-        {
-            o = 0u;                               // the lane whose list holds pair p: pref[o] <= p < pref[o + 1]
-#pragma unroll
-            for(int s = 16; s > 0; s >>= 1) if(w.pref[o + uint32_t(s)] <= p) o += uint32_t(s);
-            const uint32_t idx = w.list[p - w.pref[o]][o];
-            const float lenBits = reinterpret_cast<const float*>(g.sPosLen + idx)[3];
-            const float4 dv = g.sDirVm[idx], tv = g.sThrVcm[idx];
-            const float cp = g.sContProb[idx];
-            c = pairContribution(sc, ic, w.q, o, lenBits, dv, tv, cp);
-        }
-        // pairs come owner-major: runs of equal owners are summed with a segmented shuffle scan
-#pragma unroll
-        for(int d = 1; d < 32; d <<= 1)
-        {
-            const uint32_t ou = __shfl_up_sync(FULL_MASK, o, d);
-            const float cx = __shfl_up_sync(FULL_MASK, c.x, d), cy = __shfl_up_sync(FULL_MASK, c.y, d),
-                        cz = __shfl_up_sync(FULL_MASK, c.z, d);
-            if(lane >= uint32_t(d) && ou == o) { c.x += cx; c.y += cy; c.z += cz; }
-        }
-        const uint32_t on = __shfl_down_sync(FULL_MASK, o, 1);
-        if(p < total && (lane == 31u || on != o)) { w.acc[0][o] += c.x; w.acc[1][o] += c.y; w.acc[2][o] += c.z; }
-        __syncwarp();
-    }
-    cnt = 0u;
-    __syncwarp();
-}
-
-template<int PCAP>
-__global__ void __launch_bounds__(GM_WARPS * 32)
-k_mergeGroup(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
-             const __grid_constant__ QueryStore qs, const uint32_t *groupEnd, const uint32_t numGroups,
-             const __grid_constant__ GridBuffers g, float *accum, float *contribOut, int32_t *countsOut,
-             unsigned long long *counters)
-{
-    extern __shared__ __align__(128) unsigned char smemRaw[];
-    GroupWarpSmem<PCAP> &w = reinterpret_cast<GroupWarpSmem<PCAP>*>(smemRaw)[threadIdx.x >> 5];
-    const uint32_t lane = laneId();
-    const f3 bbMin = mk3(orderedToFloat(g.bboxBits[0]), orderedToFloat(g.bboxBits[1]), orderedToFloat(g.bboxBits[2]));
-    const f3 bbMax = mk3(orderedToFloat(g.bboxBits[3]), orderedToFloat(g.bboxBits[4]), orderedToFloat(g.bboxBits[5]));
-    const int shift = mortonShift(bbMin, bbMax, ic.invCellSize);
-    const int B = 1 << shift;
-    if(B > GM_MAXB)
-    {
-        // finer than this kernel's tables: the launcher's estimate (groupMergeApplicable) should have
-        // sent the iteration to k_mergeLane; say so instead of rendering nothing
-        if(counters && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(counters + CNT_OVERFLOW, 1ull);
-        return;
-    }
-    const int E = B + 2;                          // edge of the neighbourhood cube
-    const uint32_t numCells = uint32_t(E * E * E);
-    uint32_t nCand = 0u, nAcc = 0u;
-    uint32_t parity = 0u;
-    if(lane == 0u) { mbarInit(&w.bar, 1u); mbarInitFence(); }
-    __syncwarp();
-
-    // groups are dealt to warps 32 at a time: one coalesced read of the table finds the non-empty ones
-    const uint32_t warpGlobal = blockIdx.x * GM_WARPS + (threadIdx.x >> 5);
-    const uint32_t totalWarps = gridDim.x * GM_WARPS;
-    for(uint32_t k0 = warpGlobal * 32u; k0 < numGroups; k0 += totalWarps * 32u)
-    {
-        const uint32_t key = k0 + lane;
-        uint32_t myEnd = 0u, myStart = 0u;
-        if(key < numGroups) { myEnd = groupEnd[key]; myStart = key ? groupEnd[key - 1u] : 0u; }
-        uint32_t todo = __ballot_sync(FULL_MASK, myEnd > myStart);
-        while(todo)
-        {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            const uint32_t gKey = k0 + uint32_t(src);
-            const uint32_t gStart = __shfl_sync(FULL_MASK, myStart, src), gEnd = __shfl_sync(FULL_MASK, myEnd, src);
-            // cube origin (cell coordinates) minus one: the neighbourhood starts there
-            const int ox = int(unmorton7(gKey) << shift) - 1, oy = int(unmorton7(gKey >> 1) << shift) - 1,
-                      oz = int(unmorton7(gKey >> 2) << shift) - 1;
-
-            // ---- the buckets of the neighbourhood: hash, range, stage room ------------------------
-            uint32_t staged = 0u;                 // particles reserved in the stage so far (warp-uniform)
-            for(uint32_t c0 = 0u; c0 < numCells; c0 += 32u)
-            {
-                const uint32_t c = c0 + lane;
-                uint32_t start = 0u, count = 0u;
-                if(c < numCells)
-                {
-                    const int rx = int(c % uint32_t(E)), ry = int((c / uint32_t(E)) % uint32_t(E)), rz = int(c / uint32_t(E * E));
-                    const uint32_t h = refHash(ox + rx, oy + ry, oz + rz, ic);
-                    start = (h == 0u) ? 0u : g.cellCount[h - 1u];      // GetCellRange
-                    count = g.cellCount[h] - start;
-                }
-                // stage offsets: exclusive prefix of the counts that still fit
-                uint32_t inc = count;
-#pragma unroll
-                for(int o = 1; o < 32; o <<= 1)
-                {
-                    const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o);
-                    if(lane >= uint32_t(o)) inc += t;
-                }
-                // a bucket that does not fit the stage is walked from global memory; the offsets of the
-                // ones behind it in this round include its size, so they cannot fit either — the ones
-                // that fit always form a prefix of the round, and the next round continues behind them
-                const uint32_t off = staged + inc - count;
-                const bool ok = count > 0u && off + count <= uint32_t(PCAP);
-                if(c < numCells) { w.cellStart[c] = start; w.cellCount[c] = count; w.cellOff[c] = ok ? off : BS_GLOBAL; }
-                const uint32_t okMask = __ballot_sync(FULL_MASK, ok);
-                const uint32_t lastOk = okMask ? uint32_t(31 - __clz(okMask)) : 0u;
-                const uint32_t endOk = __shfl_sync(FULL_MASK, off + count, lastOk);
-                if(okMask) staged = endOk;
-            }
-            __syncwarp();
-            // bytes to expect = sum of the staged buckets
-            uint32_t bytes = 0u;
-            for(uint32_t c = lane; c < numCells; c += 32u) if(w.cellOff[c] != BS_GLOBAL) bytes += w.cellCount[c] * 16u;
-#pragma unroll
-            for(int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(FULL_MASK, bytes, o);
-            if(bytes > 0u)
-            {
-                if(lane == 0u) mbarArriveExpectTx(&w.bar, bytes);
-                __syncwarp();
-                for(uint32_t c = lane; c < numCells; c += 32u)
-                {
-                    const uint32_t off = w.cellOff[c];
-                    if(off != BS_GLOBAL) bulkLoad(&w.stage[off], g.sPosLen + w.cellStart[c], w.cellCount[c] * 16u, &w.bar);
-                }
-            }
-            bool stageReady = bytes == 0u;
-
-            // ---- the group's queries, 32 at a time ------------------------------------------------
-            for(uint32_t q0i = gStart; q0i < gEnd; q0i += 32u)
-            {
-                bool valid = q0i + lane < gEnd;
-                const uint32_t q = valid ? qs.order[q0i + lane] : 0u;
-                f3 qpos = mk3(0.f), scale = mk3(0.f);
-                uint32_t pixel = 0u, cand = 0u, accepted = 0u;
-                w.acc[0][lane] = 0.f; w.acc[1][lane] = 0.f; w.acc[2][lane] = 0.f;
-                uint32_t cells0 = 0u, cells1 = 0u;             // 8 x 8-bit positions in the neighbourhood cube
-                bool inside = false;
-                if(valid)
-                {
-                    const float4 q0 = qs.q0[q], q1 = qs.q1[q], q2 = qs.q2[q], q3 = qs.q3[q];
-                    qpos = xyz(q0); scale = xyz(q3) * ic.vmNormalization; pixel = __float_as_uint(q0.w);
-                    const uint32_t lenMat = __float_as_uint(q1.w);
-                    Bsdf bsdf;                     // BSDF<false>::Setup from normal / local direction / material
-                    bsdf.frame.setFromZ(xyz(q1));
-                    bsdf.localDirFix = xyz(q2);
-                    bsdf.diffProb = bsdf.phongProb = bsdf.reflProb = bsdf.refrProb = 0.f;
-                    bsdfFromLocal(sc, int32_t((lenMat >> 16) & 0xFFu), bsdf);
-                    parkQuery(w.q, lane, bsdf, q1.w, q2.w, q3.w);
-                    // HashGrid::Process: bbox early-out (the sort only lists queries that pass it), then
-                    // the 8 cells (src/hashgrid.hxx:116-155)
-                    inside = !(qpos.x - bbMin.x < 0.f || bbMax.x - qpos.x < 0.f || qpos.y - bbMin.y < 0.f ||
-                               bbMax.y - qpos.y < 0.f || qpos.z - bbMin.z < 0.f || bbMax.z - qpos.z < 0.f);
-                    if(inside)
-                    {
-                        const f3 cellPt = mk3(ic.invCellSize * (qpos.x - bbMin.x), ic.invCellSize * (qpos.y - bbMin.y),
-                                              ic.invCellSize * (qpos.z - bbMin.z));
-                        const f3 coordF = mk3(floorf(cellPt.x), floorf(cellPt.y), floorf(cellPt.z));
-                        const int px = int(coordF.x) - ox, py = int(coordF.y) - oy, pz = int(coordF.z) - oz;   // in the cube: 1 .. B
-                        const int pxo = px + ((cellPt.x - coordF.x) < 0.5f ? -1 : +1);
-                        const int pyo = py + ((cellPt.y - coordF.y) < 0.5f ? -1 : +1);
-                        const int pzo = pz + ((cellPt.z - coordF.z) < 0.5f ? -1 : +1);
-#pragma unroll
-                        for(int j = 0; j < 8; j++)
-                        {
-                            const uint32_t ci = uint32_t((((j & 1) ? pzo : pz) * E + ((j & 2) ? pyo : py)) * E + ((j & 4) ? pxo : px));
-                            if(j < 4) cells0 |= ci << (8 * j); else cells1 |= ci << (8 * (j - 4));
-                        }
-                    }
-                }
-                __syncwarp();
-                if(!stageReady) { mbarWait(&w.bar, parity); parity ^= 1u; stageReady = true; }
-
-                // ---- walk the 8 ranges in the reference's order -----------------------------------
-                uint32_t cnt = 0u, j = 0u;
-                const float4 *p = g.sPosLen, *pend = g.sPosLen;
-                uint32_t slot = 0u;                // sorted slot of *p
-                bool begun = false;
-                for(;;)
-                {
-                    bool exhausted = false;        // else: stopped at a full list
-                    for(;;)
-                    {
-                        while(p == pend)
-                        {
-                            if(begun) j++;
-                            begun = true;
-                            if(!inside || j >= 8u) { exhausted = true; break; }
-                            const uint32_t ci = ((j < 4u ? cells0 >> (8u * j) : cells1 >> (8u * (j - 4u))) & 0xFFu);
-                            const uint32_t n = w.cellCount[ci], off = w.cellOff[ci];
-                            slot = w.cellStart[ci];
-                            p = (off != BS_GLOBAL) ? &w.stage[off] : g.sPosLen + slot;     // generic pointer: either space
-                            pend = p + n;
-                            cand += n;
-                        }
-                        if(exhausted) break;
-                        if(cnt == uint32_t(GM_LCAP)) break;
-                        if(inRange(qpos, *p, ic.radiusSqr)) { w.list[cnt++][lane] = slot; accepted++; }
-                        p++; slot++;
-                    }
-                    if(!__any_sync(FULL_MASK, !exhausted)) break;
-                    flushGroupLists<PCAP>(sc, ic, g, w, cnt);
-                }
-                flushGroupLists<PCAP>(sc, ic, g, w, cnt);
-
-                if(valid)
-                {
-                    const f3 contrib = mk3(w.acc[0][lane], w.acc[1][lane], w.acc[2][lane]);
-                    nCand += cand; nAcc += accepted;
-                    if(contribOut)
-                    {
-                        contribOut[3ull * q + 0] = contrib.x; contribOut[3ull * q + 1] = contrib.y;
-                        contribOut[3ull * q + 2] = contrib.z;
-                    }
-                    if(countsOut) { countsOut[2ull * q] = int32_t(cand); countsOut[2ull * q + 1] = int32_t(accepted); }
-                    // color += cameraState.mThroughput * mVmNormalization * query.GetContrib()  (src/vertexcm.hxx:534)
-                    if(accum) addPixel(accum, pixel, scale * contrib);
-                }
-                __syncwarp();
-            }
-            // a group whose queries were all consumed before the copies landed cannot happen (the
-            // first pass waits), but an empty pass list can: drain the barrier before the stage is reused
-            if(!stageReady) { mbarWait(&w.bar, parity); parity ^= 1u; }
-            __syncwarp();
-        }
-    }
-    if(counters)
-    {
-        warpCount(counters + CNT_CANDIDATES, nCand);
-        warpCount(counters + CNT_ACCEPTED, nAcc);
-    }
-}
-
-// true if the group-staged kernel can run this grid: the group cube must not exceed GM_MAXB cells per
-// axis, i.e. the particle bbox must span fewer than 128 * GM_MAXB cells. The host only knows the
-// scene's bounding sphere; particles lie inside it.
-bool groupMergeApplicable(float sceneRadius, float radius)
-{
-    const double cells = 2.0 * double(sceneRadius) / (2.0 * double(radius)) + 2.0;
-    return cells < 128.0 * GM_MAXB;
-}
-
-template<int PCAP>
-static void launchGroupMergeT(const DevScene &sc, const IterConst &ic, const QueryStore &queries, const uint32_t *groupEnd,
-                              const GridBuffers &grid, float *accum, float *contribOut, int32_t *countsOut,
-                              unsigned long long *counters, cudaStream_t stream)
-{
-    const size_t smem = sizeof(GroupWarpSmem<PCAP>) * GM_WARPS;
-    static bool configured = false;
-    if(!configured)
-    {
-        cudaFuncSetAttribute(k_mergeGroup<PCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        configured = true;
-    }
-    int perSM = int((227u * 1024u) / (smem + 1024u));
-    if(perSM < 1) perSM = 1;
-    if(perSM > 8) perSM = 8;
-    const uint32_t numGroups = 1u << 21;
-    k_mergeGroup<PCAP><<<numSMs() * perSM, GM_WARPS * 32, smem, stream>>>(sc, ic, queries, groupEnd, numGroups, grid, accum,
-                                                                         contribOut, countsOut, counters);
-}
-
-void launchGroupMerge(const DevScene &sc, const IterConst &ic, const QueryStore &queries, const uint32_t *groupEnd,
-                      const GridBuffers &grid, float *accum, float *contribOut, int32_t *countsOut,
-                      unsigned long long *counters, cudaStream_t stream)
-{
-    // stage size by the group cube the grid will have (estimated like groupMergeApplicable): cubes of
-    // up to 2 cells per axis need a quarter of what 4-cell cubes need
-    const double cells = 2.0 * double(sc.sphereRadius) * double(ic.invCellSize) + 2.0;
-    if(cells < 256.0)
-        launchGroupMergeT<256>(sc, ic, queries, groupEnd, grid, accum, contribOut, countsOut, counters, stream);
-    else
-        launchGroupMergeT<512>(sc, ic, queries, groupEnd, grid, accum, contribOut, countsOut, counters, stream);
-}
-
 template<int PCAP, int LCAP, bool kBulk>
 static void launchBucketStagedT(const DevScene &sc, const IterConst &ic, const QueryStore &queries,
                                 const unsigned long long *queryCount, uint32_t hostQueryCount, const GridBuffers &grid,
@@ -1923,10 +1421,7 @@ void launchBucketStagedMerge(const DevScene &sc, const IterConst &ic, const Quer
 {
     const uint64_t maxQueries = queryCount ? queries.capacity : hostQueryCount;
     if(maxQueries == 0) return;
-    if(variant == 6)
-        k_mergeLaneV2<<<gridFor(maxQueries, SVCM_BLOCK, 4), SVCM_BLOCK, 0, stream>>>(
-            sc, ic, queries, queryCount, hostQueryCount, grid, accum, contribOut, countsOut, counters);
-    else if(variant == 3)
+    if(variant == 3)
         launchBucketStagedT<512, 16, false>(sc, ic, queries, queryCount, hostQueryCount, grid, accum, contribOut, countsOut,
                                             counters, maxQueries, stream);
     else if(variant == 4)

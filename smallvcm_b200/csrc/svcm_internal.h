@@ -288,12 +288,6 @@ void launchBucketStagedMerge(const DevScene &sc, const IterConst &ic, const Quer
                              const unsigned long long *queryCount, uint32_t hostQueryCount,
                              const GridBuffers &grid, float *accum, float *contribOut, int32_t *countsOut,
                              unsigned long long *counters, int variant, cudaStream_t stream);
-// merge over the bucket layout, one warp per GROUP of the spatially sorted queries (needs
-// launchQuerySort(spatial = 1); groupEnd = qs.cellEnd, the per-code ends of that sort)
-bool groupMergeApplicable(float sceneRadius, float radius);
-void launchGroupMerge(const DevScene &sc, const IterConst &ic, const QueryStore &queries, const uint32_t *groupEnd,
-                      const GridBuffers &grid, float *accum, float *contribOut, int32_t *countsOut,
-                      unsigned long long *counters, cudaStream_t stream);
 // per sorted slot: the reference hash bucket of that particle (T1 export of the cell layout)
 void launchCellRefKeys(const IterConst &ic, const GridBuffers &grid, uint32_t count, uint32_t *out, cudaStream_t stream);
 uint64_t hashMagicFor(uint32_t numCells);

@@ -157,7 +157,7 @@ def test_hashgrid_build_exact(scene_id, alg, w, layout, monkeypatch):
 
 
 @pytest.mark.parametrize("layout,variant", [("bucket", "1"), ("bucket", "2"), ("bucket", "3"), ("bucket", "4"),
-                                            ("bucket", "6"), ("bucket", "7"), ("cell", "0"), ("cell", "1"), ("cell", "3")])
+                                            ("cell", "0"), ("cell", "1"), ("cell", "3")])
 def test_hashgrid_edge_cases(layout, variant, monkeypatch):
     monkeypatch.setenv("SVCM_GRID_LAYOUT", layout)
     monkeypatch.setenv("SVCM_MERGE_VARIANT", variant)
@@ -188,7 +188,7 @@ def test_hashgrid_edge_cases(layout, variant, monkeypatch):
     assert close(gc, oc).all()
 
 
-@pytest.mark.parametrize("merge_kernel", ["1", "2", "3", "4", "5", "6", "7", "8", "32", "cell0", "cell1", "cell3"])
+@pytest.mark.parametrize("merge_kernel", ["1", "2", "3", "4", "5", "8", "32", "cell0", "cell1", "cell3"])
 @pytest.mark.parametrize("scene_id,alg,w,ppm", [(1, "vcm", 128, False), (3, "bpm", 128, False), (1, "ppm", 96, True),
                                                 (0, "vcm", 96, False)])
 def test_hashgrid_query_against_oracle(scene_id, alg, w, ppm, merge_kernel, monkeypatch):
@@ -227,8 +227,7 @@ def test_hashgrid_query_against_oracle(scene_id, alg, w, ppm, merge_kernel, monk
     assert np.abs(oc2).sum() < np.abs(oc).sum()
 
 
-@pytest.mark.parametrize("layout,variant", [("bucket", "1"), ("bucket", "2"), ("bucket", "3"), ("bucket", "6"), ("bucket", "7"),
-                                            ("cell", "0"), ("cell", "1")])
+@pytest.mark.parametrize("layout,variant", [("bucket", "1"), ("bucket", "2"), ("bucket", "3"), ("cell", "0"), ("cell", "1")])
 @pytest.mark.parametrize("num_cells", [2, 7, 64, 1000])
 def test_hashgrid_bucket_collisions(num_cells, layout, variant, monkeypatch):
     """With few buckets most queries see two or more of their 8 cells share a bucket; the reference
