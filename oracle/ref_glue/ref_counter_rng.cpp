@@ -9,7 +9,7 @@
 // Why: the reference draws from ONE sequential mt19937_64 stream across all paths
 // (src/vertexcm.hxx:1030), which no parallel renderer can reproduce; keyed per
 // (seed, iteration, phase, path) the same arithmetic becomes reproducible lane by lane
-// (SURVEY §8c). This library is what pins oracle/vcm_oracle.cpp (tests/test_oracle_pin.py):
+// (SURVEY §8c). This library is what pins oracle/vcm_oracle.cpp (tests/test_oracle.py):
 // both must agree BIT FOR BIT on images, light vertices, grids and merge contributions.
 #include <vector>
 #include <cmath>
@@ -28,7 +28,7 @@
 // Generator: Philox2x32-7 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"),
 // counter = (draw index, path index), key = seed + 0x85EBCA6B * (2*iteration + phase);
 // float = (top 24 bits | 1) / 2^24: strictly inside (0,1).  The same definition is restated in
-// oracle/vcm_oracle.cpp and in the product (smallvcm_b200/csrc/svcm_rng.cuh).
+// oracle/vcm_oracle.cpp and in the product (smallvcm_b200/csrc/svcm_device.cuh).
 // ---------------------------------------------------------------------------------------
 #define __RNG_HXX__
 class Rng

@@ -6,7 +6,7 @@
 // have no command-line switch in the reference (src/config.hxx:233-240).
 //
 // Uses: (1) pins oracle/vcm_oracle.cpp against the reference's own output
-// (tests/test_oracle_pin.py), (2) regenerates tests/golden/*, (3) is the
+// (tests/test_oracle.py), (2) regenerates tests/golden/*, (3) is the
 // `--impl reference` / cpu_baseline arm of bench.py (the reference's own OpenMP path,
 // src/smallvcm.cxx:52-151, timed with a wall clock because render() returns CPU time).
 //

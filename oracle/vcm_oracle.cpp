@@ -10,7 +10,7 @@
 // on the FLAT scene of include/svcm.h (the same bytes the CUDA library receives), not on
 // the reference's classes.
 //
-// Pinning (tests/test_oracle_pin.py, run where oracle/_ref exists):
+// Pinning (tests/test_oracle.py, run where oracle/_ref exists):
 //   * rngMode 0 (one sequential std::mt19937_64 stream, src/rng.hxx:41-86) reproduces the
 //     UNMODIFIED reference's framebuffer BIT FOR BIT (BASELINE.md §3 known answers:
 //     scene 1 vcm 512x512 TotalLuminance 69769.8, ...);
