@@ -337,6 +337,21 @@ def measure(sv, D, args, rank, world, device, tdev, sharded, want_e2e, clocks=No
                       "note": "svcm_run_iterations(1) + svcm_download_accum per iteration, as "
                               "VertexCMGpu::RunIteration does (the non-virtual GetFramebuffer forces the copy); the "
                               "inputs of a step are the iteration index and the kernel parameter blocks"}
+    if want_e2e:
+        # per-stage times of the stages ALONE: the default schedule runs the camera walk with the light
+        # pass, the grid build with the camera walk and the merge with vertex connection, so its stage
+        # times overlap and are inflated by sharing the SMs. The roofline is stated for the kernel alone.
+        r.set_option(abi.OPT_OVERLAP, 0)
+        rewind()
+        r.run_iterations(state["next"], 2); r.synchronize(); r.profile()
+        rewind()
+        n_iso = min(args.steps, 20)
+        for _ in range(n_iso):
+            r.run_iterations(state["next"], 1)
+            state["next"] += stride
+        r.synchronize()
+        out["prof_isolated"] = r.profile()
+        r.set_option(abi.OPT_OVERLAP, 7)
     r.close()
     return out
 
@@ -433,11 +448,12 @@ def run_gpu_arm(args):
         except Exception as exc:                      # a side record must never cost the headline
             config5 = {"error": str(exc)[:200]}
 
-    # roofline of the merge kernel (one launch per iteration)
+    # roofline of the merge stage (one launch set per iteration), timed ALONE (see measure())
     prof = head["prof"]
-    n = max(1, prof["timedIterations"])
-    nq, ncand, nacc = prof["mergeQueries"] / n, prof["mergeCandidates"] / n, prof["mergeAccepted"] / n
-    merge_ms = prof["msMerge"] / n
+    iso = head.get("prof_isolated") or prof
+    n = max(1, iso["timedIterations"])
+    nq, ncand, nacc = iso["mergeQueries"] / n, iso["mergeCandidates"] / n, iso["mergeAccepted"] / n
+    merge_ms = iso["msMerge"] / n
     peak, peak_kind = measured_peak_gbs()
     achieved = merge_algorithmic_bytes(nq, ncand, nacc) / (merge_ms * 1e-3) / 1e9 if merge_ms > 0 else 0.0
     # DRAM bytes of the merge kernel cannot be read without a profiler: the figure is the committed
@@ -454,26 +470,32 @@ def run_gpu_arm(args):
     stage = lambda p: {k: p[k] / max(1, p["timedIterations"]) for k in
                        ("msLightTrace", "msGather", "msGridBuild", "msCameraTrace", "msMerge", "msTotal")}
     st_ms = stage(prof)
-    build_bytes = prof["lightVertices"] / n * 136 + WIDTH * HEIGHT * 8
-    trace_s = (st_ms["msLightTrace"] + st_ms["msCameraTrace"]) * 1e-3
-    rays = {k: prof[k] / n for k in ("lightRays", "cameraRays", "shadowRays")}
+    iso_ms = stage(iso)
+    build_bytes = iso["lightVertices"] / n * 136 + WIDTH * HEIGHT * 8
+    trace_s = (iso_ms["msLightTrace"] + iso_ms["msCameraTrace"]) * 1e-3
+    rays = {k: prof[k] / max(1, prof["timedIterations"]) for k in ("lightRays", "cameraRays", "shadowRays")}
     trace = {"closest_hit_rays_per_iteration": rays["lightRays"] + rays["cameraRays"],
              "shadow_rays_per_iteration": rays["shadowRays"],
              "grays_per_s": (rays["lightRays"] + rays["cameraRays"] + rays["shadowRays"]) / trace_s / 1e9 if trace_s > 0 else None,
              "ms_light_plus_camera": trace_s * 1e3,
+             "ms_critical_path_in_schedule": st_ms["msLightTrace"] + st_ms["msCameraTrace"],
              "note": "light + camera passes (closest-hit rays of both walks, deferred any-hit segments, vertex "
-                     "connection): instruction-bound on 22 primitives in the constant bank, reported as rays/s, not "
-                     "against the HBM roofline (SURVEY 8d)"}
+                     "connection) timed one after the other; instruction-bound on 22 primitives in the constant bank, "
+                     "reported as rays/s, not against the HBM roofline (SURVEY 8d)"}
     roofline = {"kernel": "merge stage: query sort + merge kernel (HashGrid::Process + RangeQuery::Process)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_source,
                 "peak_source": peak_kind, "ms_per_launch": merge_ms, "queries": nq, "candidates": ncand,
                 "accepted": nacc, "algorithmic_bytes_per_launch": merge_algorithmic_bytes(nq, ncand, nacc),
+                "timed": "alone: %d iterations of the same window with SVCM_OPT_OVERLAP = 0 (no other kernel on the "
+                         "device); in the default schedule the stage runs concurrently with vertex connection" % n,
                 "stage_ms_per_iteration": st_ms,
-                "grid_build": {"algorithmic_bytes": build_bytes, "ms": st_ms["msGridBuild"],
-                               "achieved": build_bytes / (st_ms["msGridBuild"] * 1e-3) / 1e9 if st_ms["msGridBuild"] > 0 else None,
-                               "frac": build_bytes / (st_ms["msGridBuild"] * 1e-3) / 1e9 / peak if st_ms["msGridBuild"] > 0 else None,
-                               "formula": "N_v*136 + cells*8 (SURVEY 8d)"}}
+                "stage_ms_per_iteration_alone": iso_ms,
+                "grid_build": {"algorithmic_bytes": build_bytes, "ms": iso_ms["msGridBuild"],
+                               "ms_in_schedule": st_ms["msGridBuild"],
+                               "achieved": build_bytes / (iso_ms["msGridBuild"] * 1e-3) / 1e9 if iso_ms["msGridBuild"] > 0 else None,
+                               "frac": build_bytes / (iso_ms["msGridBuild"] * 1e-3) / 1e9 / peak if iso_ms["msGridBuild"] > 0 else None,
+                               "formula": "N_v*136 + cells*8 (SURVEY 8d); timed alone like the merge"}}
 
     # CPU baseline beside it (rank 0, N = 1 only)
     cpu = None

@@ -17,7 +17,7 @@ ALG_LIGHT_TRACE, ALG_PPM, ALG_BPM, ALG_BPT, ALG_VCM, ALG_PATH_TRACE, ALG_EYE_LIG
 ALGORITHMS = {"lt": ALG_LIGHT_TRACE, "ppm": ALG_PPM, "bpm": ALG_BPM, "bpt": ALG_BPT, "vcm": ALG_VCM,
               "pt": ALG_PATH_TRACE, "el": ALG_EYE_LIGHT}
 OPT_PROFILE, OPT_MERGE_GROUP, OPT_COUNTERS = 1, 2, 3
-OPT_GRID_LAYOUT, OPT_MERGE_VARIANT, OPT_REF_CANDIDATES = 4, 5, 6
+OPT_GRID_LAYOUT, OPT_MERGE_VARIANT, OPT_REF_CANDIDATES, OPT_OVERLAP = 4, 5, 6, 7
 GRID_BUCKET, GRID_CELL = 0, 1
 COMM_ID_BYTES = 128
 

@@ -118,6 +118,7 @@ struct svcm_renderer
     unsigned long long *hostCounters; // pinned ring [SVCM_PROFILE_RING][CNT_WORDS]
     int       ringLaunches[SVCM_PROFILE_RING];
     bool      ringTimed[SVCM_PROFILE_RING];
+    bool      ringGridSerial[SVCM_PROFILE_RING];   // the grid build ran on the main stream, between light and camera pass
     long long ringHead;             // iterations recorded so far
     long long ringTail;             // first iteration not yet returned by svcm_get_profile
     float    *accum;
@@ -147,6 +148,8 @@ struct svcm_renderer
     cudaStream_t cameraStream;
     cudaEvent_t  evIterStart, evCameraDone;
     bool overlapPasses;             // SVCM_NO_PASS_OVERLAP=1 serialises them again (A/B)
+    bool overlapMerge;              // SVCM_NO_MERGE_OVERLAP=1: merge on the main stream behind the connection kernels
+    cudaEvent_t evMergeDone;
     bool overlapGrid;               // SVCM_NO_GRID_OVERLAP=1: grid build on the main stream (isolated stage times)
     bool spatialQueries;            // SVCM_QUERY_ORDER=bucket restores round 1's order (A/B)
     bool legacyBuild;               // SVCM_LEGACY_BUILD=1: round 1's three-kernel scan + direct record scatter (A/B)
@@ -159,9 +162,10 @@ struct svcm_renderer
     bool refCandidates;             // SVCM_OPT_REF_CANDIDATES
     ScanGen scanGenGrid, scanGenQuery;
     bool profile;
-    cudaEvent_t (*ev)[9];          // [SVCM_PROFILE_RING][9], created when profiling is enabled:
+    cudaEvent_t (*ev)[11];         // [SVCM_PROFILE_RING][11], created when profiling is enabled:
                                    // 0 start, 1 light pass done, 4 camera pass done, 5 merge done (main
-                                   // stream); 6 grid stream starts, 7 gather done, 8 build done
+                                   // stream); 6 grid stream starts, 7 gather done, 8 build done; 9 / 10 merge
+                                   // stage starts / ends (on whichever stream it runs)
     cudaEvent_t userEv[SVCM_NUM_USER_EVENTS];
     SvcmStats stats;
     bool statsPending;
@@ -667,6 +671,40 @@ int enqueueCameraBounces(svcm_renderer *r, const IterConst &ic, const TraceArgs 
     return int(camBounces);
 }
 
+// The deferred merging of all recorded camera vertices: query sort (bbox early-out, spatial order,
+// count) + merge kernel, on stream `ms`, which must already be ordered behind the camera walk and
+// the grid build. Returns the number of kernels launched.
+int enqueueMerge(svcm_renderer *r, const IterConst &ic, cudaStream_t ms)
+{
+    int launches = 0;
+    QueryStore qs = r->queries;
+    // the queries take a cell-coherent order; the keying kernel applies HashGrid::Process' bbox
+    // early-out and counts the queries
+    const unsigned long long *count = r->counters + CNT_QUERIES;
+    if(r->cellLayout)
+    {
+        launches += launchCellQuerySort(ic, r->queries, r->counters + CNT_CAM_VERTS, 0, r->grid, r->qsort,
+                                        r->scanGenQuery, r->counters, ms);
+        qs.order = r->qsort.order;
+        GridBuffers grid = r->grid;
+        if(!r->refCandidates) grid.refCount = NULL;
+        launchCellMerge(r->scene, ic, qs, count, 0, grid, r->accum, NULL, NULL, r->counters, r->mergeVariant, ms);
+    }
+    else
+    {
+        launches += launchQuerySort(ic, r->queries, r->counters + CNT_CAM_VERTS, r->grid.bboxBits, r->qsort,
+                                    r->counters, r->legacyBuild ? NULL : &r->scanGenQuery, r->spatialQueries, ms);
+        qs.order = r->qsort.order;
+        if(r->mergeGroup >= 2 && r->mergeGroup <= 5)
+            launchBucketStagedMerge(r->scene, ic, qs, count, 0, r->grid, r->accum, NULL, NULL, r->counters,
+                                    r->mergeGroup, ms);
+        else
+            launchMerge(r->scene, ic, qs, count, 0, r->grid, r->accum, NULL, NULL,
+                        r->counters, r->mergeGroup, ms);
+    }
+    return launches + 1;
+}
+
 // One iteration: the kernel schedule that replaces the two serial per-pixel loops
 static double hostNowMs()
 {
@@ -726,7 +764,7 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
             launchShadow(r->scene, ic, a, 1, st);      // next-event visibility, then splat
             launches++;
         }
-        if(timed) { cudaEventRecord(ev[4], st); cudaEventRecord(ev[5], st); }
+        if(timed) { cudaEventRecord(ev[4], st); cudaEventRecord(ev[9], st); cudaEventRecord(ev[10], st); cudaEventRecord(ev[5], st); }
         SVCM_CUDA(r, cudaMemcpyAsync(r->hostCounters + size_t(slot) * CNT_WORDS, r->counters,
                                      sizeof(unsigned long long) * CNT_WORDS, cudaMemcpyDeviceToHost, st));
         SVCM_CUDA(r, cudaGetLastError());
@@ -800,6 +838,18 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
         SVCM_CUDA(r, cudaEventRecord(r->evGridDone, sg));
     }
     else if(timed) { cudaEventRecord(ev[6], st); cudaEventRecord(ev[7], st); cudaEventRecord(ev[8], st); }
+    // the merge goes behind the camera walk on its stream as soon as the grid is enqueued
+    bool mergeForked = false;
+    if(r->useVM && !r->lightTraceOnly && r->overlapPasses && r->overlapMerge)
+    {
+        cudaStream_t cs = r->cameraStream;
+        SVCM_CUDA(r, cudaStreamWaitEvent(cs, r->evGridDone, 0));
+        if(timed) cudaEventRecord(ev[9], cs);
+        launches += enqueueMerge(r, ic, cs);
+        if(timed) cudaEventRecord(ev[10], cs);
+        SVCM_CUDA(r, cudaEventRecord(r->evMergeDone, cs));
+        mergeForked = true;
+    }
     th[3] = hostNowMs();
 
     // ---- camera sub-paths (src/vertexcm.hxx:415-545) ---------------------------------------
@@ -824,36 +874,23 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     th[4] = hostNowMs();
 
     // ---- deferred merging of all queued camera vertices ------------------------------------
-    if(r->useVM) SVCM_CUDA(r, cudaStreamWaitEvent(st, r->evGridDone, 0));
+    // Merging reads the camera vertices and the grid and adds to the image with atomics: it depends on
+    // neither vertex connection nor its visibility tests. With the passes overlapped it was enqueued on
+    // the camera stream right behind the walk (`mergeForked` below) and runs concurrently with the
+    // connection kernels of this stream; here the two meet again.
     if(r->useVM && !r->lightTraceOnly)
     {
-        QueryStore qs = r->queries;
-        // the queries take the particles' order (neighbouring lanes then share cells); the keying
-        // kernel applies HashGrid::Process' bbox early-out and counts the queries
-        const unsigned long long *count = r->counters + CNT_QUERIES;
-        if(r->cellLayout)
-        {
-            launches += launchCellQuerySort(ic, r->queries, r->counters + CNT_CAM_VERTS, 0, r->grid, r->qsort,
-                                            r->scanGenQuery, r->counters, st);
-            qs.order = r->qsort.order;
-            GridBuffers grid = r->grid;
-            if(!r->refCandidates) grid.refCount = NULL;
-            launchCellMerge(r->scene, ic, qs, count, 0, grid, r->accum, NULL, NULL, r->counters, r->mergeVariant, st);
-        }
+        if(mergeForked) SVCM_CUDA(r, cudaStreamWaitEvent(st, r->evMergeDone, 0));
         else
         {
-            launches += launchQuerySort(ic, r->queries, r->counters + CNT_CAM_VERTS, r->grid.bboxBits, r->qsort,
-                                        r->counters, r->legacyBuild ? NULL : &r->scanGenQuery, r->spatialQueries, st);
-            qs.order = r->qsort.order;
-            if(r->mergeGroup >= 2 && r->mergeGroup <= 5)
-                launchBucketStagedMerge(r->scene, ic, qs, count, 0, r->grid, r->accum, NULL, NULL, r->counters,
-                                        r->mergeGroup, st);
-            else
-                launchMerge(r->scene, ic, qs, count, 0, r->grid, r->accum, NULL, NULL,
-                            r->counters, r->mergeGroup, st);
+            SVCM_CUDA(r, cudaStreamWaitEvent(st, r->evGridDone, 0));
+            if(timed) cudaEventRecord(ev[9], st);
+            launches += enqueueMerge(r, ic, st);
+            if(timed) cudaEventRecord(ev[10], st);
         }
-        launches++;
     }
+    else if(r->useVM) SVCM_CUDA(r, cudaStreamWaitEvent(st, r->evGridDone, 0));
+    if(timed && !(r->useVM && !r->lightTraceOnly)) { cudaEventRecord(ev[9], st); cudaEventRecord(ev[10], st); }
     if(timed) cudaEventRecord(ev[5], st);
 
     SVCM_CUDA(r, cudaMemcpyAsync(r->hostCounters + size_t(slot) * CNT_WORDS, r->counters,
@@ -865,6 +902,7 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
                 th[1] - th[0], th[2] - th[1], th[3] - th[2], th[4] - th[3], th[5] - th[4]);
     r->ringLaunches[slot] = launches;
     r->ringTimed[slot] = timed;
+    r->ringGridSerial[slot] = r->useVM && !r->overlapGrid;
     r->ringHead++;
     if(r->ringHead - r->ringTail > SVCM_PROFILE_RING) r->ringTail = r->ringHead - SVCM_PROFILE_RING;
     r->stats.radius = ic.radius;
@@ -908,7 +946,8 @@ int finishStats(svcm_renderer *r)
         cudaEventElapsedTime(&s.msGather, ev[6], ev[7]);
         cudaEventElapsedTime(&s.msGridBuild, ev[7], ev[8]);
         cudaEventElapsedTime(&s.msCameraTrace, ev[1], ev[4]);
-        cudaEventElapsedTime(&s.msMerge, ev[4], ev[5]);
+        if(r->ringGridSerial[slot]) { float g = 0.f; cudaEventElapsedTime(&g, ev[6], ev[8]); s.msCameraTrace -= g; }
+        cudaEventElapsedTime(&s.msMerge, ev[9], ev[10]);
         cudaEventElapsedTime(&s.msTotal, ev[0], ev[5]);
     }
     r->statsPending = false;
@@ -962,10 +1001,11 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     r->devCounts64 = NULL; r->hostCounts64 = NULL;
     r->accumReduced = NULL; r->reducedValid = false;
     r->gridStream = NULL; r->evLightDone = NULL; r->evGridDone = NULL;
-    r->cameraStream = NULL; r->evIterStart = NULL; r->evCameraDone = NULL;
+    r->cameraStream = NULL; r->evIterStart = NULL; r->evCameraDone = NULL; r->evMergeDone = NULL;
     r->overlapPasses = !(getenv("SVCM_NO_PASS_OVERLAP") && atoi(getenv("SVCM_NO_PASS_OVERLAP")) != 0);
     r->legacyBuild = getenv("SVCM_LEGACY_BUILD") && atoi(getenv("SVCM_LEGACY_BUILD")) != 0;
     r->overlapGrid = !(getenv("SVCM_NO_GRID_OVERLAP") && atoi(getenv("SVCM_NO_GRID_OVERLAP")) != 0);
+    r->overlapMerge = !(getenv("SVCM_NO_MERGE_OVERLAP") && atoi(getenv("SVCM_NO_MERGE_OVERLAP")) != 0);
     r->spatialQueries = !(getenv("SVCM_QUERY_ORDER") && strcmp(getenv("SVCM_QUERY_ORDER"), "bucket") == 0);
     r->iterationsDone = 0; r->profile = false;
     r->mergeGroup = getenv("SVCM_MERGE_KERNEL") ? atoi(getenv("SVCM_MERGE_KERNEL")) : 1;
@@ -981,6 +1021,7 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     }
     r->ev = NULL; r->ringHead = r->ringTail = 0;
     memset(r->ringLaunches, 0, sizeof(r->ringLaunches)); memset(r->ringTimed, 0, sizeof(r->ringTimed));
+    memset(r->ringGridSerial, 0, sizeof(r->ringGridSerial));
     memset(r->userEv, 0, sizeof(r->userEv)); memset(&r->stats, 0, sizeof(r->stats));
     r->statsPending = false; r->lastLaunches = 0;
     r->params = *params;
@@ -1046,6 +1087,7 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     SVCM_TRY(cudaStreamCreateWithFlags(&r->cameraStream, cudaStreamNonBlocking));
     SVCM_TRY(cudaEventCreateWithFlags(&r->evIterStart, cudaEventDisableTiming));
     SVCM_TRY(cudaEventCreateWithFlags(&r->evCameraDone, cudaEventDisableTiming));
+    SVCM_TRY(cudaEventCreateWithFlags(&r->evMergeDone, cudaEventDisableTiming));
     SVCM_TRY(cudaMallocHost((void**)&r->hostCounters, sizeof(unsigned long long) * CNT_WORDS * SVCM_PROFILE_RING));
     SVCM_TRY(cudaMallocHost((void**)&r->hostCounts64, sizeof(unsigned long long) * 8 * SVCM_PROFILE_RING));
     memset(r->hostCounters, 0, sizeof(unsigned long long) * CNT_WORDS * SVCM_PROFILE_RING);
@@ -1074,6 +1116,7 @@ void svcm_destroy(svcm_renderer *r)
     if(r->cameraStream) { cudaStreamSynchronize(r->cameraStream); cudaStreamDestroy(r->cameraStream); }
     if(r->evIterStart) cudaEventDestroy(r->evIterStart);
     if(r->evCameraDone) cudaEventDestroy(r->evCameraDone);
+    if(r->evMergeDone) cudaEventDestroy(r->evMergeDone);
     devFree(r->queueCountsLight); devFree(r->queueCountsCamera);
     devFree(r->shadow.r0); devFree(r->shadow.r1); devFree(r->shadow.r2); devFree(r->shadow.counts);
     freeVerts(r); freeQueries(r); freeGridSorted(r);
@@ -1092,7 +1135,7 @@ void svcm_destroy(svcm_renderer *r)
     if(r->hostCounts64) cudaFreeHost(r->hostCounts64);
     if(r->ev)
     {
-        for(int k = 0; k < SVCM_PROFILE_RING; k++) for(int i = 0; i < 9; i++) if(r->ev[k][i]) cudaEventDestroy(r->ev[k][i]);
+        for(int k = 0; k < SVCM_PROFILE_RING; k++) for(int i = 0; i < 11; i++) if(r->ev[k][i]) cudaEventDestroy(r->ev[k][i]);
         delete[] r->ev;
     }
     for(int i = 0; i < SVCM_NUM_USER_EVENTS; i++) if(r->userEv[i]) cudaEventDestroy(r->userEv[i]);
@@ -1109,9 +1152,9 @@ int svcm_set_option(svcm_renderer *r, int32_t option, int64_t value)
         if(value != 0 && !r->ev)
         {
             SVCM_CUDA(r, cudaSetDevice(r->device));
-            r->ev = new cudaEvent_t[SVCM_PROFILE_RING][9];
-            memset(r->ev, 0, sizeof(cudaEvent_t) * 9 * SVCM_PROFILE_RING);
-            for(int k = 0; k < SVCM_PROFILE_RING; k++) for(int i = 0; i < 9; i++) SVCM_CUDA(r, cudaEventCreate(&r->ev[k][i]));
+            r->ev = new cudaEvent_t[SVCM_PROFILE_RING][11];
+            memset(r->ev, 0, sizeof(cudaEvent_t) * 11 * SVCM_PROFILE_RING);
+            for(int k = 0; k < SVCM_PROFILE_RING; k++) for(int i = 0; i < 11; i++) SVCM_CUDA(r, cudaEventCreate(&r->ev[k][i]));
         }
         r->profile = value != 0;
         return SVCM_OK;
@@ -1128,6 +1171,10 @@ int svcm_set_option(svcm_renderer *r, int32_t option, int64_t value)
         r->mergeVariant = int(value); return SVCM_OK;
     case SVCM_OPT_REF_CANDIDATES:
         r->refCandidates = value != 0; return SVCM_OK;
+    case SVCM_OPT_OVERLAP:
+        if(value < 0 || value > 7) return fail(r, SVCM_E_INVALID, "overlap mask must be 0..7");
+        r->overlapPasses = (value & 1) != 0; r->overlapGrid = (value & 2) != 0; r->overlapMerge = (value & 4) != 0;
+        return SVCM_OK;
     default: return fail(r, SVCM_E_INVALID, "unknown option %d", option);
     }
 }
@@ -1295,7 +1342,8 @@ int svcm_get_profile(svcm_renderer *r, SvcmProfile *out)
             float ms[6] = { 0, 0, 0, 0, 0, 0 };
             cudaEventElapsedTime(&ms[0], ev[0], ev[1]); cudaEventElapsedTime(&ms[1], ev[6], ev[7]);
             cudaEventElapsedTime(&ms[2], ev[7], ev[8]); cudaEventElapsedTime(&ms[3], ev[1], ev[4]);
-            cudaEventElapsedTime(&ms[4], ev[4], ev[5]); cudaEventElapsedTime(&ms[5], ev[0], ev[5]);
+            if(r->ringGridSerial[slot]) { float g = 0.f; cudaEventElapsedTime(&g, ev[6], ev[8]); ms[3] -= g; }
+            cudaEventElapsedTime(&ms[4], ev[9], ev[10]); cudaEventElapsedTime(&ms[5], ev[0], ev[5]);
             out->msLightTrace += ms[0]; out->msGather += ms[1]; out->msGridBuild += ms[2];
             out->msCameraTrace += ms[3]; out->msMerge += ms[4]; out->msTotal += ms[5];
             out->timedIterations++;
