@@ -126,7 +126,7 @@ struct svcm_renderer
     GridBuffers grid;
     uint32_t  gridCells, gridCapacity;
     int32_t  *bboxInit;
-    // multi-rank: ONE buffer of worldSize blocks [GatherHeader | 64-byte merge records];
+    // multi-rank: ONE buffer of worldSize blocks [GatherHeader | posLen | thrVcm | dirVm | contProb];
     // block `rank` is where the local light pass writes, ncclAllGather fills the others in place
     ncclComm_t comm;
     unsigned char *gatherBuf;
@@ -318,22 +318,25 @@ void freeVerts(svcm_renderer *r)
     if(r->gatherBuf)
     {
         // the merge streams live inside the gather buffer
-        r->verts.rec = NULL;
+        r->verts.posLen = r->verts.thrVcm = r->verts.dirVm = NULL; r->verts.contProb = NULL;
         freeGather(r);
     }
-    devFree(r->verts.rec);
+    devFree(r->verts.posLen); devFree(r->verts.thrVcm); devFree(r->verts.dirVm); devFree(r->verts.contProb);
     devFree(r->verts.conn);
     r->verts.capacity = 0; r->vertSlots = 0; r->verts.connSlots = 0;
 }
 
 // bytes of one all-gather block holding `slots` records, and the stream offsets inside it
-size_t gatherBlockBytes(uint32_t slots) { return sizeof(GatherHeader) + size_t(slots) * 64u; }
+size_t gatherBlockBytes(uint32_t slots) { return (sizeof(GatherHeader) + size_t(slots) * 52u + 255u) & ~size_t(255u); }
 
 // points the local merge streams at block `rank` of the gather buffer laid out for `stride` slots
 void pointGatherStreams(svcm_renderer *r, uint32_t stride)
 {
     unsigned char *block = r->gatherBuf + size_t(r->params.rank) * gatherBlockBytes(stride);
-    r->verts.rec      = reinterpret_cast<float4*>(block + sizeof(GatherHeader));
+    r->verts.posLen   = reinterpret_cast<float4*>(block + sizeof(GatherHeader));
+    r->verts.thrVcm   = r->verts.posLen + stride;
+    r->verts.dirVm    = r->verts.thrVcm + stride;
+    r->verts.contProb = reinterpret_cast<float*>(r->verts.dirVm + stride);
     r->verts.capacity = stride;
     r->gatherStride   = stride;
 }
@@ -446,7 +449,7 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
         }
         // bytes per stored vertex: merge record 52, plus per rank the gathered copy (sharded runs)
         // and the cell-sorted copy with its key
-        const uint64_t perVertex = 64u + (r->useVM ? (ws > 1u ? 124u * ws : 60u) : 0u) + 6u;
+        const uint64_t perVertex = 52u + (r->useVM ? (ws > 1u ? 112u * ws : 60u) : 0u) + 6u;
         const uint64_t budget = uint64_t(double(freeB) * 0.45);
         uint64_t cap = std::min<uint64_t>(worst, budget / perVertex);
         cap = std::min<uint64_t>(cap, 0xFFFFFF00u / ws);
@@ -463,7 +466,10 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
         }
         else
         {
-            if(r->useVM) if((rc = devAlloc(r, &r->verts.rec, cap * 4u))) return rc;
+            if((rc = devAlloc(r, &r->verts.posLen, cap))) return rc;
+            if((rc = devAlloc(r, &r->verts.thrVcm, cap))) return rc;
+            if((rc = devAlloc(r, &r->verts.dirVm, cap))) return rc;
+            if((rc = devAlloc(r, &r->verts.contProb, cap))) return rc;
         }
         r->verts.capacity = uint32_t(cap);
         r->vertSlots = lightBounces;
@@ -609,7 +615,8 @@ int gatherLightVertices(svcm_renderer *r, MergeSet &set, cudaStream_t st, int sl
     const size_t blockBytes = gatherBlockBytes(stride);
 
     MergeSet local; memset(&local, 0, sizeof(local));
-    local.rec = r->verts.rec;
+    local.posLen = r->verts.posLen; local.thrVcm = r->verts.thrVcm; local.dirVm = r->verts.dirVm;
+    local.contProb = r->verts.contProb;
     local.singleCount = r->counters + CNT_LIGHT_VERTS;
     local.capacity = stride; local.segStride = stride; local.numSegs = 1;
     unsigned char *mine = r->gatherBuf + size_t(r->params.rank) * blockBytes;
@@ -624,7 +631,10 @@ int gatherLightVertices(svcm_renderer *r, MergeSet &set, cudaStream_t st, int sl
                                  cudaMemcpyDeviceToHost, st));
 
     memset(&set, 0, sizeof(set));
-    set.rec = reinterpret_cast<const float4*>(r->gatherBuf + sizeof(GatherHeader));
+    set.posLen   = reinterpret_cast<const float4*>(r->gatherBuf + sizeof(GatherHeader));
+    set.thrVcm   = set.posLen + stride;
+    set.dirVm    = set.thrVcm + stride;
+    set.contProb = reinterpret_cast<const float*>(set.dirVm + stride);
     set.singleCount = NULL;
     set.capacity = stride * uint32_t(ws);
     set.segStride = stride;
@@ -826,7 +836,8 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
         else
         {
             memset(&set, 0, sizeof(set));
-            set.rec = r->verts.rec;
+            set.posLen = r->verts.posLen; set.thrVcm = r->verts.thrVcm; set.dirVm = r->verts.dirVm;
+            set.contProb = r->verts.contProb;
             set.singleCount = r->counters + CNT_LIGHT_VERTS;
             set.capacity = r->verts.capacity;
             set.segStride = r->verts.capacity; set.numSegs = 1;
@@ -1476,7 +1487,7 @@ struct svcm_hashgrid
     int64_t count;
     uint32_t numCells;
     float radius;
-    float4 *rec;                    // unsorted merge records (VertexStore::rec layout)
+    float4 *posLen, *thrVcm, *dirVm; float *contProb;
     unsigned long long *countDev;
     GridBuffers grid;
     int32_t *bboxInit;
@@ -1537,7 +1548,7 @@ int svcm_hashgrid_build(const SvcmMergeVertex *vertices, int64_t count, float ra
 
     svcm_hashgrid *g = new svcm_hashgrid;
     g->device = device; g->stream = NULL; g->count = count; g->numCells = uint32_t(numCells); g->radius = radius;
-    g->rec = NULL; g->countDev = NULL; g->bboxInit = NULL;
+    g->posLen = g->thrVcm = g->dirVm = NULL; g->contProb = NULL; g->countDev = NULL; g->bboxInit = NULL;
     memset(&g->grid, 0, sizeof(g->grid));
     {
         const char *layout = getenv("SVCM_GRID_LAYOUT");
@@ -1550,7 +1561,7 @@ int svcm_hashgrid_build(const SvcmMergeVertex *vertices, int64_t count, float ra
     const size_t n = size_t(std::max<int64_t>(count, 1));
 #define G_ALLOC(p, cnt) if(e == cudaSuccess) e = cudaMalloc((void**)&(p), sizeof(*(p)) * (cnt))
     G_ALLOC(staging, n);
-    G_ALLOC(g->rec, n * 4);
+    G_ALLOC(g->posLen, n); G_ALLOC(g->thrVcm, n); G_ALLOC(g->dirVm, n); G_ALLOC(g->contProb, n);
     G_ALLOC(g->countDev, 1); G_ALLOC(g->bboxInit, 6);
     G_ALLOC(g->grid.cellKey, n); G_ALLOC(g->grid.cellCount, size_t(numCells) + 1);
     G_ALLOC(g->grid.blockSums, (size_t(numCells) + 1) / 2048 + 2); G_ALLOC(g->grid.bboxBits, 6);
@@ -1569,12 +1580,12 @@ int svcm_hashgrid_build(const SvcmMergeVertex *vertices, int64_t count, float ra
     if(e == cudaSuccess && count) e = cudaMemcpy(staging, vertices, sizeof(SvcmMergeVertex) * size_t(count), cudaMemcpyHostToDevice);
     if(e == cudaSuccess)
     {
-        launchPackMergeVertices(staging, count, g->rec, 0);
+        launchPackMergeVertices(staging, count, g->posLen, g->thrVcm, g->dirVm, g->contProb, 0);
         IterConst ic; memset(&ic, 0, sizeof(ic));
         ic.radius = radius; ic.radiusSqr = radius * radius; ic.invCellSize = 1.f / (radius * 2.f);
         ic.numCells = uint32_t(numCells); ic.hashMagic = hashMagicFor(ic.numCells);
         MergeSet set; memset(&set, 0, sizeof(set));
-        set.rec = g->rec;
+        set.posLen = g->posLen; set.thrVcm = g->thrVcm; set.dirVm = g->dirVm; set.contProb = g->contProb;
         set.singleCount = g->countDev; set.capacity = uint32_t(count); set.segStride = uint32_t(count); set.numSegs = 1;
         if(g->cellLayout)
         {
@@ -1608,7 +1619,7 @@ void svcm_hashgrid_destroy(svcm_hashgrid *g)
 {
     if(!g) return;
     cudaSetDevice(g->device);
-    cudaFree(g->rec); cudaFree(g->countDev);
+    cudaFree(g->posLen); cudaFree(g->thrVcm); cudaFree(g->dirVm); cudaFree(g->contProb); cudaFree(g->countDev);
     cudaFree(g->bboxInit); cudaFree(g->grid.cellKey); cudaFree(g->grid.cellCount); cudaFree(g->grid.blockSums);
     cudaFree(g->grid.bboxBits); cudaFree(g->grid.sPosLen); cudaFree(g->grid.sThrVcm); cudaFree(g->grid.sDirVm);
     cudaFree(g->grid.sContProb); cudaFree(g->grid.sIndex);

@@ -97,7 +97,7 @@ k_cellKeys(const __grid_constant__ MergeSet set, const __grid_constant__ IterCon
         const MergeSlot ms = mergeSetSlot(set, i);
         if(mergeSetValid(set, ms))
         {
-            const float4 p = mergeSetRecord(set, ms)[0];
+            const float4 p = *mergeSetStream(set, set.posLen, ms);
             const int32_t cx = cellCoord(p.x, bbMin.x, ic.invCellSize), cy = cellCoord(p.y, bbMin.y, ic.invCellSize),
                           cz = cellCoord(p.z, bbMin.z, ic.invCellSize);
             k = cellKey(d, storageX(cx, d.m), foldCoord(cy, d.fy), foldCoord(cz, d.fz));
@@ -349,13 +349,11 @@ k_cellGather(const __grid_constant__ MergeSet set, const __grid_constant__ GridB
     const uint32_t total = totalPtr ? *totalPtr : g.cellEnd[g.dims->numKeys];
     for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += gridDim.x * blockDim.x)
     {
-        // one 64-byte record in (two full sectors), four dense streams out
-        const float4 *rec = mergeSetRecord(set, mergeSetSlot(set, uint32_t(g.sIndex[slot])));
-        const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
-        g.sPosLen[slot]   = r0;
-        g.sThrVcm[slot]   = r1;
-        g.sDirVm[slot]    = r2;
-        g.sContProb[slot] = r3.x;
+        const MergeSlot ms = mergeSetSlot(set, uint32_t(g.sIndex[slot]));
+        g.sPosLen[slot]   = *mergeSetStream(set, set.posLen, ms);
+        g.sThrVcm[slot]   = *mergeSetStream(set, set.thrVcm, ms);
+        g.sDirVm[slot]    = *mergeSetStream(set, set.dirVm, ms);
+        g.sContProb[slot] = *mergeSetStream(set, set.contProb, ms);
     }
 }
 
@@ -385,7 +383,7 @@ k_cellBBox(const __grid_constant__ MergeSet set, int32_t *bboxBits)
     {
         const MergeSlot ms = mergeSetSlot(set, i);
         if(!mergeSetValid(set, ms)) continue;
-        const float4 p = mergeSetRecord(set, ms)[0];
+        const float4 p = *mergeSetStream(set, set.posLen, ms);
         mn = mk3(fminf(mn.x, p.x), fminf(mn.y, p.y), fminf(mn.z, p.z));
         mx = mk3(fmaxf(mx.x, p.x), fmaxf(mx.y, p.y), fmaxf(mx.z, p.z));
     }
@@ -1547,12 +1545,6 @@ void launchCellMerge(const DevScene &sc, const IterConst &ic, const QueryStore &
                                     counters, maxQueries, stream);
         break;
     }
-}
-
-void launchParticleBBox(const MergeSet &set, int32_t *bboxBits, cudaStream_t stream)
-{
-    const uint32_t maxTotal = set.singleCount ? set.capacity : set.numSegs * set.segStride;
-    if(maxTotal > 0u) k_cellBBox<<<gridFor(maxTotal, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(set, bboxBits);
 }
 
 void launchGatherPackHeader(const MergeSet &localSet, const int32_t *bboxInit, GatherHeader *header, cudaStream_t stream)

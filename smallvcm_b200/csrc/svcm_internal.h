@@ -45,32 +45,34 @@ struct PathQueue
 enum { PATH_FLAG_FINITE = 1u << 30, PATH_FLAG_SPECULAR = 1u << 31, PATH_LEN_MASK = (1u << 30) - 1u };
 
 // Light vertices of the LOCAL light sub-paths (PathVertex<true>, src/vertexcm.hxx:79-98), stored
-// twice, once per consumer, each as ONE 64-byte record (two full sectors, written and read whole):
-//   merge record (all-gathered and bucket-sorted; only when merging), `rec`, in creation order:
-//       [0] hitpoint.xyz | pathLength   [1] throughput.xyz | dVCM
-//       [2] WorldDirFix().xyz | dVM     [3] light-BSDF continuation probability | - | - | -
-//   connection record (local; only when connecting), `conn`, PATH-MAJOR — the k-th stored vertex of
-//     local path l lies at conn[(l * connSlots + k) * 4 .. +3], so the vertices one camera vertex
-//     connects to (its own light sub-path, src/vertexcm.hxx:504-506) are contiguous:
+// twice, once per consumer:
+//   merge record (52 B, all-gathered and cell-sorted; only when merging): posLen, thrVcm, dirVm,
+//     contProb, in the order the vertices were created
+//   connection record (64 B, local; only when connecting): `conn`, PATH-MAJOR — the k-th stored
+//     vertex of local path l lies at conn[(l * connSlots + k) * 4 .. +3], so the vertices one
+//     camera vertex connects to (its own light sub-path, src/vertexcm.hxx:504-506) are contiguous:
 //       [0] hitpoint.xyz | pathLength   [1] throughput.xyz | dVCM
 //       [2] shading normal.xyz | dVC    [3] local fixed direction.xyz | matID
 //     pathVertCount[l] says how many there are (replaces mPathEnds)
 struct VertexStore
 {
-    float4  *rec;       // merge records, 4 x float4 per vertex
+    float4  *posLen;    // hitpoint.xyz | pathLength (bits)
+    float4  *thrVcm;    // throughput.xyz | dVCM
+    float4  *dirVm;     // WorldDirFix().xyz | dVM
+    float   *contProb;  // light BSDF continuation probability
     float4  *conn;      // connection records, 4 x float4 per slot
     uint32_t connSlots; // slots per path (maxPathLength - 1)
     uint32_t capacity;
 };
 
-// The particle set of one grid build: the merge records (VertexStore::rec layout) of ALL light vertices.
-//   single rank : the local records, `*singleCount` of them (device counter, clamped to capacity).
-//   all ranks   : numSegs blocks of one all-gather, `segBytes` apart; `rec` addresses the records of
-//                 block 0, every block holds `segStride` record slots of which the first
-//                 segCountDev[seg] are valid (device array filled from the block headers).
+// The particle set of one grid build: the merge records of ALL light vertices.
+//   single rank : the local streams, `*singleCount` records (device counter, clamped to capacity).
+//   all ranks   : numSegs blocks of one all-gather, `segBytes` apart; the four pointers address the
+//                 streams of block 0, every block holds `segStride` record slots of which the
+//                 first segCountDev[seg] are valid (device array filled from the block headers).
 struct MergeSet
 {
-    const float4 *rec;
+    const float4 *posLen; const float4 *thrVcm; const float4 *dirVm; const float *contProb;
     const unsigned long long *singleCount;
     uint32_t capacity;
     uint32_t segStride;
@@ -265,8 +267,6 @@ int  launchCellQuerySort(const IterConst &ic, const QueryStore &queries, const u
                          unsigned long long *counters, cudaStream_t stream);
 // the all-gather block headers (GatherHeader): bbox + count of the local vertices into `header`,
 // and after the collective the per-block counts, the union bbox and the total out of all headers
-// bbox of the particles into bboxBits (ordered-int atomics; the caller initialised it)
-void launchParticleBBox(const MergeSet &set, int32_t *bboxBits, cudaStream_t stream);
 void launchGatherPackHeader(const MergeSet &localSet, const int32_t *bboxInit, GatherHeader *header, cudaStream_t stream);
 void launchGatherUnpackHeaders(const unsigned char *blocks, uint64_t blockBytes, uint32_t numSegs, uint32_t segStride,
                                uint32_t *segCountDev, int32_t *bboxBits, unsigned long long *totals, cudaStream_t stream);
@@ -316,7 +316,8 @@ void launchImageConvert(const float *accum, int width, int height, int iteration
 void launchRngStream(uint32_t key, uint32_t firstPath, int paths, int draws, float *out,
                      cudaStream_t stream);
 // packs host-layout records into the device streams
-void launchPackMergeVertices(const SvcmMergeVertex *verts, int64_t count, float4 *rec, cudaStream_t stream);
+void launchPackMergeVertices(const SvcmMergeVertex *verts, int64_t count, float4 *posLen,
+                             float4 *thrVcm, float4 *dirVm, float *contProb, cudaStream_t stream);
 void launchPackMergeQueries(const DevScene &sc, const SvcmMergeQuery *queries, int64_t count,
                             QueryStore store, cudaStream_t stream);
 

@@ -267,12 +267,10 @@ k_lightBounce(const __grid_constant__ DevScene sc, const __grid_constant__ IterC
                 const float4 thrVcm = mk4(s.throughput, s.dVCM);
                 if(ic.useVM)
                 {
-                    // merge record: 64 contiguous bytes, two full sectors
-                    float4 *rec = a.verts.rec + size_t(vidx) * 4u;
-                    rec[0] = posLen;
-                    rec[1] = thrVcm;
-                    rec[2] = mk4(bsdf.worldDirFix(), s.dVM);
-                    rec[3] = make_float4(bsdf.contProb, 0.f, 0.f, 0.f);
+                    a.verts.posLen[vidx]   = posLen;
+                    a.verts.thrVcm[vidx]   = thrVcm;
+                    a.verts.dirVm[vidx]    = mk4(bsdf.worldDirFix(), s.dVM);
+                    a.verts.contProb[vidx] = bsdf.contProb;
                 }
                 if(ic.useVC)
                 {
@@ -877,7 +875,40 @@ k_eyeLight(const __grid_constant__ DevScene sc, const __grid_constant__ IterCons
 // hash grid build (HashGrid::Build, reference src/hashgrid.hxx:41-107)
 // ------------------------------------------------------------------------------------------
 
-// (bounding box of the particles, src/hashgrid.hxx:50-61: k_cellBBox in svcm_grid.cu, launchParticleBBox)
+// bounding box of the particles (reference src/hashgrid.hxx:50-61)
+__global__ void __launch_bounds__(SVCM_BLOCK)
+k_gridBBox(const __grid_constant__ MergeSet set, int32_t *bboxBits)
+{
+    f3 mn = mk3(1e36f), mx = mk3(-1e36f);
+    const uint32_t total = mergeSetTotal(set);
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    {
+        const MergeSlot ms = mergeSetSlot(set, i);
+        if(!mergeSetValid(set, ms)) continue;
+        const float4 p = *mergeSetStream(set, set.posLen, ms);
+        mn = mk3(fminf(mn.x, p.x), fminf(mn.y, p.y), fminf(mn.z, p.z));
+        mx = mk3(fmaxf(mx.x, p.x), fmaxf(mx.y, p.y), fmaxf(mx.z, p.z));
+    }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1)
+    {
+        mn.x = fminf(mn.x, __shfl_xor_sync(FULL_MASK, mn.x, o));
+        mn.y = fminf(mn.y, __shfl_xor_sync(FULL_MASK, mn.y, o));
+        mn.z = fminf(mn.z, __shfl_xor_sync(FULL_MASK, mn.z, o));
+        mx.x = fmaxf(mx.x, __shfl_xor_sync(FULL_MASK, mx.x, o));
+        mx.y = fmaxf(mx.y, __shfl_xor_sync(FULL_MASK, mx.y, o));
+        mx.z = fmaxf(mx.z, __shfl_xor_sync(FULL_MASK, mx.z, o));
+    }
+    if(laneId() == 0u)
+    {
+        atomicMin(bboxBits + 0, floatToOrdered(mn.x));
+        atomicMin(bboxBits + 1, floatToOrdered(mn.y));
+        atomicMin(bboxBits + 2, floatToOrdered(mn.z));
+        atomicMax(bboxBits + 3, floatToOrdered(mx.x));
+        atomicMax(bboxBits + 4, floatToOrdered(mx.y));
+        atomicMax(bboxBits + 5, floatToOrdered(mx.z));
+    }
+}
 
 // cell key of every particle + per-cell histogram (reference src/hashgrid.hxx:67-71,189-202)
 __global__ void __launch_bounds__(SVCM_BLOCK)
@@ -892,7 +923,7 @@ k_gridKeys(const __grid_constant__ MergeSet set, const int32_t *bboxBits, float 
         const MergeSlot ms = mergeSetSlot(set, i);
         if(mergeSetValid(set, ms))
         {
-            const float4 p = mergeSetRecord(set, ms)[0];
+            const float4 p = *mergeSetStream(set, set.posLen, ms);
             const f3 distMin = xyz(p) - bbMin;
             key = cellHash(int32_t(floorf(invCellSize * distMin.x)), int32_t(floorf(invCellSize * distMin.y)),
                            int32_t(floorf(invCellSize * distMin.z)), numCells);
@@ -1009,11 +1040,11 @@ k_gridScatter(const __grid_constant__ MergeSet set, const __grid_constant__ Grid
         {
             if(key[k] == 0xFFFFFFFFu) continue;
             const uint32_t i = i0 + uint32_t(k) * blockDim.x;
-            const float4 *rec = mergeSetRecord(set, mergeSetSlot(set, i));
-            g.sPosLen[dst[k]]   = rec[0];
-            g.sThrVcm[dst[k]]   = rec[1];
-            g.sDirVm[dst[k]]    = rec[2];
-            g.sContProb[dst[k]] = rec[3].x;
+            const MergeSlot ms = mergeSetSlot(set, i);
+            g.sPosLen[dst[k]]   = *mergeSetStream(set, set.posLen, ms);
+            g.sThrVcm[dst[k]]   = *mergeSetStream(set, set.thrVcm, ms);
+            g.sDirVm[dst[k]]    = *mergeSetStream(set, set.dirVm, ms);
+            g.sContProb[dst[k]] = *mergeSetStream(set, set.contProb, ms);
             g.sIndex[dst[k]]    = int32_t(i);
         }
     }
@@ -1587,15 +1618,15 @@ __global__ void k_rngStream(uint32_t key, uint32_t firstPath, int paths, int dra
     for(int k = 0; k < draws; k++) out[size_t(p) * draws + k] = rng.next();
 }
 
-__global__ void k_packMergeVertices(const SvcmMergeVertex *v, int64_t count, float4 *rec)
+__global__ void k_packMergeVertices(const SvcmMergeVertex *v, int64_t count, float4 *posLen, float4 *thrVcm,
+                                    float4 *dirVm, float *contProb)
 {
     for(int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x)
     {
-        float4 *r = rec + size_t(i) * 4u;
-        r[0] = make_float4(v[i].position[0], v[i].position[1], v[i].position[2], __uint_as_float(v[i].pathLength));
-        r[1] = make_float4(v[i].throughput[0], v[i].throughput[1], v[i].throughput[2], v[i].dVCM);
-        r[2] = make_float4(v[i].dirFix[0], v[i].dirFix[1], v[i].dirFix[2], v[i].dVM);
-        r[3] = make_float4(v[i].contProb, 0.f, 0.f, 0.f);
+        posLen[i] = make_float4(v[i].position[0], v[i].position[1], v[i].position[2], __uint_as_float(v[i].pathLength));
+        thrVcm[i] = make_float4(v[i].throughput[0], v[i].throughput[1], v[i].throughput[2], v[i].dVCM);
+        dirVm[i]  = make_float4(v[i].dirFix[0], v[i].dirFix[1], v[i].dirFix[2], v[i].dVM);
+        contProb[i] = v[i].contProb;
     }
 }
 
@@ -1729,7 +1760,7 @@ int launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers 
     if(maxTotal > 0)
     {
         const uint32_t gridN = gridFor(maxTotal, SVCM_BLOCK, 8);
-        if(!bboxReady) launchParticleBBox(set, grid.bboxBits, stream);
+        if(!bboxReady) k_gridBBox<<<gridN, SVCM_BLOCK, 0, stream>>>(set, grid.bboxBits);
         k_gridKeys<<<gridN, SVCM_BLOCK, 0, stream>>>(set, grid.bboxBits, ic.invCellSize, ic.numCells,
                                                      grid.cellKey, grid.cellCount);
         launches += 2;
@@ -1903,10 +1934,11 @@ void launchRngStream(uint32_t key, uint32_t firstPath, int paths, int draws, flo
     if(paths <= 0) return;
     k_rngStream<<<(paths + 127) / 128, 128, 0, stream>>>(key, firstPath, paths, draws, out);
 }
-void launchPackMergeVertices(const SvcmMergeVertex *verts, int64_t count, float4 *rec, cudaStream_t stream)
+void launchPackMergeVertices(const SvcmMergeVertex *verts, int64_t count, float4 *posLen, float4 *thrVcm,
+                             float4 *dirVm, float *contProb, cudaStream_t stream)
 {
     if(count <= 0) return;
-    k_packMergeVertices<<<gridFor(count, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(verts, count, rec);
+    k_packMergeVertices<<<gridFor(count, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(verts, count, posLen, thrVcm, dirVm, contProb);
 }
 void launchPackMergeQueries(const DevScene &sc, const SvcmMergeQuery *queries, int64_t count, QueryStore store,
                             cudaStream_t stream)

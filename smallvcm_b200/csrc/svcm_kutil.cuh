@@ -91,11 +91,9 @@ SVCM_D bool mergeSetValid(const MergeSet &set, MergeSlot s)
 {
     return set.singleCount ? true : s.j < set.segCountDev[s.seg];
 }
-// the 4 x float4 record of a slot
-SVCM_D const float4 *mergeSetRecord(const MergeSet &set, MergeSlot s)
+template<typename T> SVCM_D const T *mergeSetStream(const MergeSet &set, const T *base, MergeSlot s)
 {
-    return reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(set.rec) + uint64_t(s.seg) * set.segBytes) +
-           size_t(s.j) * 4u;
+    return reinterpret_cast<const T*>(reinterpret_cast<const unsigned char*>(base) + uint64_t(s.seg) * set.segBytes) + s.j;
 }
 
 // HashGrid::GetCellIndex(Vec3i), reference src/hashgrid.hxx:179-187
