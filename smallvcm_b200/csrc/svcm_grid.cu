@@ -1547,6 +1547,12 @@ void launchCellMerge(const DevScene &sc, const IterConst &ic, const QueryStore &
     }
 }
 
+void launchParticleBBox(const MergeSet &set, int32_t *bboxBits, cudaStream_t stream)
+{
+    const uint32_t maxTotal = set.singleCount ? set.capacity : set.numSegs * set.segStride;
+    if(maxTotal > 0u) k_cellBBox<<<gridFor(maxTotal, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(set, bboxBits);
+}
+
 void launchGatherPackHeader(const MergeSet &localSet, const int32_t *bboxInit, GatherHeader *header, cudaStream_t stream)
 {
     cudaMemcpyAsync(header->bbox, bboxInit, sizeof(int32_t) * 6, cudaMemcpyDeviceToDevice, stream);

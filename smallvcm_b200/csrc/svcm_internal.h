@@ -267,6 +267,8 @@ int  launchCellQuerySort(const IterConst &ic, const QueryStore &queries, const u
                          unsigned long long *counters, cudaStream_t stream);
 // the all-gather block headers (GatherHeader): bbox + count of the local vertices into `header`,
 // and after the collective the per-block counts, the union bbox and the total out of all headers
+// bbox of the particles into bboxBits (ordered-int atomics; the caller initialised it)
+void launchParticleBBox(const MergeSet &set, int32_t *bboxBits, cudaStream_t stream);
 void launchGatherPackHeader(const MergeSet &localSet, const int32_t *bboxInit, GatherHeader *header, cudaStream_t stream);
 void launchGatherUnpackHeaders(const unsigned char *blocks, uint64_t blockBytes, uint32_t numSegs, uint32_t segStride,
                                uint32_t *segCountDev, int32_t *bboxBits, unsigned long long *totals, cudaStream_t stream);

@@ -875,40 +875,7 @@ k_eyeLight(const __grid_constant__ DevScene sc, const __grid_constant__ IterCons
 // hash grid build (HashGrid::Build, reference src/hashgrid.hxx:41-107)
 // ------------------------------------------------------------------------------------------
 
-// bounding box of the particles (reference src/hashgrid.hxx:50-61)
-__global__ void __launch_bounds__(SVCM_BLOCK)
-k_gridBBox(const __grid_constant__ MergeSet set, int32_t *bboxBits)
-{
-    f3 mn = mk3(1e36f), mx = mk3(-1e36f);
-    const uint32_t total = mergeSetTotal(set);
-    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
-    {
-        const MergeSlot ms = mergeSetSlot(set, i);
-        if(!mergeSetValid(set, ms)) continue;
-        const float4 p = *mergeSetStream(set, set.posLen, ms);
-        mn = mk3(fminf(mn.x, p.x), fminf(mn.y, p.y), fminf(mn.z, p.z));
-        mx = mk3(fmaxf(mx.x, p.x), fmaxf(mx.y, p.y), fmaxf(mx.z, p.z));
-    }
-#pragma unroll
-    for(int o = 16; o > 0; o >>= 1)
-    {
-        mn.x = fminf(mn.x, __shfl_xor_sync(FULL_MASK, mn.x, o));
-        mn.y = fminf(mn.y, __shfl_xor_sync(FULL_MASK, mn.y, o));
-        mn.z = fminf(mn.z, __shfl_xor_sync(FULL_MASK, mn.z, o));
-        mx.x = fmaxf(mx.x, __shfl_xor_sync(FULL_MASK, mx.x, o));
-        mx.y = fmaxf(mx.y, __shfl_xor_sync(FULL_MASK, mx.y, o));
-        mx.z = fmaxf(mx.z, __shfl_xor_sync(FULL_MASK, mx.z, o));
-    }
-    if(laneId() == 0u)
-    {
-        atomicMin(bboxBits + 0, floatToOrdered(mn.x));
-        atomicMin(bboxBits + 1, floatToOrdered(mn.y));
-        atomicMin(bboxBits + 2, floatToOrdered(mn.z));
-        atomicMax(bboxBits + 3, floatToOrdered(mx.x));
-        atomicMax(bboxBits + 4, floatToOrdered(mx.y));
-        atomicMax(bboxBits + 5, floatToOrdered(mx.z));
-    }
-}
+// (bounding box of the particles, src/hashgrid.hxx:50-61: k_cellBBox in svcm_grid.cu, launchParticleBBox)
 
 // cell key of every particle + per-cell histogram (reference src/hashgrid.hxx:67-71,189-202)
 __global__ void __launch_bounds__(SVCM_BLOCK)
@@ -1760,7 +1727,7 @@ int launchGridBuild(const IterConst &ic, const MergeSet &set, const GridBuffers 
     if(maxTotal > 0)
     {
         const uint32_t gridN = gridFor(maxTotal, SVCM_BLOCK, 8);
-        if(!bboxReady) k_gridBBox<<<gridN, SVCM_BLOCK, 0, stream>>>(set, grid.bboxBits);
+        if(!bboxReady) launchParticleBBox(set, grid.bboxBits, stream);
         k_gridKeys<<<gridN, SVCM_BLOCK, 0, stream>>>(set, grid.bboxBits, ic.invCellSize, ic.numCells,
                                                      grid.cellKey, grid.cellCount);
         launches += 2;
