@@ -534,8 +534,9 @@ def run_gpu_arm(args):
                                "parity_note": "||reduce_accum(N-rank render) - 1-GPU render|| / ||1-GPU render||, scene 1 "
                                               "vcm 512^2, iterations 0..1 (differs only by the order of float atomics)",
                                "note": "every iteration split over the GPUs by image rows (round robin); per "
-                                       "iteration one NCCL all-gather of the 52-byte light-vertex merge records "
-                                       "(counts first, then one group of four ncclAllGather) before the grid build; "
+                                       "iteration ONE in-place ncclAllGather of fixed-size blocks [256-byte header with the "
+                                       "rank's count and bounding box | its 52-byte light-vertex merge records] before "
+                                       "the grid build, no host round trip; "
                                        "a step is N such iterations. Fixed per-iteration costs (replicated grid "
                                        "build, gather, launch floors of 1/N-sized kernels) bound this mode at 1024^2; "
                                        "it exists for iterations too large for one GPU (BASELINE config #5)"}

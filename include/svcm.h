@@ -490,6 +490,18 @@ typedef struct SvcmBvhNode {
 SVCM_API int svcm_bvh_build(const SvcmPrimitive *primitives, int32_t numPrimitives, SvcmBvhNode *nodes,
                             int32_t nodeCapacity, int32_t *order, int32_t *numNodes);
 
+/* How svcm_create cuts a list of at most SVCM_MAX_PRIMITIVES primitives (the reference's scenes:
+ * GeometryList, src/geometry.hxx:65-91, tests every primitive for every ray) into contiguous runs
+ * (host code, no GPU needed; exposed for inspection and tests). The list order is kept. Run i
+ * covers primitives [runs[i].first, runs[i].first + runs[i].count). Bit i of *skippable set: the
+ * run is consecutive small triangles inside the padded box runs[i].lo/hi and a ray that misses
+ * the box skips it — like a leaf of the hierarchy above and under the same rules (no primitive the
+ * arithmetic of the reference's test would hit is ever skipped); bit clear: always tested (large
+ * triangles, spheres). At most SVCM_MAX_RUNS runs. */
+#define SVCM_MAX_RUNS 8
+SVCM_API int svcm_primitive_runs(const SvcmPrimitive *primitives, int32_t numPrimitives, SvcmBvhNode *runs,
+                                 uint32_t *skippable, int32_t *numRuns);
+
 /* The image conversions of svcm_download_image on a caller-supplied accumulated image
  * [height][width][3] (host memory); out holds svcm_image_bytes(format, width, height). */
 SVCM_API int svcm_image_convert_batch(const float *accum, int32_t width, int32_t height, int32_t iterations,

@@ -13,6 +13,7 @@ LIGHT_AREA, LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_BACKGROUND = 0, 1, 2, 3
 # VertexCM::AlgorithmType numbering (reference src/vertexcm.hxx:182-204)
 IMAGE_BMP24, IMAGE_RGBE = 0, 1   # SVCM_IMAGE_*
 MAX_PRIMITIVES, MAX_PRIMITIVES_BVH, MAX_MATERIALS, MAX_LIGHTS = 64, 1 << 24, 16, 8
+MAX_RUNS = 8
 ALG_LIGHT_TRACE, ALG_PPM, ALG_BPM, ALG_BPT, ALG_VCM, ALG_PATH_TRACE, ALG_EYE_LIGHT = 0, 1, 2, 3, 4, 5, 6
 ALGORITHMS = {"lt": ALG_LIGHT_TRACE, "ppm": ALG_PPM, "bpm": ALG_BPM, "bpt": ALG_BPT, "vcm": ALG_VCM,
               "pt": ALG_PATH_TRACE, "el": ALG_EYE_LIGHT}
@@ -129,6 +130,7 @@ PROTOTYPES = {
     "svcm_download_image": (i32, [VP, i32, f32, VP, C.POINTER(i32)]),
     "svcm_save_image": (i32, [VP, C.c_char_p, f32]),
     "svcm_bvh_build": (i32, [VP, i32, VP, i32, VP, C.POINTER(i32)]),
+    "svcm_primitive_runs": (i32, [VP, i32, VP, C.POINTER(u32), C.POINTER(i32)]),
     "svcm_image_convert_batch": (i32, [VP, i32, i32, i32, i32, f32, i32, VP]),
     "svcm_get_stats": (i32, [VP, C.POINTER(Stats)]),
     "svcm_get_profile": (i32, [VP, C.POINTER(Profile)]),

@@ -243,6 +243,12 @@ int buildDevScene(svcm_renderer *r, const SvcmSceneDesc *d, DevScene &s)
         memcpy(s.prims[i].v, p.v, sizeof(float) * 12);
         s.prims[i].type = p.type; s.prims[i].matID = p.matID;
     }
+    s.numRuns = 0; s.runCull = 0u;
+    if(d->numPrimitives > 0 && d->numPrimitives <= SVCM_MAX_PRIMITIVES)
+    {
+        const bool plain = getenv("SVCM_DEBUG_NO_RUNS") && atoi(getenv("SVCM_DEBUG_NO_RUNS")) != 0;   // A/B switch of the tests
+        s.numRuns = primitiveRuns(d->primitives, d->numPrimitives, plain, s.runs, &s.runCull);
+    }
     for(int i = 0; i < d->numLights; i++)
     {
         const SvcmLight &l = d->lights[i];

@@ -166,6 +166,66 @@ int bvhBuild(const SvcmPrimitive *prims, int32_t count, std::vector<BvhNode> &no
     return 0;
 }
 
+// Cuts a primitive list small enough for the constant bank into at most SVCM_MAX_RUNS contiguous
+// runs (DevScene::runs, svcm_device.cuh); the list order is kept. Consecutive triangles whose common
+// box stays small against the scene's (surface area at most kRunAreaFraction of it) form a run that
+// a ray skips when it misses the box; everything else — large triangles, spheres (their own
+// discriminant test already rejects early) — goes into runs that are always tested (bit clear in
+// cullMask, box = everything). Boxes are padded like the hierarchy's. A skippable run of fewer than
+// three triangles is not worth its box test and is marked always-tested. `plain`: one always-tested
+// run with the whole list. Returns the number of runs.
+int primitiveRuns(const SvcmPrimitive *prims, int32_t n, bool plain, BvhNode *runs, uint32_t *cullMask)
+{
+    const float kRunAreaFraction = 0.05f;
+    *cullMask = 0u;
+    if(n <= 0) return 0;
+    std::vector<Box> boxes((size_t)n);
+    Box scene; scene.clear();
+    float maxAbs = 1e-30f; bool finite = true;
+    for(int32_t i = 0; i < n; i++)
+    {
+        const SvcmPrimitive &p = prims[i];
+        Box &b = boxes[(size_t)i];
+        b.clear();
+        if(p.type == SVCM_PRIM_TRIANGLE) { b.grow(p.v); b.grow(p.v + 3); b.grow(p.v + 6); }
+        else for(int a = 0; a < 3; a++) { b.lo[a] = p.v[a] - p.v[3]; b.hi[a] = p.v[a] + p.v[3]; }
+        for(int a = 0; a < 3; a++)
+        {
+            finite = finite && std::isfinite(b.lo[a]) && std::isfinite(b.hi[a]);
+            maxAbs = std::max(maxAbs, std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a])));
+        }
+        scene.grow(b);
+    }
+    const float pad = 1e-5f * maxAbs;
+    const float limit = kRunAreaFraction * scene.halfArea();
+    if(!finite) plain = true;
+
+    int numRuns = 0;
+    auto close = [&](int32_t first, int32_t end, bool cull, const Box &b)
+    {
+        cull = cull && (end - first) >= 3;
+        BvhNode &r = runs[numRuns];
+        r.first = first; r.count = end - first;
+        for(int a = 0; a < 3; a++) { r.lo[a] = cull ? b.lo[a] - pad : -3.0e38f; r.hi[a] = cull ? b.hi[a] + pad : 3.0e38f; }
+        if(cull) *cullMask |= 1u << numRuns;
+        numRuns++;
+    };
+    auto isSmall = [&](int32_t i) { return !plain && prims[i].type == SVCM_PRIM_TRIANGLE && boxes[(size_t)i].halfArea() <= limit; };
+    int32_t first = 0; bool cull = isSmall(0); Box cur = boxes[0];
+    for(int32_t i = 1; i < n; i++)
+    {
+        const bool small = isSmall(i);
+        Box joined = cur; joined.grow(boxes[(size_t)i]);
+        const bool extend = (small == cull) && (!cull || joined.halfArea() <= limit);
+        if(extend) { cur = joined; continue; }
+        if(numRuns == SVCM_MAX_RUNS - 1) { cull = false; cur = joined; continue; }   // the last slot takes the rest, always tested
+        close(first, i, cull, cur);
+        first = i; cull = small; cur = boxes[(size_t)i];
+    }
+    close(first, n, cull, cur);
+    return numRuns;
+}
+
 } // namespace svcm
 
 extern "C" {
@@ -181,6 +241,17 @@ SVCM_API int svcm_bvh_build(const SvcmPrimitive *primitives, int32_t numPrimitiv
     static_assert(sizeof(SvcmBvhNode) == sizeof(svcm::BvhNode), "node layouts must match");
     memcpy(nodes, built.data(), sizeof(svcm::BvhNode) * built.size());
     memcpy(order, perm.data(), sizeof(int32_t) * perm.size());
+    return SVCM_OK;
+}
+
+SVCM_API int svcm_primitive_runs(const SvcmPrimitive *primitives, int32_t numPrimitives, SvcmBvhNode *runs,
+                                 uint32_t *skippable, int32_t *numRuns)
+{
+    if(!primitives || numPrimitives <= 0 || numPrimitives > SVCM_MAX_PRIMITIVES || !runs || !skippable || !numRuns)
+        return SVCM_E_INVALID;
+    svcm::BvhNode built[SVCM_MAX_RUNS];
+    *numRuns = svcm::primitiveRuns(primitives, numPrimitives, false, built, skippable);
+    memcpy(runs, built, sizeof(svcm::BvhNode) * size_t(*numRuns));
     return SVCM_OK;
 }
 

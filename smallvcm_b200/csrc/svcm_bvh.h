@@ -35,6 +35,9 @@ struct alignas(16) BvhNode
     float   hi[3]; int32_t count;
 };
 
+#ifndef SVCM_MAX_RUNS
+#define SVCM_MAX_RUNS  8           // runs of the constant-bank primitive list (primitiveRuns, svcm_bvh.cpp; also in svcm.h)
+#endif
 #define SVCM_BVH_STACK 64          // the builder never produces a deeper tree (bvhBuild checks)
 #define SVCM_BVH_LEAF  4           // primitives per leaf the builder aims for
 

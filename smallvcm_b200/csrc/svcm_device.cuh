@@ -151,6 +151,13 @@ struct DevScene
     SvcmMaterial mats[SVCM_MAX_MATERIALS];
     DevLight lights[SVCM_MAX_LIGHTS];
     DevPrim  prims[SVCM_MAX_PRIMITIVES];
+    // The constant-bank list cut into contiguous runs (list order kept). A run whose bit is set in
+    // runCull consists of triangles inside a small padded box (lo / hi): a ray that misses the box
+    // skips the run, like a leaf of the hierarchy below and under the same rules (svcm_bvh.h).
+    // Walls, spheres and anything large sit in runs that are always tested.
+    int32_t  numRuns;
+    uint32_t runCull;
+    BvhNode  runs[SVCM_MAX_RUNS];
     // numPrims > SVCM_MAX_PRIMITIVES: the list lives in global memory under a hierarchy instead
     const BvhNode  *bvh;         // NULL for the constant-bank list above
     const DevPrimG *bvhPrims;
@@ -159,9 +166,23 @@ struct DevScene
 struct Hit { float dist; int32_t matID; int32_t prim; f3 normal; };
 
 // Triangle::Intersect, reference src/geometry.hxx:125-156
-SVCM_D bool hitTriangle(const float *v, f3 org, f3 dir, float tmax, float &oDist)
+SVCM_HD bool hitTriangle(const float *v, f3 org, f3 dir, float tmax, float &oDist)
 {
     const f3 ao = ld3(v) - org;
+    const f3 n = ld3(v + 9);
+    const float num = dot(n, ao), den = dot(n, dir);
+    // The reference evaluates the three edge tests first and the plane distance num / den last; a hit
+    // needs both, so the order is free. The distance is the cheap half and, for a segment between two
+    // points inside a closed room, almost always out of range: decide that first, WITHOUT the division
+    // and only where the IEEE quotient is certain to fail 0 < distance < tmax —
+    //   * num and den of opposite sign, or num == 0, or den == 0: the quotient is negative, a zero, NaN
+    //     or an infinity;
+    //   * |num| > tmax |den| by more than 1e-5 relative (the quotient and the product round by 6e-8
+    //     each; products in the subnormal range, where that no longer holds, are left to the division).
+    // Everything else runs the reference's test unchanged, so the result is the same bit for bit.
+    const float sn = (den < 0.f) ? -num : num;
+    const float q = tmax * fabsf(den);
+    if(!(sn > 0.f) || (q >= 1e-30f && sn > q * 1.00001f)) return false;
     const f3 bo = ld3(v + 3) - org;
     const f3 co = ld3(v + 6) - org;
     const float v0d = dot(cross(co, bo), dir);
@@ -169,8 +190,7 @@ SVCM_D bool hitTriangle(const float *v, f3 org, f3 dir, float tmax, float &oDist
     const float v2d = dot(cross(ao, co), dir);
     if(((v0d < 0.f) && (v1d < 0.f) && (v2d < 0.f)) || ((v0d >= 0.f) && (v1d >= 0.f) && (v2d >= 0.f)))
     {
-        const f3 n = ld3(v + 9);
-        const float distance = dot(n, ao) / dot(n, dir);
+        const float distance = num / den;
         if((distance > 0.f) && (distance < tmax)) { oDist = distance; return true; }
     }
     return false;
@@ -255,13 +275,23 @@ SVCM_D bool sceneIntersect(const DevScene &sc, f3 org, f3 dir, Hit &hit)
     if(kBvh) return bvhSceneIntersect(sc.bvh, sc.bvhPrims, org, dir, hit);
     float best = 1e36f;
     int prim = -1;
-    for(int i = 0; i < sc.numPrims; i++)
+    for(int r = 0; r < sc.numRuns; r++)
     {
-        float d;
-        const bool h = (sc.prims[i].type == SVCM_PRIM_TRIANGLE)
-            ? hitTriangle(sc.prims[i].v, org, dir, best, d)
-            : hitSphere(sc.prims[i].v, org, dir, best, d);
-        if(h) { best = d; prim = i; }
+        if((sc.runCull >> r) & 1u)
+        {
+            float tEnter;           // the box against [0, best]: a run behind the closest hit so far is skipped too
+            if(!bvhSlab(sc.runs[r], org.x, org.y, org.z, __frcp_rn(dir.x), __frcp_rn(dir.y), __frcp_rn(dir.z), best, tEnter))
+                continue;
+        }
+        const int end = sc.runs[r].first + sc.runs[r].count;
+        for(int i = sc.runs[r].first; i < end; i++)
+        {
+            float d;
+            const bool h = (sc.prims[i].type == SVCM_PRIM_TRIANGLE)
+                ? hitTriangle(sc.prims[i].v, org, dir, best, d)
+                : hitSphere(sc.prims[i].v, org, dir, best, d);
+            if(h) { best = d; prim = i; }
+        }
     }
     if(prim < 0) return false;
     hit.dist  = best;
@@ -286,13 +316,23 @@ SVCM_D bool sceneOccluded(const DevScene &sc, f3 point, f3 dir, float tMax)
     const f3 org = point + dir * SVCM_EPS_RAY;
     const float tmax = tMax - 2.f * SVCM_EPS_RAY;
     if(kBvh) return bvhSceneOccluded(sc.bvh, sc.bvhPrims, org, dir, tmax);
-    for(int i = 0; i < sc.numPrims; i++)
+    for(int r = 0; r < sc.numRuns; r++)
     {
-        float d;
-        const bool h = (sc.prims[i].type == SVCM_PRIM_TRIANGLE)
-            ? hitTriangle(sc.prims[i].v, org, dir, tmax, d)
-            : hitSphere(sc.prims[i].v, org, dir, tmax, d);
-        if(h) return true;
+        if((sc.runCull >> r) & 1u)
+        {
+            float tEnter;
+            if(!bvhSlab(sc.runs[r], org.x, org.y, org.z, __frcp_rn(dir.x), __frcp_rn(dir.y), __frcp_rn(dir.z), tmax, tEnter))
+                continue;
+        }
+        const int end = sc.runs[r].first + sc.runs[r].count;
+        for(int i = sc.runs[r].first; i < end; i++)
+        {
+            float d;
+            const bool h = (sc.prims[i].type == SVCM_PRIM_TRIANGLE)
+                ? hitTriangle(sc.prims[i].v, org, dir, tmax, d)
+                : hitSphere(sc.prims[i].v, org, dir, tmax, d);
+            if(h) return true;
+        }
     }
     return false;
 }

@@ -311,6 +311,7 @@ void launchLightBatch(const DevScene &sc, int op, int lightIndex, const float *i
 void launchCameraBatch(const DevScene &sc, const float *in, int64_t count, float *out, cudaStream_t stream);
 // svcm_bvh.cpp: hierarchy over a primitive list; order[slot] = original index. 0 on success.
 int bvhBuild(const SvcmPrimitive *prims, int32_t count, std::vector<BvhNode> &nodes, std::vector<int32_t> &order);
+int primitiveRuns(const SvcmPrimitive *prims, int32_t count, bool plain, BvhNode *runs, uint32_t *cullMask);
 
 // SaveBMP / SaveHDR pixel payloads of the accumulated image (src/framebuffer.hxx:170-251)
 void launchImageConvert(const float *accum, int width, int height, int iterations, int format, float gamma,

@@ -133,6 +133,15 @@ class Scene:
         dt = np.dtype([("lo", np.float32, 3), ("first", np.int32), ("hi", np.float32, 3), ("count", np.int32)])
         return np.frombuffer(nodes, dt)[:count.value].copy(), order
 
+    def primitive_runs(self):
+        """(runs structured array, skippable bit mask) of a constant-bank scene (svcm_primitive_runs)."""
+        runs = (abi.BvhNode * abi.MAX_RUNS)()
+        mask = C.c_uint32(); count = C.c_int32()
+        _check(load_library().svcm_primitive_runs(self.desc.primitives, self.desc.numPrimitives, runs, C.byref(mask),
+                                                  C.byref(count)))
+        dt = np.dtype([("lo", np.float32, 3), ("first", np.int32), ("hi", np.float32, 3), ("count", np.int32)])
+        return np.frombuffer(runs, dt)[:count.value].copy(), int(mask.value)
+
     @property
     def width(self):
         return int(self.desc.camera.resolution[0])

@@ -90,6 +90,48 @@ def test_builder_invariants(big):
     assert np.all(seen == 1) and depth.max() < 56 and nodes["count"].max() <= 4
 
 
+def test_primitive_runs_of_small_scenes():
+    """svcm_primitive_runs: the constant-bank list in contiguous runs, list order kept; only runs of
+    three or more small triangles are skippable, and their padded boxes contain them."""
+    import ctypes as C
+    for sid, nprim, skippable in [(0, 22, True), (1, 21, True), (2, 12, False), (3, 22, True)]:
+        scene = sv.Scene.cornell_box(sid, 16, 16)
+        runs, mask = scene.primitive_runs()
+        types, _, v = prim_array(scene)
+        assert scene.desc.numPrimitives == nprim and runs["first"][0] == 0
+        assert np.array_equal(runs["first"][1:], (runs["first"] + runs["count"])[:-1]) and runs["count"].sum() == nprim
+        if not skippable:
+            assert mask == 0 and len(runs) == 1
+            continue
+        assert len(runs) == 2 and mask == 0b10 and runs["count"][1] == 10          # the light box: the last ten triangles
+        assert np.all(runs["lo"][0] < -1e38) and np.all(runs["hi"][0] > 1e38)       # walls and spheres: always tested
+        box = v[nprim - 10:, :9].reshape(-1, 3)
+        assert np.all(types[nprim - 10:] == 0)
+        assert np.all(box.min(0) > runs["lo"][1]) and np.all(box.max(0) < runs["hi"][1])
+        assert np.all(box.min(0) - runs["lo"][1] < 1e-4) and np.all(runs["hi"][1] - box.max(0) < 1e-4)
+    # many separate clusters of small triangles: never more than SVCM_MAX_RUNS runs, the tail is always tested
+    base = sv.Scene.cornell_box(2, 16, 16)
+    rng = np.random.default_rng(5)
+    tri = []
+    for c in range(12):
+        centre = rng.uniform(-1, 1, 3)
+        tri.append(centre + rng.uniform(-0.05, 0.05, (4, 3, 3)))
+    scene = base.with_triangles(np.concatenate(tri).astype(np.float32), np.full(48, 5))
+    runs, mask = scene.primitive_runs()
+    assert len(runs) == abi.MAX_RUNS and runs["count"].sum() == 60 and not (mask >> (abi.MAX_RUNS - 1)) & 1
+    assert np.array_equal(runs["first"][1:], (runs["first"] + runs["count"])[:-1])
+    for r in range(len(runs)):
+        if (mask >> r) & 1:
+            _, _, v = prim_array(scene)
+            pts = v[runs["first"][r]:runs["first"][r] + runs["count"][r], :9].reshape(-1, 3)
+            assert runs["count"][r] >= 3 and np.all(pts.min(0) > runs["lo"][r]) and np.all(pts.max(0) < runs["hi"][r])
+    lib = sv.load_library()
+    out = (abi.BvhNode * abi.MAX_RUNS)(); m = C.c_uint32(); k = C.c_int32()
+    assert lib.svcm_primitive_runs(None, 12, out, C.byref(m), C.byref(k)) == abi.E_INVALID
+    assert lib.svcm_primitive_runs(base.desc.primitives, 65, out, C.byref(m), C.byref(k)) == abi.E_INVALID
+    assert lib.svcm_primitive_runs(base.desc.primitives, 0, out, C.byref(m), C.byref(k)) == abi.E_INVALID
+
+
 def test_degenerate_inputs_build():
     base = sv.Scene.cornell_box(0, 16, 16)
     same = np.tile(np.array([[[0, 0, 0], [0.1, 0, 0], [0, 0.1, 0]]], np.float32), (300, 1, 1))   # 300 identical triangles
@@ -117,6 +159,22 @@ def test_traversal_equals_list_order_loop(big, tmp_path):
         assert bad == 0
         assert np.array_equal(out[0], out[2]) and np.array_equal(out[1], out[3]) and np.array_equal(out[4], out[5])
         assert 0.3 < (out[0] >= 0).mean() and 0.1 < out[4].mean() < 0.95     # the rays do exercise both answers
+
+
+@pytest.mark.parametrize("flags", [[], ["-Xcompiler", "-mfma,-ffp-contract=fast"]], ids=["unfused", "fma"])
+def test_triangle_early_out_never_changes_the_answer(flags, tmp_path):
+    """hitTriangle (svcm_device.cuh) rejects on the plane distance before the edge tests and without the
+    division; tests/native/tri_early_out_check.cu runs it as host code against the reference's order of
+    evaluation on 48 M random and adversarial ray / triangle / tmax combinations, with and without FMA
+    contraction: same hit flag and bit-identical distance every time."""
+    exe = str(tmp_path / "tri_early_out_check")
+    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-x", "cu", "-Wno-deprecated-gpu-targets", *flags,
+                           "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "smallvcm_b200", "csrc"),
+                           os.path.join(HERE, "native", "tri_early_out_check.cu"), "-o", exe])
+    out = subprocess.run([exe, "200000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    fields = out.stdout.split()
+    assert fields[-2:] == ["disagreements", "0"] and int(fields[3]) > 1000000 and int(fields[5]) > 1000000
 
 
 def test_oracle_bit_exact_on_a_scene_that_is_not_a_hard_coded_box():

@@ -70,6 +70,52 @@ def test_intersect_and_occluded(scene_id):
     assert 0.05 < go.mean() < 0.95
 
 
+@pytest.mark.parametrize("scene_id", [0, 1, 3])
+def test_primitive_runs_never_change_a_hit(scene_id, monkeypatch):
+    """The constant-bank list is cut into runs and a ray skips a run of small triangles whose padded
+    box it misses (DevScene::runs). Skipping must never change a result: closest hits and occlusion
+    flags with the runs and with the whole list in one always-tested run (SVCM_DEBUG_NO_RUNS=1) are
+    BIT-identical, on random rays and on rays built to graze, start on, end on and run along the
+    faces of the light box — the run that is skipped in the reference's scenes."""
+    rng = np.random.default_rng(77 + scene_id)
+    scene = sv.Scene.cornell_box(scene_id, 64, 64)
+    n = 100000
+    lo = np.array([-0.25, -0.25, 1.26002], np.float32); hi = np.array([0.25, 0.25, 1.28002], np.float32)
+    inside = rng.uniform(-1.25, 1.25, (n, 3)).astype(np.float32)
+    # points on the faces of the light box (one coordinate snapped to a face), and just off them
+    on_box = (lo + (hi - lo) * rng.uniform(0, 1, (n, 3))).astype(np.float32)
+    axis = rng.integers(0, 3, n); side = rng.integers(0, 2, n)
+    on_box[np.arange(n), axis] = np.where(side == 1, hi[axis], lo[axis])
+    near_box = (on_box + rng.normal(scale=2e-3, size=(n, 3))).astype(np.float32)
+    rays, segs = [], []
+
+    def toward(a, b):
+        d = (b - a).astype(np.float32); ln = np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+        return d / np.maximum(ln, 1e-20), ln
+    for org, dst in [(inside, rng.uniform(-1.25, 1.25, (n, 3)).astype(np.float32)),      # anywhere to anywhere
+                     (inside, on_box), (inside, near_box),                              # ending on / near the box
+                     (on_box, inside), (near_box, inside),                              # starting on / near the box
+                     (on_box, np.roll(on_box, 1, 0)), (near_box, np.roll(on_box, 7, 0))]:   # along the faces
+        d, ln = toward(org, dst)
+        rays.append(np.concatenate([org, d], 1))
+        for scale in (1.0, 0.5, 1.5):
+            segs.append(np.concatenate([org, d, (ln * scale).astype(np.float32)], 1))
+    # axis-parallel rays in the planes of the box faces (zero direction components: infinite slab reciprocals)
+    d = np.zeros((n, 3), np.float32); d[np.arange(n), (axis + 1) % 3] = np.where(rng.integers(0, 2, n) == 1, 1.0, -1.0)
+    start = on_box - d * rng.uniform(0, 2, (n, 1)).astype(np.float32)
+    rays.append(np.concatenate([start, d], 1)); segs.append(np.concatenate([start, d, rng.uniform(0.01, 3, (n, 1)).astype(np.float32)], 1))
+    rays = np.concatenate(rays); segs = np.concatenate(segs)
+
+    with_runs = sv.intersect_batch(scene, rays), sv.occluded_batch(scene, segs)
+    monkeypatch.setenv("SVCM_DEBUG_NO_RUNS", "1")
+    without = sv.intersect_batch(scene, rays), sv.occluded_batch(scene, segs)
+    for a, b in zip(with_runs[0], without[0]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(with_runs[1], without[1])
+    hits_box = np.isin(with_runs[0][0], np.arange(scene.desc.numPrimitives - 10, scene.desc.numPrimitives))
+    assert hits_box.mean() > 0.05 and 0.02 < with_runs[1].mean() < 0.98          # the box itself is hit often enough
+
+
 @pytest.mark.parametrize("scene_id", [0, 1])
 @pytest.mark.parametrize("fix_is_light", [0, 1])
 def test_bsdf_evaluate_and_sample(scene_id, fix_is_light):

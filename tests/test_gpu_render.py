@@ -106,6 +106,20 @@ def test_t2_cell_layout_parity(scene_id, alg, variant):
         assert abs(st[key] - cnt[key]) <= 2e-3 * cnt[key] + 8, (key, st[key], cnt[key])
 
 
+@pytest.mark.parametrize("scene_id,alg", [(1, "vcm"), (0, "vcm"), (3, "bpt")])
+def test_primitive_runs_do_not_change_a_single_path(scene_id, alg, monkeypatch):
+    """Whole iterations with the skippable primitive runs (the default) and with the plain list
+    (SVCM_DEBUG_NO_RUNS=1): every workload counter is IDENTICAL — no path took a different branch —
+    and the images agree to the order of the float atomics."""
+    scene = sv.Scene.cornell_box(scene_id, 256, 256)
+    a_img, _, a_st = render(scene, alg, 4)
+    monkeypatch.setenv("SVCM_DEBUG_NO_RUNS", "1")
+    b_img, _, b_st = render(scene, alg, 4)
+    for key in ("lightVertices", "mergeQueries", "mergeCandidates", "mergeAccepted", "cameraRays", "lightRays", "shadowRays"):
+        assert a_st[key] == b_st[key], key
+    assert rel_l2(a_img, b_img) <= 1e-5
+
+
 def test_t2_path_length_limits():
     """min/max path length windows (src/vertexcm.hxx:133-135,382,387,438,472,482,489,512-521)."""
     scene = sv.Scene.cornell_box(1, 96, 96)
