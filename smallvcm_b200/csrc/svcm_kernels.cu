@@ -15,6 +15,35 @@
 #include "svcm_internal.h"
 #include "svcm_kutil.cuh"
 
+// Resident blocks per SM the register allocation of the hot kernels is held to. Unset: ptxas' own
+// choice for a 256-thread block (A/B builds: -DSVCM_<KERNEL>_MINBLOCKS=n, tools/build_variant.sh).
+#define SVCM_CAMERA_MINBLOCKS_DEFAULT 3
+#ifndef SVCM_CAMERA_MINBLOCKS
+#define SVCM_CAMERA_MINBLOCKS SVCM_CAMERA_MINBLOCKS_DEFAULT
+#endif
+#ifndef SVCM_LIGHT_MINBLOCKS
+#define SVCM_LIGHT_MINBLOCKS 3       // like the camera walk: three resident blocks beat two with every value in a register (0.76 vs 0.83 ms)
+#endif
+#define SVCM_LB_LIGHT __launch_bounds__(SVCM_BLOCK, SVCM_LIGHT_MINBLOCKS)
+#ifndef SVCM_CONNECT_MINBLOCKS
+#define SVCM_CONNECT_MINBLOCKS 4      // 64 registers, 24 spill bytes: 1.40 -> 1.33 ms for the camera pass alone at 1024^2 (latency-bound gathers)
+#endif
+#ifdef SVCM_CONNECT_MINBLOCKS
+#define SVCM_LB_CONNECT __launch_bounds__(SVCM_BLOCK, SVCM_CONNECT_MINBLOCKS)
+#else
+#define SVCM_LB_CONNECT __launch_bounds__(SVCM_BLOCK)
+#endif
+#ifdef SVCM_SHADOW_MINBLOCKS
+#define SVCM_LB_SHADOW __launch_bounds__(SVCM_BLOCK, SVCM_SHADOW_MINBLOCKS)
+#else
+#define SVCM_LB_SHADOW __launch_bounds__(SVCM_BLOCK)
+#endif
+#ifdef SVCM_MERGE_MINBLOCKS
+#define SVCM_LB_MERGE __launch_bounds__(SVCM_BLOCK, SVCM_MERGE_MINBLOCKS)
+#else
+#define SVCM_LB_MERGE __launch_bounds__(SVCM_BLOCK)
+#endif
+
 namespace svcm {
 
 // Queue one visibility test: "add `contrib` to `pixel` unless point -> point + dir*tMax is
@@ -207,7 +236,7 @@ SVCM_D void connectToCamera(const DevScene &sc, const IterConst &ic, const SubPa
 
 // One bounce of every live light sub-path: reference src/vertexcm.hxx:328-393 (loop body)
 template<bool kBvh>
-__global__ void __launch_bounds__(SVCM_BLOCK)
+__global__ void SVCM_LB_LIGHT
 k_lightBounce(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
               const __grid_constant__ TraceArgs a, const uint32_t bounce)
 {
@@ -433,7 +462,7 @@ SVCM_D f3 connectVertices(const DevScene &sc, const IterConst &ic, f3 lvPos, con
 template<bool kBvh>
 // (three resident blocks per SM: 80 registers with a few spill stores beat 86 registers and two
 // blocks — measured 1.73 -> 1.63 ms for the camera pass at 1024^2)
-__global__ void __launch_bounds__(SVCM_BLOCK, 3)
+__global__ void __launch_bounds__(SVCM_BLOCK, SVCM_CAMERA_MINBLOCKS)
 k_cameraBounce(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
                const __grid_constant__ TraceArgs a, const uint32_t bounce)
 {
@@ -605,7 +634,7 @@ k_makePairs(const __grid_constant__ IterConst ic, const __grid_constant__ TraceA
 // connection is evaluated with its MIS weight and, if it carries energy, its visibility
 // segment is queued for k_shadow.
 template<bool kBvh>
-__global__ void __launch_bounds__(SVCM_BLOCK)
+__global__ void SVCM_LB_CONNECT
 k_connect(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
           const __grid_constant__ TraceArgs a)
 {
@@ -654,7 +683,7 @@ k_connect(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst
 // queued segment, then Framebuffer::AddColor for the unoccluded ones. Every lane runs the same
 // primitive loop: this is where the bounce kernels' divergent any-hit loops went.
 template<bool kBvh>
-__global__ void __launch_bounds__(SVCM_BLOCK)
+__global__ void SVCM_LB_SHADOW
 k_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ TraceArgs a, const uint32_t bounce)
 {
     const uint32_t queued = a.shadow.counts[bounce];
@@ -1305,7 +1334,7 @@ SVCM_D void mergeEvaluatePairs(const DevScene &sc, const IterConst &ic, const Gr
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(SVCM_BLOCK)
+__global__ void SVCM_LB_MERGE
 k_mergeLane(const __grid_constant__ DevScene sc, const __grid_constant__ IterConst ic,
             const __grid_constant__ QueryStore qs, const unsigned long long *queryCountPtr,
             const uint32_t hostQueryCount, const __grid_constant__ GridBuffers g, float *accum,
