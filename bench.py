@@ -351,7 +351,7 @@ def measure(sv, D, args, rank, world, device, tdev, sharded, want_e2e, clocks=No
             state["next"] += stride
         r.synchronize()
         out["prof_isolated"] = r.profile()
-        r.set_option(abi.OPT_OVERLAP, 7)
+        r.set_option(abi.OPT_OVERLAP, 15)
     r.close()
     return out
 

@@ -240,11 +240,14 @@ enum {
                                    memory, 1 = neighbourhood staged through shared
                                    memory by bulk async copies (default), 3 = like 1
                                    with smaller stages                                  */
-    SVCM_OPT_OVERLAP       = 7, /* which stages of an iteration run concurrently (bit mask,
-                                   default 7): 1 = camera walk with the light pass, 2 = grid
-                                   build (and all-gather) with the camera walk, 4 = merge
-                                   with vertex connection. 0 = one stage after the other:
-                                   per-stage times are then those of the stage alone      */
+    SVCM_OPT_OVERLAP       = 7, /* which stages run concurrently (bit mask, default 15):
+                                   1 = camera walk with the light pass, 2 = grid build (and
+                                   all-gather) with the camera walk, 4 = merge with vertex
+                                   connection, 8 = the merge of one iteration with the light
+                                   pass of the next (iterations enqueued back to back; every
+                                   other entry point waits for the pending merge first).
+                                   0 = one stage after the other: per-stage times are then
+                                   those of the stage alone                               */
     SVCM_OPT_REF_CANDIDATES = 6 /* 0/1, cell layout: also histogram the reference's
                                    buckets so that mergeCandidates counts what the
                                    reference's walk would visit (statistics; off: the

@@ -150,6 +150,14 @@ struct svcm_renderer
     bool overlapPasses;             // SVCM_NO_PASS_OVERLAP=1 serialises them again (A/B)
     bool overlapMerge;              // SVCM_NO_MERGE_OVERLAP=1: merge on the main stream behind the connection kernels
     cudaEvent_t evMergeDone;
+    // ... and the merge of one iteration is left running while the next iteration's light pass starts
+    // (nothing it reads is written before the next grid build / camera walk, which wait for it).
+    // tailPending: an iteration's merge + counter copy are still only ordered on the camera stream;
+    // joinTail() orders the main stream behind them (every entry point but svcm_run_iterations calls it).
+    bool overlapIterations;         // SVCM_NO_ITERATION_OVERLAP=1 joins at the end of every iteration again (A/B)
+    bool tailPending;
+    cudaEvent_t evMainDone;
+    unsigned long long *countersBase;   // two blocks of CNT_WORDS; `counters` points at the current iteration's
     bool overlapGrid;               // SVCM_NO_GRID_OVERLAP=1: grid build on the main stream (isolated stage times)
     bool spatialQueries;            // SVCM_QUERY_ORDER=bucket restores round 1's order (A/B)
     bool legacyBuild;               // SVCM_LEGACY_BUILD=1: round 1's three-kernel scan + direct record scatter (A/B)
@@ -721,6 +729,17 @@ int enqueueMerge(svcm_renderer *r, const IterConst &ic, cudaStream_t ms)
     return launches + 1;
 }
 
+// Orders the main stream behind an iteration tail left on the camera stream (overlapIterations).
+int joinTail(svcm_renderer *r)
+{
+    if(r->tailPending)
+    {
+        SVCM_CUDA(r, cudaStreamWaitEvent(r->stream, r->evMergeDone, 0));
+        r->tailPending = false;
+    }
+    return SVCM_OK;
+}
+
 // One iteration: the kernel schedule that replaces the two serial per-pixel loops
 static double hostNowMs()
 {
@@ -739,6 +758,9 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     const bool timed = r->profile && r->ev != NULL;
     cudaEvent_t *ev = timed ? r->ev[slot] : NULL;
 
+    // the counters of two consecutive iterations are distinct blocks: the tail of the previous one may
+    // still be counting (overlapIterations)
+    r->counters = r->countersBase + size_t(r->ringHead & 1) * CNT_WORDS;
     SVCM_CUDA(r, cudaMemsetAsync(r->counters, 0, sizeof(unsigned long long) * CNT_WORDS, st));
     SVCM_CUDA(r, cudaMemsetAsync(r->queueCountsLight, 0, sizeof(uint32_t) * r->countsAlloc, st));
     SVCM_CUDA(r, cudaMemsetAsync(r->queueCountsCamera, 0, sizeof(uint32_t) * r->countsAlloc, st));
@@ -831,6 +853,8 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
         cudaStream_t sg = r->overlapGrid ? r->gridStream : st;      // same stream: strictly after the light pass, before the camera pass joins
         SVCM_CUDA(r, cudaEventRecord(r->evLightDone, st));
         SVCM_CUDA(r, cudaStreamWaitEvent(sg, r->evLightDone, 0));
+        // the previous iteration's merge still reads the grid this build overwrites
+        if(r->tailPending) SVCM_CUDA(r, cudaStreamWaitEvent(sg, r->evMergeDone, 0));
         if(timed) cudaEventRecord(ev[6], sg);
         MergeSet set;
         if(r->params.worldSize > 1)
@@ -895,9 +919,15 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     // neither vertex connection nor its visibility tests. With the passes overlapped it was enqueued on
     // the camera stream right behind the walk (`mergeForked` below) and runs concurrently with the
     // connection kernels of this stream; here the two meet again.
+    // With overlapIterations the merge is NOT joined here: the main stream goes on to the next
+    // iteration's light pass, the camera stream finishes this one (merge, then — once the main stream's
+    // part is through as well — the counter copy) and whoever needs the result joins (joinTail, the next
+    // grid build, the next camera walk by stream order).
+    bool leaveTail = false;
     if(r->useVM && !r->lightTraceOnly)
     {
-        if(mergeForked) SVCM_CUDA(r, cudaStreamWaitEvent(st, r->evMergeDone, 0));
+        if(mergeForked && r->overlapIterations) leaveTail = true;
+        else if(mergeForked) SVCM_CUDA(r, cudaStreamWaitEvent(st, r->evMergeDone, 0));
         else
         {
             SVCM_CUDA(r, cudaStreamWaitEvent(st, r->evGridDone, 0));
@@ -908,10 +938,22 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     }
     else if(r->useVM) SVCM_CUDA(r, cudaStreamWaitEvent(st, r->evGridDone, 0));
     if(timed && !(r->useVM && !r->lightTraceOnly)) { cudaEventRecord(ev[9], st); cudaEventRecord(ev[10], st); }
-    if(timed) cudaEventRecord(ev[5], st);
+    cudaStream_t last = st;
+    if(leaveTail)
+    {
+        last = r->cameraStream;
+        // the grid build read the light vertices the next light pass overwrites: it is long done when the
+        // camera walk is, but nothing else orders the main stream behind it
+        SVCM_CUDA(r, cudaStreamWaitEvent(st, r->evGridDone, 0));
+        SVCM_CUDA(r, cudaEventRecord(r->evMainDone, st));
+        SVCM_CUDA(r, cudaStreamWaitEvent(last, r->evMainDone, 0));
+    }
+    if(timed) cudaEventRecord(ev[5], last);
 
     SVCM_CUDA(r, cudaMemcpyAsync(r->hostCounters + size_t(slot) * CNT_WORDS, r->counters,
-                                 sizeof(unsigned long long) * CNT_WORDS, cudaMemcpyDeviceToHost, st));
+                                 sizeof(unsigned long long) * CNT_WORDS, cudaMemcpyDeviceToHost, last));
+    if(leaveTail) SVCM_CUDA(r, cudaEventRecord(r->evMergeDone, last));
+    r->tailPending = leaveTail;
     SVCM_CUDA(r, cudaGetLastError());
     th[5] = hostNowMs();
     if(traceHost)
@@ -1011,7 +1053,8 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     memset(&r->shadow, 0, sizeof(r->shadow));
     memset(&r->pairs, 0, sizeof(r->pairs));
     memset(&r->qsort, 0, sizeof(r->qsort)); r->sortQueries = getenv("SVCM_NO_QUERY_SORT") == NULL;
-    r->counters = NULL; r->hostCounters = NULL; r->accum = NULL;
+    r->counters = NULL; r->countersBase = NULL; r->hostCounters = NULL; r->accum = NULL;
+    r->tailPending = false; r->evMainDone = NULL;
     memset(&r->grid, 0, sizeof(r->grid)); r->gridCells = 0; r->gridCapacity = 0; r->bboxInit = NULL;
     r->comm = NULL; r->gatherBuf = NULL; r->gatherBytes = 0; r->gatherSlots = 0; r->gatherStride = 0;
     r->strideMaxLen = 0; r->lastMaxCount = 0; r->segCountDev = NULL;
@@ -1023,6 +1066,7 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     r->legacyBuild = getenv("SVCM_LEGACY_BUILD") && atoi(getenv("SVCM_LEGACY_BUILD")) != 0;
     r->overlapGrid = !(getenv("SVCM_NO_GRID_OVERLAP") && atoi(getenv("SVCM_NO_GRID_OVERLAP")) != 0);
     r->overlapMerge = !(getenv("SVCM_NO_MERGE_OVERLAP") && atoi(getenv("SVCM_NO_MERGE_OVERLAP")) != 0);
+    r->overlapIterations = !(getenv("SVCM_NO_ITERATION_OVERLAP") && atoi(getenv("SVCM_NO_ITERATION_OVERLAP")) != 0);
     r->spatialQueries = !(getenv("SVCM_QUERY_ORDER") && strcmp(getenv("SVCM_QUERY_ORDER"), "bucket") == 0);
     r->iterationsDone = 0; r->profile = false;
     r->mergeGroup = getenv("SVCM_MERGE_KERNEL") ? atoi(getenv("SVCM_MERGE_KERNEL")) : 1;
@@ -1092,7 +1136,8 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
                                params->algorithm != SVCM_ALG_LIGHT_TRACE;
     for(int i = 0; i < (bidirectional ? 4 : 2); i++) if((rc = allocQueue(r, r->queue[i], r->localPaths))) SVCM_CREATE_FAIL(rc);
     if((rc = devAlloc(r, &r->pathVertCount, r->localPaths))) SVCM_CREATE_FAIL(rc);
-    if((rc = devAlloc(r, &r->counters, CNT_WORDS))) SVCM_CREATE_FAIL(rc);
+    if((rc = devAlloc(r, &r->countersBase, 2 * CNT_WORDS))) SVCM_CREATE_FAIL(rc);
+    r->counters = r->countersBase;
     if((rc = devAlloc(r, &r->accum, size_t(r->paths) * 3))) SVCM_CREATE_FAIL(rc);
     if((rc = devAlloc(r, &r->grid.bboxBits, 6))) SVCM_CREATE_FAIL(rc);
     if((rc = devAlloc(r, &r->bboxInit, 6))) SVCM_CREATE_FAIL(rc);
@@ -1105,6 +1150,7 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     SVCM_TRY(cudaEventCreateWithFlags(&r->evIterStart, cudaEventDisableTiming));
     SVCM_TRY(cudaEventCreateWithFlags(&r->evCameraDone, cudaEventDisableTiming));
     SVCM_TRY(cudaEventCreateWithFlags(&r->evMergeDone, cudaEventDisableTiming));
+    SVCM_TRY(cudaEventCreateWithFlags(&r->evMainDone, cudaEventDisableTiming));
     SVCM_TRY(cudaMallocHost((void**)&r->hostCounters, sizeof(unsigned long long) * CNT_WORDS * SVCM_PROFILE_RING));
     SVCM_TRY(cudaMallocHost((void**)&r->hostCounts64, sizeof(unsigned long long) * 8 * SVCM_PROFILE_RING));
     memset(r->hostCounters, 0, sizeof(unsigned long long) * CNT_WORDS * SVCM_PROFILE_RING);
@@ -1127,17 +1173,18 @@ void svcm_destroy(svcm_renderer *r)
 {
     if(!r) return;
     cudaSetDevice(r->device);
-    if(r->stream) cudaStreamSynchronize(r->stream);
+    if(r->stream) { joinTail(r); cudaStreamSynchronize(r->stream); }
     if(r->comm && ncclApi()->lib) ncclApi()->CommDestroy(r->comm);
     for(int i = 0; i < 4; i++) freeQueue(r->queue[i]);
     if(r->cameraStream) { cudaStreamSynchronize(r->cameraStream); cudaStreamDestroy(r->cameraStream); }
     if(r->evIterStart) cudaEventDestroy(r->evIterStart);
     if(r->evCameraDone) cudaEventDestroy(r->evCameraDone);
     if(r->evMergeDone) cudaEventDestroy(r->evMergeDone);
+    if(r->evMainDone) cudaEventDestroy(r->evMainDone);
     devFree(r->queueCountsLight); devFree(r->queueCountsCamera);
     devFree(r->shadow.r0); devFree(r->shadow.r1); devFree(r->shadow.r2); devFree(r->shadow.counts);
     freeVerts(r); freeQueries(r); freeGridSorted(r);
-    devFree(r->pathVertCount); devFree(r->counters); devFree(r->accum); devFree(r->image8);
+    devFree(r->pathVertCount); devFree(r->countersBase); r->counters = NULL; devFree(r->accum); devFree(r->image8);
     r->geometry.release();
     devFree(r->grid.cellCount); devFree(r->grid.blockSums); devFree(r->grid.bboxBits);
     devFree(r->grid.cellEnd); devFree(r->grid.dims); devFree(r->grid.refCount);
@@ -1163,6 +1210,7 @@ void svcm_destroy(svcm_renderer *r)
 int svcm_set_option(svcm_renderer *r, int32_t option, int64_t value)
 {
     if(!r) return SVCM_E_INVALID;
+    if(r->tailPending) { cudaSetDevice(r->device); const int rc = joinTail(r); if(rc) return rc; }
     switch(option)
     {
     case SVCM_OPT_PROFILE:
@@ -1189,8 +1237,9 @@ int svcm_set_option(svcm_renderer *r, int32_t option, int64_t value)
     case SVCM_OPT_REF_CANDIDATES:
         r->refCandidates = value != 0; return SVCM_OK;
     case SVCM_OPT_OVERLAP:
-        if(value < 0 || value > 7) return fail(r, SVCM_E_INVALID, "overlap mask must be 0..7");
+        if(value < 0 || value > 15) return fail(r, SVCM_E_INVALID, "overlap mask must be 0..15");
         r->overlapPasses = (value & 1) != 0; r->overlapGrid = (value & 2) != 0; r->overlapMerge = (value & 4) != 0;
+        r->overlapIterations = (value & 8) != 0;
         return SVCM_OK;
     default: return fail(r, SVCM_E_INVALID, "unknown option %d", option);
     }
@@ -1215,6 +1264,7 @@ int svcm_run_iterations(svcm_renderer *r, int32_t firstIteration, int32_t count,
         // wait and look at them, so that no iteration's overflow report is ever overwritten unseen
         if(r->ringHead - r->ringTail >= SVCM_PROFILE_RING - 1)
         {
+            if((rc = joinTail(r))) return rc;
             SVCM_CUDA(r, cudaStreamSynchronize(r->stream));
             if((rc = finishStats(r))) return rc;
             r->ringTail = r->ringHead - 1;       // keep the last iteration's record for svcm_get_profile
@@ -1228,6 +1278,7 @@ int svcm_synchronize(svcm_renderer *r)
 {
     if(!r) return SVCM_E_INVALID;
     SVCM_CUDA(r, cudaSetDevice(r->device));
+    { const int rc = joinTail(r); if(rc) return rc; }
     SVCM_CUDA(r, cudaStreamSynchronize(r->stream));
     return finishStats(r);
 }
@@ -1238,6 +1289,7 @@ int svcm_download_accum(svcm_renderer *r, float *rgb, int32_t *iterationsDone)
     SVCM_CUDA(r, cudaSetDevice(r->device));
     // after svcm_reduce_accum the root serves the sum over ranks (until more iterations are rendered)
     const float *src = (r->reducedValid && r->accumReduced) ? r->accumReduced : r->accum;
+    { const int rc = joinTail(r); if(rc) return rc; }
     SVCM_CUDA(r, cudaMemcpyAsync(rgb, src, sizeof(float) * 3 * size_t(r->paths), cudaMemcpyDeviceToHost, r->stream));
     SVCM_CUDA(r, cudaStreamSynchronize(r->stream));
     if(iterationsDone) *iterationsDone = r->iterationsDone;
@@ -1287,6 +1339,7 @@ int svcm_download_image(svcm_renderer *r, int32_t format, float gamma, uint8_t *
     if(format == SVCM_IMAGE_BMP24 && !(gamma > 0.f)) return fail(r, SVCM_E_INVALID, "gamma must be positive");
     SVCM_CUDA(r, cudaSetDevice(r->device));
     if(!r->image8) { const int rc = devAlloc(r, &r->image8, size_t(r->paths) * 4u); if(rc) return rc; }
+    { const int rc = joinTail(r); if(rc) return rc; }
     launchImageConvert(r->accum, r->resX, r->resY, r->iterationsDone, format, gamma, r->image8, r->stream);
     SVCM_CUDA(r, cudaGetLastError());
     SVCM_CUDA(r, cudaMemcpyAsync(out, r->image8, size_t(svcm_image_bytes(format, r->resX, r->resY)), cudaMemcpyDeviceToHost, r->stream));
@@ -1322,6 +1375,7 @@ int svcm_clear_accum(svcm_renderer *r)
 {
     if(!r) return SVCM_E_INVALID;
     SVCM_CUDA(r, cudaSetDevice(r->device));
+    { const int rc = joinTail(r); if(rc) return rc; }
     SVCM_CUDA(r, cudaMemsetAsync(r->accum, 0, sizeof(float) * 3 * size_t(r->paths), r->stream));
     r->iterationsDone = 0; r->reducedValid = false;
     return SVCM_OK;
@@ -1397,6 +1451,7 @@ int svcm_event_record(svcm_renderer *r, int32_t slot)
 {
     if(!r || slot < 0 || slot >= SVCM_NUM_USER_EVENTS) return r ? fail(r, SVCM_E_INVALID, "bad event slot") : SVCM_E_INVALID;
     SVCM_CUDA(r, cudaSetDevice(r->device));
+    { const int rc = joinTail(r); if(rc) return rc; }     // an event marks the end of everything enqueued so far
     SVCM_CUDA(r, cudaEventRecord(r->userEv[slot], r->stream));
     return SVCM_OK;
 }
@@ -1474,6 +1529,7 @@ int svcm_reduce_accum(svcm_renderer *r, int32_t root)
         const int rc = devAlloc(r, &r->accumReduced, size_t(r->paths) * 3);
         if(rc) return rc;
     }
+    { const int rcj = joinTail(r); if(rcj) return rcj; }
     const int rc = ncclCheck(r, ncclApi()->Reduce(r->accum, r->params.rank == root ? r->accumReduced : r->accum,
                                                   size_t(r->paths) * 3, NCCL_FLOAT32, NCCL_SUM, root, r->comm, r->stream),
                              "ncclReduce(accum)");

@@ -175,6 +175,40 @@ def test_accumulate_clear_and_linearity():
     r.close(); fb.close()
 
 
+@pytest.mark.parametrize("scene_id,alg,w", [(1, "vcm", 160), (3, "bpm", 128), (0, "ppm", 96), (0, "bpt", 96), (1, "lt", 96)])
+def test_stream_schedules_agree(scene_id, alg, w):
+    """SVCM_OPT_OVERLAP: every schedule of the stages — one after the other (0), the three overlaps
+    inside an iteration (7), the merge of an iteration left running under the next iteration's light
+    pass (15, the default), iterations enqueued in one call, one call each, or with an entry point that
+    joins in between — renders the same image and reports the same per-iteration counters."""
+    scene = sv.Scene.cornell_box(scene_id, w, w)
+    results = []
+    for mask, mode in [(0, "batch"), (7, "batch"), (15, "batch"), (15, "single"), (15, "joined"), (8, "batch")]:
+        r = sv.VertexCM(scene, alg); r.max_path_length = 8
+        r.set_option(abi.OPT_OVERLAP, mask)
+        r.set_option(abi.OPT_PROFILE, 1)
+        if mode == "batch":
+            r.run_iterations(0, 7)
+        else:
+            for it in range(7):
+                r.run_iterations(it, 1)
+                if mode == "joined":
+                    if it % 2: r.event_record(0)
+                    else: r.synchronize()
+        prof = r.profile()
+        img, n = r.accum()
+        st = r.stats()
+        r.close()
+        assert n == 7 and prof["iterations"] == 7
+        results.append((img, prof, st))
+    img0, prof0, st0 = results[0]
+    for img, prof, st in results[1:]:
+        assert rel_l2(img, img0) < 1e-5
+        for key in ("lightVertices", "mergeQueries", "mergeCandidates", "mergeAccepted", "lightRays", "cameraRays", "shadowRays"):
+            assert prof[key] == prof0[key], key
+            if key in st: assert st[key] == st0[key], key
+
+
 def test_merge_group_sizes_agree():
     scene = sv.Scene.cornell_box(3, 128, 128)
     imgs = []
