@@ -478,17 +478,22 @@ def run_gpu_arm(args):
              "shadow_rays_per_iteration": rays["shadowRays"],
              "grays_per_s": (rays["lightRays"] + rays["cameraRays"] + rays["shadowRays"]) / trace_s / 1e9 if trace_s > 0 else None,
              "ms_light_plus_camera": trace_s * 1e3,
-             "ms_critical_path_in_schedule": st_ms["msLightTrace"] + st_ms["msCameraTrace"],
-             "note": "light + camera passes (closest-hit rays of both walks, deferred any-hit segments, vertex "
-                     "connection) timed one after the other; instruction-bound on 22 primitives in the constant bank, "
-                     "reported as rays/s, not against the HBM roofline (SURVEY 8d)"}
+             "ms_start_to_camera_pass_done_in_schedule": st_ms["msLightTrace"] + st_ms["msCameraTrace"],
+             "note": "ms_light_plus_camera: light + camera passes (closest-hit rays of both walks, deferred any-hit "
+                     "segments, vertex connection) timed alone, one after the other (SVCM_OPT_OVERLAP = 0); "
+                     "instruction-bound on 22 primitives in the constant bank, reported as rays/s, not against the "
+                     "HBM roofline (SURVEY 8d). In the default schedule the two walks run concurrently with each "
+                     "other and the light pass shares the SMs with the previous iteration's merge: "
+                     "ms_start_to_camera_pass_done_in_schedule is the wall time from the first kernel of an "
+                     "iteration to the end of its vertex-connection visibility tests under that sharing"}
     roofline = {"kernel": "merge stage: query sort + merge kernel (HashGrid::Process + RangeQuery::Process)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_source,
                 "peak_source": peak_kind, "ms_per_launch": merge_ms, "queries": nq, "candidates": ncand,
                 "accepted": nacc, "algorithmic_bytes_per_launch": merge_algorithmic_bytes(nq, ncand, nacc),
                 "timed": "alone: %d iterations of the same window with SVCM_OPT_OVERLAP = 0 (no other kernel on the "
-                         "device); in the default schedule the stage runs concurrently with vertex connection" % n,
+                         "device); in the default schedule (SVCM_OPT_OVERLAP = 15) the stage runs concurrently with "
+                         "vertex connection and with the next iteration's light pass" % n,
                 "stage_ms_per_iteration": st_ms,
                 "stage_ms_per_iteration_alone": iso_ms,
                 "grid_build": {"algorithmic_bytes": build_bytes, "ms": iso_ms["msGridBuild"],

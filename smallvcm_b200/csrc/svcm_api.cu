@@ -158,6 +158,9 @@ struct svcm_renderer
     bool tailPending;
     cudaEvent_t evMainDone;
     unsigned long long *countersBase;   // two blocks of CNT_WORDS; `counters` points at the current iteration's
+    int32_t *bboxBlocks;                // two blocks of 6 words; grid.bboxBits points at the current iteration's (the
+                                        // pending merge still reads the previous one while the all-gather headers of
+                                        // the next are unpacked)
     bool overlapGrid;               // SVCM_NO_GRID_OVERLAP=1: grid build on the main stream (isolated stage times)
     bool spatialQueries;            // SVCM_QUERY_ORDER=bucket restores round 1's order (A/B)
     bool legacyBuild;               // SVCM_LEGACY_BUILD=1: round 1's three-kernel scan + direct record scatter (A/B)
@@ -761,6 +764,7 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     // the counters of two consecutive iterations are distinct blocks: the tail of the previous one may
     // still be counting (overlapIterations)
     r->counters = r->countersBase + size_t(r->ringHead & 1) * CNT_WORDS;
+    r->grid.bboxBits = r->bboxBlocks + size_t(r->ringHead & 1) * 8;
     SVCM_CUDA(r, cudaMemsetAsync(r->counters, 0, sizeof(unsigned long long) * CNT_WORDS, st));
     SVCM_CUDA(r, cudaMemsetAsync(r->queueCountsLight, 0, sizeof(uint32_t) * r->countsAlloc, st));
     SVCM_CUDA(r, cudaMemsetAsync(r->queueCountsCamera, 0, sizeof(uint32_t) * r->countsAlloc, st));
@@ -853,8 +857,6 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
         cudaStream_t sg = r->overlapGrid ? r->gridStream : st;      // same stream: strictly after the light pass, before the camera pass joins
         SVCM_CUDA(r, cudaEventRecord(r->evLightDone, st));
         SVCM_CUDA(r, cudaStreamWaitEvent(sg, r->evLightDone, 0));
-        // the previous iteration's merge still reads the grid this build overwrites
-        if(r->tailPending) SVCM_CUDA(r, cudaStreamWaitEvent(sg, r->evMergeDone, 0));
         if(timed) cudaEventRecord(ev[6], sg);
         MergeSet set;
         if(r->params.worldSize > 1)
@@ -873,6 +875,9 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
             set.segStride = r->verts.capacity; set.numSegs = 1;
         }
         if(timed) cudaEventRecord(ev[7], sg);
+        // the previous iteration's merge still reads the grid this build overwrites (the all-gather
+        // above touches nothing of it: the bounding box lives in the other block)
+        if(r->tailPending) SVCM_CUDA(r, cudaStreamWaitEvent(sg, r->evMergeDone, 0));
         if(r->cellLayout) launches += launchCellGridBuild(ic, set, r->grid, r->scanGenGrid, r->refCandidates, sg);
         else launches += launchGridBuild(ic, set, r->grid, r->legacyBuild ? NULL : &r->scanGenGrid, sg);
         if(timed) cudaEventRecord(ev[8], sg);
@@ -1053,6 +1058,7 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     memset(&r->shadow, 0, sizeof(r->shadow));
     memset(&r->pairs, 0, sizeof(r->pairs));
     memset(&r->qsort, 0, sizeof(r->qsort)); r->sortQueries = getenv("SVCM_NO_QUERY_SORT") == NULL;
+    r->bboxBlocks = NULL;
     r->counters = NULL; r->countersBase = NULL; r->hostCounters = NULL; r->accum = NULL;
     r->tailPending = false; r->evMainDone = NULL;
     memset(&r->grid, 0, sizeof(r->grid)); r->gridCells = 0; r->gridCapacity = 0; r->bboxInit = NULL;
@@ -1139,7 +1145,8 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     if((rc = devAlloc(r, &r->countersBase, 2 * CNT_WORDS))) SVCM_CREATE_FAIL(rc);
     r->counters = r->countersBase;
     if((rc = devAlloc(r, &r->accum, size_t(r->paths) * 3))) SVCM_CREATE_FAIL(rc);
-    if((rc = devAlloc(r, &r->grid.bboxBits, 6))) SVCM_CREATE_FAIL(rc);
+    if((rc = devAlloc(r, &r->bboxBlocks, 16))) SVCM_CREATE_FAIL(rc);
+    r->grid.bboxBits = r->bboxBlocks;
     if((rc = devAlloc(r, &r->bboxInit, 6))) SVCM_CREATE_FAIL(rc);
     if((rc = devAlloc(r, &r->devCounts64, 8))) SVCM_CREATE_FAIL(rc);
     if((rc = devAlloc(r, &r->segCountDev, 8))) SVCM_CREATE_FAIL(rc);
@@ -1158,7 +1165,8 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     const int32_t init[6] = { floatToOrdered(1e36f), floatToOrdered(1e36f), floatToOrdered(1e36f),
                               floatToOrdered(-1e36f), floatToOrdered(-1e36f), floatToOrdered(-1e36f) };
     SVCM_TRY(cudaMemcpy(r->bboxInit, init, sizeof(init), cudaMemcpyHostToDevice));
-    SVCM_TRY(cudaMemcpy(r->grid.bboxBits, init, sizeof(init), cudaMemcpyHostToDevice));
+    SVCM_TRY(cudaMemcpy(r->bboxBlocks, init, sizeof(init), cudaMemcpyHostToDevice));
+    SVCM_TRY(cudaMemcpy(r->bboxBlocks + 8, init, sizeof(init), cudaMemcpyHostToDevice));
     r->grid.bboxInit = r->bboxInit;
     SVCM_TRY(cudaMemset(r->accum, 0, sizeof(float) * 3 * size_t(r->paths)));
     SVCM_TRY(cudaMemset(r->devCounts64, 0, sizeof(unsigned long long) * 8));
@@ -1186,7 +1194,7 @@ void svcm_destroy(svcm_renderer *r)
     freeVerts(r); freeQueries(r); freeGridSorted(r);
     devFree(r->pathVertCount); devFree(r->countersBase); r->counters = NULL; devFree(r->accum); devFree(r->image8);
     r->geometry.release();
-    devFree(r->grid.cellCount); devFree(r->grid.blockSums); devFree(r->grid.bboxBits);
+    devFree(r->grid.cellCount); devFree(r->grid.blockSums); devFree(r->bboxBlocks); r->grid.bboxBits = NULL;
     devFree(r->grid.cellEnd); devFree(r->grid.dims); devFree(r->grid.refCount);
     devFree(r->grid.scanState); devFree(r->grid.scanCounter);
     devFree(r->qsort.cellCount); devFree(r->qsort.blockSums);
