@@ -149,7 +149,18 @@ struct svcm_renderer
     cudaEvent_t  evIterStart, evCameraDone;
     bool overlapPasses;             // SVCM_NO_PASS_OVERLAP=1 serialises them again (A/B)
     bool overlapMerge;              // SVCM_NO_MERGE_OVERLAP=1: merge on the main stream behind the connection kernels
-    cudaEvent_t evMergeDone;
+    // merge stage: its own stream behind the camera walk and the grid build. evMergeDone[b]: the merge
+    // that read camera-vertex buffer b (and counter / bbox block b) is through, its counters are copied.
+    cudaStream_t mergeStream;
+    cudaEvent_t evMergeDone[2];
+    int  lastMergeBlock;            // which of the two the most recent merge records
+    // Camera vertices and the scratch of their sort exist twice when memory allows (queryBuffers == 2):
+    // the camera walk of iteration i+1 then writes one set while the merge of iteration i still reads
+    // the other. `queries` / `qsort` / `scanGenQuery` are the current iteration's; the *Alt members
+    // hold the other set and the two are swapped at the start of every iteration.
+    QueryStore queriesAlt;
+    QuerySortBuffers qsortAlt;
+    int  queryBuffers;
     // ... and the merge of one iteration is left running while the next iteration's light pass starts
     // (nothing it reads is written before the next grid build / camera walk, which wait for it).
     // tailPending: an iteration's merge + counter copy are still only ordered on the camera stream;
@@ -171,7 +182,7 @@ struct svcm_renderer
     bool cellLayout;                // SVCM_OPT_GRID_LAYOUT
     int  mergeVariant;              // SVCM_OPT_MERGE_VARIANT
     bool refCandidates;             // SVCM_OPT_REF_CANDIDATES
-    ScanGen scanGenGrid, scanGenQuery;
+    ScanGen scanGenGrid, scanGenQuery, scanGenQueryAlt;
     bool profile;
     cudaEvent_t (*ev)[11];         // [SVCM_PROFILE_RING][11], created when profiling is enabled:
                                    // 0 start, 1 light pass done, 4 camera pass done, 5 merge done (main
@@ -362,7 +373,10 @@ void freeQueries(svcm_renderer *r)
     devFree(r->queries.q0); devFree(r->queries.q1); devFree(r->queries.q2); devFree(r->queries.q3);
     devFree(r->queries.q4); devFree(r->pairs.pairs);
     devFree(r->qsort.key); devFree(r->qsort.order);
-    r->queries.capacity = 0; r->pairs.capacity = 0; r->pairsSizedFor = 0;
+    devFree(r->queriesAlt.q0); devFree(r->queriesAlt.q1); devFree(r->queriesAlt.q2); devFree(r->queriesAlt.q3);
+    devFree(r->queriesAlt.q4); devFree(r->qsortAlt.key); devFree(r->qsortAlt.order);
+    r->queries.capacity = 0; r->queriesAlt.capacity = 0; r->pairs.capacity = 0; r->pairsSizedFor = 0;
+    r->queryBuffers = 1;
 }
 void freeGridSorted(svcm_renderer *r)
 {
@@ -521,17 +535,26 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
             uint64_t cap = std::min<uint64_t>(worst, uint64_t(double(freeB) * 0.4) / perVertex);
             cap = std::min<uint64_t>(cap, 0xFFFFFF00u);
             cap = std::max<uint64_t>(cap, old);
-            if((rc = devAlloc(r, &r->queries.q0, cap))) return rc;
-            if((rc = devAlloc(r, &r->queries.q1, cap))) return rc;
-            if((rc = devAlloc(r, &r->queries.q2, cap))) return rc;
-            if((rc = devAlloc(r, &r->queries.q3, cap))) return rc;
-            if(r->useVC) if((rc = devAlloc(r, &r->queries.q4, cap))) return rc;
-            if(r->useVM)
+            // a second set for the iteration overlap, only when the worst case fits twice with room to spare
+            const bool twice = r->useVM && cap == worst && 2u * worst * (80u + 8u) < uint64_t(double(freeB) * 0.25) &&
+                               !(getenv("SVCM_SINGLE_QUERY_BUFFER") && atoi(getenv("SVCM_SINGLE_QUERY_BUFFER")) != 0);
+            for(int b = 0; b < (twice ? 2 : 1); b++)
             {
-                if((rc = devAlloc(r, &r->qsort.key, cap))) return rc;
-                if((rc = devAlloc(r, &r->qsort.order, cap))) return rc;
+                QueryStore &q = b ? r->queriesAlt : r->queries;
+                QuerySortBuffers &qs = b ? r->qsortAlt : r->qsort;
+                if((rc = devAlloc(r, &q.q0, cap))) return rc;
+                if((rc = devAlloc(r, &q.q1, cap))) return rc;
+                if((rc = devAlloc(r, &q.q2, cap))) return rc;
+                if((rc = devAlloc(r, &q.q3, cap))) return rc;
+                if(r->useVC) if((rc = devAlloc(r, &q.q4, cap))) return rc;
+                if(r->useVM)
+                {
+                    if((rc = devAlloc(r, &qs.key, cap))) return rc;
+                    if((rc = devAlloc(r, &qs.order, cap))) return rc;
+                }
+                q.capacity = uint32_t(cap);
             }
-            r->queries.capacity = uint32_t(cap);
+            r->queryBuffers = twice ? 2 : 1;
         }
     }
     // (camera vertex, light vertex) pairs: a camera vertex of length c pairs with at most
@@ -575,10 +598,15 @@ int ensureCapacity(svcm_renderer *r, uint32_t maxLen)
     if(r->useVM)
     {
         if((rc = ensureGridCells(r, r->paths))) return rc;
-        if(!r->qsort.cellCount)
+        for(int b = 0; b < r->queryBuffers; b++)
         {
-            if((rc = devAlloc(r, &r->qsort.cellCount, size_t(r->paths) + 1))) return rc;
-            if((rc = devAlloc(r, &r->qsort.blockSums, (size_t(r->paths) + 1) / 2048 + 2))) return rc;
+            QuerySortBuffers &qs = b ? r->qsortAlt : r->qsort;
+            if(b && (rc = allocCellTables(r, r->grid, &qs, r->paths))) return rc;
+            if(!qs.cellCount)
+            {
+                if((rc = devAlloc(r, &qs.cellCount, size_t(r->paths) + 1))) return rc;
+                if((rc = devAlloc(r, &qs.blockSums, (size_t(r->paths) + 1) / 2048 + 2))) return rc;
+            }
         }
     }
     return SVCM_OK;
@@ -737,7 +765,8 @@ int joinTail(svcm_renderer *r)
 {
     if(r->tailPending)
     {
-        SVCM_CUDA(r, cudaStreamWaitEvent(r->stream, r->evMergeDone, 0));
+        // the merge stream runs in order: the most recent merge is the last to finish
+        SVCM_CUDA(r, cudaStreamWaitEvent(r->stream, r->evMergeDone[r->lastMergeBlock], 0));
         r->tailPending = false;
     }
     return SVCM_OK;
@@ -763,8 +792,16 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
 
     // the counters of two consecutive iterations are distinct blocks: the tail of the previous one may
     // still be counting (overlapIterations)
-    r->counters = r->countersBase + size_t(r->ringHead & 1) * CNT_WORDS;
-    r->grid.bboxBits = r->bboxBlocks + size_t(r->ringHead & 1) * 8;
+    const int blk = int(r->ringHead & 1);
+    r->counters = r->countersBase + size_t(blk) * CNT_WORDS;
+    r->grid.bboxBits = r->bboxBlocks + size_t(blk) * 8;
+    if(r->queryBuffers == 2)
+    {
+        // this iteration's camera vertices go to the set the merge of TWO iterations ago read (it also
+        // counted into this counter block): wait for it, whatever else is still pending
+        if(r->tailPending) SVCM_CUDA(r, cudaStreamWaitEvent(st, r->evMergeDone[blk], 0));
+        std::swap(r->queries, r->queriesAlt); std::swap(r->qsort, r->qsortAlt); std::swap(r->scanGenQuery, r->scanGenQueryAlt);
+    }
     SVCM_CUDA(r, cudaMemsetAsync(r->counters, 0, sizeof(unsigned long long) * CNT_WORDS, st));
     SVCM_CUDA(r, cudaMemsetAsync(r->queueCountsLight, 0, sizeof(uint32_t) * r->countsAlloc, st));
     SVCM_CUDA(r, cudaMemsetAsync(r->queueCountsCamera, 0, sizeof(uint32_t) * r->countsAlloc, st));
@@ -826,6 +863,8 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     {
         SVCM_CUDA(r, cudaEventRecord(r->evIterStart, st));
         SVCM_CUDA(r, cudaStreamWaitEvent(r->cameraStream, r->evIterStart, 0));
+        // one set of camera vertices: the previous iteration's merge still reads what this walk overwrites
+        if(r->tailPending && r->queryBuffers != 2) SVCM_CUDA(r, cudaStreamWaitEvent(r->cameraStream, r->evMergeDone[blk ^ 1], 0));
         launches += enqueueCameraBounces(r, ic, a, maxLen, r->cameraStream, timed ? ev : NULL);
         SVCM_CUDA(r, cudaEventRecord(r->evCameraDone, r->cameraStream));
     }
@@ -877,7 +916,7 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
         if(timed) cudaEventRecord(ev[7], sg);
         // the previous iteration's merge still reads the grid this build overwrites (the all-gather
         // above touches nothing of it: the bounding box lives in the other block)
-        if(r->tailPending) SVCM_CUDA(r, cudaStreamWaitEvent(sg, r->evMergeDone, 0));
+        if(r->tailPending) SVCM_CUDA(r, cudaStreamWaitEvent(sg, r->evMergeDone[blk ^ 1], 0));
         if(r->cellLayout) launches += launchCellGridBuild(ic, set, r->grid, r->scanGenGrid, r->refCandidates, sg);
         else launches += launchGridBuild(ic, set, r->grid, r->legacyBuild ? NULL : &r->scanGenGrid, sg);
         if(timed) cudaEventRecord(ev[8], sg);
@@ -888,12 +927,14 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     bool mergeForked = false;
     if(r->useVM && !r->lightTraceOnly && r->overlapPasses && r->overlapMerge)
     {
-        cudaStream_t cs = r->cameraStream;
-        SVCM_CUDA(r, cudaStreamWaitEvent(cs, r->evGridDone, 0));
-        if(timed) cudaEventRecord(ev[9], cs);
-        launches += enqueueMerge(r, ic, cs);
-        if(timed) cudaEventRecord(ev[10], cs);
-        SVCM_CUDA(r, cudaEventRecord(r->evMergeDone, cs));
+        cudaStream_t ms = r->mergeStream;
+        SVCM_CUDA(r, cudaStreamWaitEvent(ms, r->evCameraDone, 0));
+        SVCM_CUDA(r, cudaStreamWaitEvent(ms, r->evGridDone, 0));
+        if(timed) cudaEventRecord(ev[9], ms);
+        launches += enqueueMerge(r, ic, ms);
+        if(timed) cudaEventRecord(ev[10], ms);
+        SVCM_CUDA(r, cudaEventRecord(r->evMergeDone[blk], ms));
+        r->lastMergeBlock = blk;
         mergeForked = true;
     }
     th[3] = hostNowMs();
@@ -932,7 +973,7 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     if(r->useVM && !r->lightTraceOnly)
     {
         if(mergeForked && r->overlapIterations) leaveTail = true;
-        else if(mergeForked) SVCM_CUDA(r, cudaStreamWaitEvent(st, r->evMergeDone, 0));
+        else if(mergeForked) SVCM_CUDA(r, cudaStreamWaitEvent(st, r->evMergeDone[blk], 0));
         else
         {
             SVCM_CUDA(r, cudaStreamWaitEvent(st, r->evGridDone, 0));
@@ -946,7 +987,7 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
     cudaStream_t last = st;
     if(leaveTail)
     {
-        last = r->cameraStream;
+        last = r->mergeStream;
         // the grid build read the light vertices the next light pass overwrites: it is long done when the
         // camera walk is, but nothing else orders the main stream behind it
         SVCM_CUDA(r, cudaStreamWaitEvent(st, r->evGridDone, 0));
@@ -957,7 +998,7 @@ int runOneIteration(svcm_renderer *r, int iteration, uint32_t minLen, uint32_t m
 
     SVCM_CUDA(r, cudaMemcpyAsync(r->hostCounters + size_t(slot) * CNT_WORDS, r->counters,
                                  sizeof(unsigned long long) * CNT_WORDS, cudaMemcpyDeviceToHost, last));
-    if(leaveTail) SVCM_CUDA(r, cudaEventRecord(r->evMergeDone, last));
+    if(leaveTail) SVCM_CUDA(r, cudaEventRecord(r->evMergeDone[blk], last));
     r->tailPending = leaveTail;
     SVCM_CUDA(r, cudaGetLastError());
     th[5] = hostNowMs();
@@ -1054,7 +1095,9 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     memset(r->queue, 0, sizeof(r->queue));
     r->queueCountsLight = r->queueCountsCamera = NULL; r->countsAlloc = 0;
     memset(&r->verts, 0, sizeof(r->verts)); r->vertSlots = 0; r->pathVertCount = NULL;
-    memset(&r->queries, 0, sizeof(r->queries));
+    memset(&r->queries, 0, sizeof(r->queries)); memset(&r->queriesAlt, 0, sizeof(r->queriesAlt));
+    memset(&r->qsortAlt, 0, sizeof(r->qsortAlt)); r->queryBuffers = 1; r->scanGenQueryAlt.value = 0u;
+    r->mergeStream = NULL; r->evMergeDone[0] = r->evMergeDone[1] = NULL; r->lastMergeBlock = 0;
     memset(&r->shadow, 0, sizeof(r->shadow));
     memset(&r->pairs, 0, sizeof(r->pairs));
     memset(&r->qsort, 0, sizeof(r->qsort)); r->sortQueries = getenv("SVCM_NO_QUERY_SORT") == NULL;
@@ -1067,7 +1110,7 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     r->devCounts64 = NULL; r->hostCounts64 = NULL;
     r->accumReduced = NULL; r->reducedValid = false;
     r->gridStream = NULL; r->evLightDone = NULL; r->evGridDone = NULL;
-    r->cameraStream = NULL; r->evIterStart = NULL; r->evCameraDone = NULL; r->evMergeDone = NULL;
+    r->cameraStream = NULL; r->evIterStart = NULL; r->evCameraDone = NULL;
     r->overlapPasses = !(getenv("SVCM_NO_PASS_OVERLAP") && atoi(getenv("SVCM_NO_PASS_OVERLAP")) != 0);
     r->legacyBuild = getenv("SVCM_LEGACY_BUILD") && atoi(getenv("SVCM_LEGACY_BUILD")) != 0;
     r->overlapGrid = !(getenv("SVCM_NO_GRID_OVERLAP") && atoi(getenv("SVCM_NO_GRID_OVERLAP")) != 0);
@@ -1156,7 +1199,9 @@ int svcm_create(const SvcmSceneDesc *scene, const SvcmParams *params, svcm_rende
     SVCM_TRY(cudaStreamCreateWithFlags(&r->cameraStream, cudaStreamNonBlocking));
     SVCM_TRY(cudaEventCreateWithFlags(&r->evIterStart, cudaEventDisableTiming));
     SVCM_TRY(cudaEventCreateWithFlags(&r->evCameraDone, cudaEventDisableTiming));
-    SVCM_TRY(cudaEventCreateWithFlags(&r->evMergeDone, cudaEventDisableTiming));
+    SVCM_TRY(cudaStreamCreateWithFlags(&r->mergeStream, cudaStreamNonBlocking));
+    SVCM_TRY(cudaEventCreateWithFlags(&r->evMergeDone[0], cudaEventDisableTiming));
+    SVCM_TRY(cudaEventCreateWithFlags(&r->evMergeDone[1], cudaEventDisableTiming));
     SVCM_TRY(cudaEventCreateWithFlags(&r->evMainDone, cudaEventDisableTiming));
     SVCM_TRY(cudaMallocHost((void**)&r->hostCounters, sizeof(unsigned long long) * CNT_WORDS * SVCM_PROFILE_RING));
     SVCM_TRY(cudaMallocHost((void**)&r->hostCounts64, sizeof(unsigned long long) * 8 * SVCM_PROFILE_RING));
@@ -1187,7 +1232,8 @@ void svcm_destroy(svcm_renderer *r)
     if(r->cameraStream) { cudaStreamSynchronize(r->cameraStream); cudaStreamDestroy(r->cameraStream); }
     if(r->evIterStart) cudaEventDestroy(r->evIterStart);
     if(r->evCameraDone) cudaEventDestroy(r->evCameraDone);
-    if(r->evMergeDone) cudaEventDestroy(r->evMergeDone);
+    if(r->mergeStream) { cudaStreamSynchronize(r->mergeStream); cudaStreamDestroy(r->mergeStream); }
+    for(int b = 0; b < 2; b++) if(r->evMergeDone[b]) cudaEventDestroy(r->evMergeDone[b]);
     if(r->evMainDone) cudaEventDestroy(r->evMainDone);
     devFree(r->queueCountsLight); devFree(r->queueCountsCamera);
     devFree(r->shadow.r0); devFree(r->shadow.r1); devFree(r->shadow.r2); devFree(r->shadow.counts);
@@ -1199,6 +1245,8 @@ void svcm_destroy(svcm_renderer *r)
     devFree(r->grid.scanState); devFree(r->grid.scanCounter);
     devFree(r->qsort.cellCount); devFree(r->qsort.blockSums);
     devFree(r->qsort.cellEnd); devFree(r->qsort.scanState); devFree(r->qsort.scanCounter);
+    devFree(r->qsortAlt.cellCount); devFree(r->qsortAlt.blockSums);
+    devFree(r->qsortAlt.cellEnd); devFree(r->qsortAlt.scanState); devFree(r->qsortAlt.scanCounter);
     devFree(r->bboxInit); devFree(r->devCounts64); devFree(r->segCountDev); devFree(r->accumReduced);
     if(r->gridStream) { cudaStreamSynchronize(r->gridStream); cudaStreamDestroy(r->gridStream); }
     if(r->evLightDone) cudaEventDestroy(r->evLightDone);

@@ -176,11 +176,15 @@ def test_accumulate_clear_and_linearity():
 
 
 @pytest.mark.parametrize("scene_id,alg,w", [(1, "vcm", 160), (3, "bpm", 128), (0, "ppm", 96), (0, "bpt", 96), (1, "lt", 96)])
-def test_stream_schedules_agree(scene_id, alg, w):
+@pytest.mark.parametrize("single_buffer", [0, 1])
+def test_stream_schedules_agree(scene_id, alg, w, single_buffer, monkeypatch):
     """SVCM_OPT_OVERLAP: every schedule of the stages — one after the other (0), the three overlaps
     inside an iteration (7), the merge of an iteration left running under the next iteration's light
     pass (15, the default), iterations enqueued in one call, one call each, or with an entry point that
     joins in between — renders the same image and reports the same per-iteration counters."""
+    # the camera vertices exist twice when memory allows (the next walk writes one set while the pending
+    # merge reads the other); SVCM_SINGLE_QUERY_BUFFER=1 is the memory-bounded arrangement
+    monkeypatch.setenv("SVCM_SINGLE_QUERY_BUFFER", str(single_buffer))
     scene = sv.Scene.cornell_box(scene_id, w, w)
     results = []
     for mask, mode in [(0, "batch"), (7, "batch"), (15, "batch"), (15, "single"), (15, "joined"), (8, "batch")]:
