@@ -12,6 +12,7 @@
 // vertex store, the grid build and the merge move real HBM traffic.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 #include "svcm_internal.h"
 #include "svcm_kutil.cuh"
 
@@ -1661,18 +1662,31 @@ int numSMs()
     return g_numSMs;
 }
 // persistent-style grid: a multiple of the SM count, capped by the work available
+// (blocksPerSM <= 0: one block per perBlock items, no grid-stride loop)
 uint32_t gridFor(uint64_t items, int perBlock, int blocksPerSM)
 {
     const uint64_t need = (items + uint64_t(perBlock) - 1) / uint64_t(perBlock);
-    const uint64_t cap = uint64_t(numSMs()) * uint64_t(blocksPerSM);
+    const uint64_t cap = blocksPerSM > 0 ? uint64_t(numSMs()) * uint64_t(blocksPerSM) : 0x7FFFFFFFull;
     return uint32_t(need < 1 ? 1 : (need < cap ? need : cap));
 }
+// blocks per SM of the hot kernels' grids; SVCM_GRID_<KERNEL>=n overrides the default (A/B)
+static int gridBlocksPerSM(const char *env, int fallback)
+{
+    const char *v = getenv(env);
+    return v ? atoi(v) : fallback;
+}
+#define SVCM_GRID_KNOB(name, env, fallback) static int name() { static const int v = gridBlocksPerSM(env, fallback); return v; }
+SVCM_GRID_KNOB(gridLight,   "SVCM_GRID_LIGHT",   16)     // 16 (or no cap) vs 8: light pass alone 0.761 -> 0.739 ms at 1024^2
+SVCM_GRID_KNOB(gridCamera,  "SVCM_GRID_CAMERA",  16)     // camera pass alone 1.324 -> 1.286 ms (profiles/r2_variants_grid_sizes.jsonl)
+SVCM_GRID_KNOB(gridConnect, "SVCM_GRID_CONNECT", 8)
+SVCM_GRID_KNOB(gridShadow,  "SVCM_GRID_SHADOW",  10)
+SVCM_GRID_KNOB(gridMerge,   "SVCM_GRID_MERGE",   4)
 
 void launchLightBounce(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t bounce,
                        uint32_t maxItems, cudaStream_t stream)
 {
-    if(sc.bvh) k_lightBounce<true><<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
-    else       k_lightBounce<false><<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
+    if(sc.bvh) k_lightBounce<true><<<gridFor(maxItems, SVCM_BLOCK, gridLight()), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
+    else       k_lightBounce<false><<<gridFor(maxItems, SVCM_BLOCK, gridLight()), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
 }
 
 void launchPathTraceBounce(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t bounce,
@@ -1692,8 +1706,8 @@ void launchEyeLight(const DevScene &sc, const IterConst &ic, const TraceArgs &ar
 void launchCameraBounce(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t bounce,
                         uint32_t maxItems, cudaStream_t stream)
 {
-    if(sc.bvh) k_cameraBounce<true><<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
-    else       k_cameraBounce<false><<<gridFor(maxItems, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
+    if(sc.bvh) k_cameraBounce<true><<<gridFor(maxItems, SVCM_BLOCK, gridCamera()), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
+    else       k_cameraBounce<false><<<gridFor(maxItems, SVCM_BLOCK, gridCamera()), SVCM_BLOCK, 0, stream>>>(sc, ic, args, bounce);
 }
 
 int launchQuerySort(const IterConst &ic, const QueryStore &queries, const unsigned long long *vertexCount,
@@ -1728,16 +1742,16 @@ int launchQuerySort(const IterConst &ic, const QueryStore &queries, const unsign
 void launchConnect(const DevScene &sc, const IterConst &ic, const TraceArgs &args, cudaStream_t stream)
 {
     k_makePairs<<<gridFor(args.queries.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(ic, args);
-    if(sc.bvh) k_connect<true><<<gridFor(args.pairs.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args);
-    else       k_connect<false><<<gridFor(args.pairs.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, ic, args);
+    if(sc.bvh) k_connect<true><<<gridFor(args.pairs.capacity, SVCM_BLOCK, gridConnect()), SVCM_BLOCK, 0, stream>>>(sc, ic, args);
+    else       k_connect<false><<<gridFor(args.pairs.capacity, SVCM_BLOCK, gridConnect()), SVCM_BLOCK, 0, stream>>>(sc, ic, args);
 }
 
 void launchShadow(const DevScene &sc, const IterConst &ic, const TraceArgs &args, uint32_t which,
                   cudaStream_t stream)
 {
     (void)ic;
-    if(sc.bvh) k_shadow<true><<<gridFor(args.shadow.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, args, which);
-    else       k_shadow<false><<<gridFor(args.shadow.capacity, SVCM_BLOCK, 8), SVCM_BLOCK, 0, stream>>>(sc, args, which);
+    if(sc.bvh) k_shadow<true><<<gridFor(args.shadow.capacity, SVCM_BLOCK, gridShadow()), SVCM_BLOCK, 0, stream>>>(sc, args, which);
+    else       k_shadow<false><<<gridFor(args.shadow.capacity, SVCM_BLOCK, gridShadow()), SVCM_BLOCK, 0, stream>>>(sc, args, which);
 }
 
 // HashGrid::Build in the reference's bucket order: bbox -> keys + histogram -> exclusive scan -> reorder.
@@ -1789,7 +1803,7 @@ void launchMerge(const DevScene &sc, const IterConst &ic, const QueryStore &quer
     if(maxQueries == 0) return;
     if(groupSize == 1)
     {
-        k_mergeLane<<<gridFor(maxQueries, SVCM_BLOCK, 4), SVCM_BLOCK, 0, stream>>>(
+        k_mergeLane<<<gridFor(maxQueries, SVCM_BLOCK, gridMerge()), SVCM_BLOCK, 0, stream>>>(
             sc, ic, queries, queryCount, hostQueryCount, grid, accum, contribOut, countsOut, counters);
         return;
     }
